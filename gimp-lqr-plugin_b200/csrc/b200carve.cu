@@ -1,0 +1,1007 @@
+// b200carve.cu -- host side of the CUDA seam-carving engine: device state per carver handle, kernel
+// sequencing of the per-seam loop, and the C ABI of include/b200carve.h.
+//
+// State model follows liblqr's: reference size (w_start,h_start), current size
+// (w,h), allocated size (w0,h0), level / max_level, the raw index table (x-th visible pixel of row y),
+// the visibility map vs, energy en, cumulative map m and parent map least -- all resident in HBM for the
+// life of the handle.  The host only sequences kernels; no pixel arithmetic happens on the CPU.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b200carve.h"
+#include "carver_kernels.cuh"
+
+using namespace b200c;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long> g_launches{0};
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    char buf[512];
+    if (e != cudaSuccess)
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else
+        snprintf(buf, sizeof buf, "%s", what);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                          \
+    do {                                                                                      \
+        cudaError_t e__ = (expr);                                                             \
+        if (e__ != cudaSuccess)                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? B200C_NOMEM : B200C_ERROR, #expr, e__); \
+    } while (0)
+#define B_TRY(expr)                      \
+    do {                                 \
+        int r__ = (expr);                \
+        if (r__ != B200C_OK) return r__; \
+    } while (0)
+
+// ---- optional per-stage timing (B200C_TIMING=1): CUDA events around every launch of a stage ----------
+struct StageStat {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    double ms = 0;
+    long launches = 0;
+};
+std::mutex g_stage_mu;
+std::map<std::string, StageStat> g_stages;
+bool g_timing = false;
+
+struct StageScope {
+    const char *name;
+    cudaStream_t s;
+    cudaEvent_t a = nullptr, b = nullptr;
+    StageScope(const char *n, cudaStream_t st, int launches = 1) : name(n), s(st)
+    {
+        g_launches += launches;
+        if (!g_timing) return;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s);
+    }
+    ~StageScope()
+    {
+        if (!g_timing) return;
+        cudaEventRecord(b, s);
+        std::lock_guard<std::mutex> lk(g_stage_mu);
+        auto &st = g_stages[name];
+        st.pending.emplace_back(a, b);
+        st.launches++;
+    }
+};
+
+void drain_stage(StageStat &st)
+{
+    for (auto &pr : st.pending) {
+        cudaEventSynchronize(pr.second);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) st.ms += ms;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    st.pending.clear();
+}
+
+int g_device_tls_default = 0;
+thread_local int g_device = -1;
+
+} // namespace
+
+struct B200Carver {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int w = 0, h = 0, w0 = 0, h0 = 0, w_start = 0, h_start = 0;
+    int level = 1, max_level = 1;
+    int channels = 0, alpha = -1, transposed = 0;
+    bool active = false, nrg_active = false, nrg_uptodate = false;
+    B200Carver *root = nullptr;
+    std::vector<B200Carver *> attached;
+
+    uint8_t *rgb = nullptr;
+    int *vs = nullptr; // owned by the root; attached carvers alias it
+    float *en = nullptr, *m = nullptr, *bias = nullptr, *rigmask = nullptr;
+    int *least = nullptr, *raw = nullptr;
+    int *vpath = nullptr, *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
+
+    float rigidity = 0.f;
+    int delta_x = 1;
+    std::vector<float> rigmap_h; // 2*delta_x+1, centred at [delta_x]
+    float *rigmap_d = nullptr;
+
+    int ef = 2, grad_kind = GRAD_XABS, read_kind = READ_BRIGHTNESS, nrg_radius = 1;
+    int leftright = 0;
+    unsigned lr_freq = 0;
+
+    uint8_t *host_out = nullptr; // pinned read-out staging
+    size_t host_out_cap = 0;
+};
+
+namespace {
+
+template <class T>
+int dalloc(B200Carver *c, T **p, size_t n, bool zero)
+{
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CU_TRY(cudaMallocAsync((void **) p, n * sizeof(T), c->stream));
+    if (zero) CU_TRY(cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream));
+    return B200C_OK;
+}
+
+template <class T>
+void dfree(B200Carver *c, T *&p)
+{
+    if (p) cudaFreeAsync((void *) p, c->stream);
+    p = nullptr;
+}
+
+int use_device(const B200Carver *c)
+{
+    CU_TRY(cudaSetDevice(c->device));
+    return B200C_OK;
+}
+
+int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(B200C_ERROR, what, e);
+    return B200C_OK;
+}
+
+DevP view(const B200Carver *c)
+{
+    DevP p;
+    p.w = c->w;
+    p.h = c->h;
+    p.w0 = c->w0;
+    p.h0 = c->h0;
+    p.w_start = c->w_start;
+    p.raw_stride = c->w_start;
+    p.channels = c->channels;
+    p.alpha = c->alpha;
+    p.level = c->level;
+    p.delta_x = c->delta_x;
+    p.leftright = c->leftright;
+    p.grad_kind = c->grad_kind;
+    p.read_kind = c->read_kind;
+    p.nrg_radius = c->nrg_radius;
+    p.use_rig = c->rigidity != 0.f;
+    p.rgb = c->rgb;
+    p.vs = c->vs;
+    p.raw = c->raw;
+    p.en = c->en;
+    p.m = c->m;
+    p.least = c->least;
+    p.bias = c->bias;
+    p.rigmask = c->rigmask;
+    p.rigmap = c->rigmap_d ? c->rigmap_d + c->delta_x : nullptr;
+    p.vpath = c->vpath;
+    p.vpath_x = c->vpath_x;
+    p.nrg_xmin = c->nrg_xmin;
+    p.nrg_xmax = c->nrg_xmax;
+    return p;
+}
+
+void set_width_one(B200Carver *c, int w1)
+{
+    c->w = w1;
+    c->level = c->w0 - w1 + 1;
+}
+
+void set_width_rec(B200Carver *c, int w1)
+{
+    set_width_one(c, w1);
+    for (B200Carver *a : c->attached) set_width_rec(a, w1);
+}
+
+void propagate_vs(B200Carver *c)
+{
+    for (B200Carver *a : c->attached) {
+        a->vs = c->vs;
+        propagate_vs(a);
+    }
+}
+
+int upload_rigmap(B200Carver *c)
+{
+    CU_TRY(cudaMemcpyAsync(c->rigmap_d, c->rigmap_h.data(), c->rigmap_h.size() * sizeof(float),
+                           cudaMemcpyHostToDevice, c->stream));
+    // the host vector may be rewritten (transpose) before the copy runs: pageable copies are staged
+    // synchronously by the runtime, so no extra sync is required here.
+    return B200C_OK;
+}
+
+int init_raw(B200Carver *c)
+{
+    dim3 grid((c->w_start + 255) / 256, c->h_start);
+    StageScope sc("init_raw", c->stream);
+    k_init_raw<<<grid, 256, 0, c->stream>>>(c->raw, c->w_start, c->h_start);
+    return check_launch("k_init_raw");
+}
+
+int init_energy_related(B200Carver *c)
+{
+    if (c->active || c->nrg_active) return fail(B200C_ERROR, "init_energy_related: already initialised");
+    const size_t n = (size_t) c->w * c->h;
+    B_TRY(dalloc(c, &c->en, n, true));
+    B_TRY(dalloc(c, &c->raw, (size_t) c->w_start * c->h_start, false));
+    B_TRY(init_raw(c));
+    c->nrg_active = true;
+    return B200C_OK;
+}
+
+// ---- A.3 / A.5 full passes ---------------------------------------------------------------------------
+int build_emap(B200Carver *c)
+{
+    if (c->nrg_uptodate) return B200C_OK;
+    dim3 grid((c->w + 255) / 256, c->h);
+    StageScope sc("energy_full", c->stream);
+    k_energy_full<<<grid, 256, 0, c->stream>>>(view(c));
+    B_TRY(check_launch("k_energy_full"));
+    c->nrg_uptodate = true;
+    return B200C_OK;
+}
+
+int build_mmap(B200Carver *c)
+{
+    StageScope sc("mmap_full", c->stream);
+    k_mmap_full<<<1, 1024, 0, c->stream>>>(view(c));
+    return check_launch("k_mmap_full");
+}
+
+// ---- A.9 inflate ----------------------------------------------------------------------------------------
+int inflate(B200Carver *c, int l)
+{
+    for (B200Carver *a : c->attached) B_TRY(inflate(a, l));
+
+    set_width_one(c, c->w0);
+    const int w1 = c->w0 + l - c->max_level + 1;
+    const size_t n1 = (size_t) w1 * c->h0;
+    uint8_t *new_rgb = nullptr;
+    int *new_vs = nullptr;
+    float *new_bias = nullptr, *new_rigmask = nullptr;
+    B_TRY(dalloc(c, &new_rgb, n1 * c->channels, true));
+    if (!c->root) B_TRY(dalloc(c, &new_vs, n1, true));
+    if (c->active) {
+        if (c->bias) B_TRY(dalloc(c, &new_bias, n1, true));
+        if (c->rigmask) B_TRY(dalloc(c, &new_rigmask, n1, true));
+    }
+    {
+        StageScope sc("inflate", c->stream);
+        k_inflate_rows<<<c->h0, B200C_ROW_THREADS, 0, c->stream>>>(
+            c->rgb, c->vs, c->w0, w1, c->channels, l, c->max_level, new_rgb, new_vs, c->bias, new_bias, c->rigmask,
+            new_rigmask, c->raw, c->w_start);
+        B_TRY(check_launch("k_inflate_rows"));
+    }
+    dfree(c, c->rgb);
+    dfree(c, c->en);
+    dfree(c, c->m);
+    dfree(c, c->least);
+    dfree(c, c->bias);
+    dfree(c, c->rigmask);
+    c->nrg_uptodate = false;
+    c->rgb = new_rgb;
+    if (!c->root) {
+        dfree(c, c->vs);
+        c->vs = new_vs;
+        propagate_vs(c);
+    }
+    if (c->nrg_active) B_TRY(dalloc(c, &c->en, n1, true));
+    if (c->active) {
+        c->bias = new_bias;
+        c->rigmask = new_rigmask;
+        B_TRY(dalloc(c, &c->m, n1, true));
+        B_TRY(dalloc(c, &c->least, n1, true));
+    }
+    c->w0 = w1;
+    c->w = c->w_start;
+    c->level = l + 1;
+    c->max_level = l + 1;
+    return B200C_OK;
+}
+
+// ---- A.7 per-seam loop ------------------------------------------------------------------------------------
+int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
+{
+    cudaStream_t s = c->stream;
+    {
+        StageScope sc("vpath", s);
+        k_vpath<<<1, 1024, 0, s>>>(view(c));
+        B_TRY(check_launch("k_vpath"));
+    }
+    const int vs_value = l + c->max_level - 1;
+    c->level++;
+    c->w--;
+    {
+        StageScope sc("carve", s);
+        k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(view(c), vs_value);
+        B_TRY(check_launch("k_carve"));
+    }
+    c->nrg_uptodate = false;
+    if (c->w > 1) {
+        {
+            StageScope sc("energy_band", s);
+            k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
+            B_TRY(check_launch("k_energy_band"));
+        }
+        c->nrg_uptodate = true;
+        if (c->lr_freq && ((l - c->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0) {
+            c->leftright ^= 1;
+            B_TRY(build_mmap(c));
+        } else {
+            StageScope sc("mmap_update", s);
+            k_mmap_update<<<1, 512, 0, s>>>(view(c));
+            B_TRY(check_launch("k_mmap_update"));
+        }
+    } else {
+        StageScope sc("finish_vsmap", s);
+        k_finish_vsmap<<<(c->h + 255) / 256, 256, 0, s>>>(view(c));
+        B_TRY(check_launch("k_finish_vsmap"));
+    }
+    return B200C_OK;
+}
+
+int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user, bool do_inflate)
+{
+    int lr_switch_interval = 0;
+    if (depth == 0) depth = c->w_start + 1;
+    if (c->lr_freq) lr_switch_interval = (depth - c->max_level - 1) / (int) c->lr_freq + 1;
+    if (update_step < 1) update_step = 1;
+    const int first = c->max_level;
+    for (int l = first; l < depth; ++l) {
+        if (progress && ((l - first) % update_step) == 0) {
+            if (progress(user, l - first)) return fail(B200C_CANCEL, "cancelled by progress callback");
+        }
+        B_TRY(seam_iteration(c, l, lr_switch_interval));
+    }
+    if (!do_inflate) return B200C_OK;
+    B_TRY(inflate(c, depth - 1));
+    set_width_one(c, c->w_start);
+    for (B200Carver *a : c->attached) set_width_rec(a, c->w_start);
+    return B200C_OK;
+}
+
+// ---- A.11 flatten / transpose ---------------------------------------------------------------------------------
+int flatten(B200Carver *c)
+{
+    for (B200Carver *a : c->attached) B_TRY(flatten(a));
+
+    dfree(c, c->en);
+    dfree(c, c->m);
+    dfree(c, c->least);
+    c->nrg_uptodate = false;
+
+    const size_t n = (size_t) c->w * c->h;
+    uint8_t *new_rgb = nullptr;
+    float *new_bias = nullptr, *new_rigmask = nullptr;
+    B_TRY(dalloc(c, &new_rgb, n * c->channels, true));
+    if (c->active && c->rigmask) B_TRY(dalloc(c, &new_rigmask, n, true));
+    if (c->nrg_active && c->bias) B_TRY(dalloc(c, &new_bias, n, true));
+    {
+        StageScope sc("flatten", c->stream);
+        k_compact_rows<<<c->h, B200C_ROW_THREADS, 0, c->stream>>>(c->rgb, c->vs, c->w0, c->w, c->channels, c->level,
+                                                                  new_rgb, c->bias, new_bias, c->rigmask, new_rigmask);
+        B_TRY(check_launch("k_compact_rows(flatten)"));
+    }
+    dfree(c, c->rgb);
+    c->rgb = new_rgb;
+    if (c->nrg_active) {
+        dfree(c, c->bias);
+        c->bias = new_bias;
+    }
+    if (c->active) {
+        dfree(c, c->rigmask);
+        c->rigmask = new_rigmask;
+    }
+    if (!c->root) {
+        dfree(c, c->vs);
+        B_TRY(dalloc(c, &c->vs, n, true));
+        propagate_vs(c);
+    }
+    c->w0 = c->w;
+    c->h0 = c->h;
+    c->w_start = c->w;
+    c->h_start = c->h;
+    c->level = 1;
+    c->max_level = 1;
+    if (c->nrg_active) {
+        dfree(c, c->raw);
+        B_TRY(dalloc(c, &c->raw, n, false));
+        B_TRY(init_raw(c));
+        B_TRY(dalloc(c, &c->en, n, true));
+    }
+    if (c->active) {
+        B_TRY(dalloc(c, &c->m, n, true));
+        B_TRY(dalloc(c, &c->least, n, true));
+    }
+    return B200C_OK;
+}
+
+int transpose_buffer(B200Carver *c, const void *in, void *out, int elem, int w, int h)
+{
+    dim3 grid((w + 31) / 32, (h + 31) / 32);
+    StageScope sc("transpose", c->stream);
+    const uint8_t *i8 = (const uint8_t *) in;
+    uint8_t *o8 = (uint8_t *) out;
+    switch (elem) {
+        case 1: k_transpose<1><<<grid, 256, 0, c->stream>>>(i8, o8, w, h); break;
+        case 2: k_transpose<2><<<grid, 256, 0, c->stream>>>(i8, o8, w, h); break;
+        case 3: k_transpose<3><<<grid, 256, 0, c->stream>>>(i8, o8, w, h); break;
+        case 4: k_transpose<4><<<grid, 256, 0, c->stream>>>(i8, o8, w, h); break;
+        default: return fail(B200C_ERROR, "transpose: unsupported element size");
+    }
+    return check_launch("k_transpose");
+}
+
+int transpose(B200Carver *c)
+{
+    if (c->level > 1) B_TRY(flatten(c));
+    for (B200Carver *a : c->attached) B_TRY(transpose(a));
+
+    const size_t n = (size_t) c->w0 * c->h0;
+    dfree(c, c->en);
+    dfree(c, c->m);
+    dfree(c, c->least);
+    c->nrg_uptodate = false;
+
+    uint8_t *new_rgb = nullptr;
+    float *new_bias = nullptr, *new_rigmask = nullptr;
+    B_TRY(dalloc(c, &new_rgb, n * c->channels, true));
+    B_TRY(transpose_buffer(c, c->rgb, new_rgb, c->channels, c->w0, c->h0));
+    if (c->nrg_active && c->bias) {
+        B_TRY(dalloc(c, &new_bias, n, true));
+        B_TRY(transpose_buffer(c, c->bias, new_bias, 4, c->w0, c->h0));
+    }
+    if (c->active && c->rigmask) {
+        B_TRY(dalloc(c, &new_rigmask, n, true));
+        B_TRY(transpose_buffer(c, c->rigmask, new_rigmask, 4, c->w0, c->h0));
+    }
+    dfree(c, c->rgb);
+    c->rgb = new_rgb;
+    if (c->nrg_active) {
+        dfree(c, c->bias);
+        c->bias = new_bias;
+    }
+    if (c->active) {
+        dfree(c, c->rigmask);
+        c->rigmask = new_rigmask;
+    }
+    if (!c->root) {
+        dfree(c, c->vs);
+        B_TRY(dalloc(c, &c->vs, n, true));
+        propagate_vs(c);
+    }
+
+    const int d = c->w0;
+    c->w0 = c->h0;
+    c->h0 = d;
+    c->w = c->w0;
+    c->h = c->h0;
+    c->w_start = c->w0;
+    c->h_start = c->h0;
+    c->level = 1;
+    c->max_level = 1;
+
+    if (c->nrg_active) {
+        dfree(c, c->raw);
+        B_TRY(dalloc(c, &c->raw, n, false));
+        B_TRY(init_raw(c));
+        B_TRY(dalloc(c, &c->en, n, true));
+    }
+    if (c->active) {
+        B_TRY(dalloc(c, &c->m, n, true));
+        B_TRY(dalloc(c, &c->least, n, true));
+        dfree(c, c->vpath);
+        dfree(c, c->vpath_x);
+        dfree(c, c->nrg_xmin);
+        dfree(c, c->nrg_xmax);
+        B_TRY(dalloc(c, &c->vpath, (size_t) c->h, true));
+        B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
+        B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
+        B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
+        for (int x = -c->delta_x; x <= c->delta_x; ++x) {
+            float &v = c->rigmap_h[x + c->delta_x];
+            v = v * c->w0 / c->h0;
+        }
+        B_TRY(upload_rigmap(c));
+    }
+    c->transposed = c->transposed ? 0 : 1;
+    return B200C_OK;
+}
+
+bool not_at_reference(const B200Carver *c)
+{
+    return c->w != c->w0 || c->w_start != c->w0 || c->h != c->h0 || c->h_start != c->h0;
+}
+
+int ensure_host_out(B200Carver *c, size_t bytes)
+{
+    if (bytes <= c->host_out_cap) return B200C_OK;
+    if (c->host_out) cudaFreeHost(c->host_out);
+    c->host_out = nullptr;
+    c->host_out_cap = 0;
+    CU_TRY(cudaHostAlloc((void **) &c->host_out, bytes, cudaHostAllocDefault));
+    c->host_out_cap = bytes;
+    return B200C_OK;
+}
+
+B200Carver *carver_new_common(int width, int height, int channels)
+{
+    if (width < 1 || height < 1 || channels < 1 || channels > 4) {
+        fail(B200C_ERROR, "carver_new: bad geometry (channels must be 1..4)");
+        return nullptr;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        fail(B200C_ERROR, "no CUDA device: the B200 engine has no CPU fallback", e);
+        return nullptr;
+    }
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char *t = getenv("B200C_TIMING");
+        g_timing = t && atoi(t) != 0;
+    });
+    B200Carver *c = new (std::nothrow) B200Carver();
+    if (!c) {
+        fail(B200C_NOMEM, "carver_new: host allocation");
+        return nullptr;
+    }
+    c->device = g_device >= 0 ? g_device : g_device_tls_default;
+    if (cudaSetDevice(c->device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        fail(B200C_ERROR, "carver_new: cannot create stream", cudaGetLastError());
+        delete c;
+        return nullptr;
+    }
+    {
+        // keep freed blocks in the pool: the per-resize maps are reallocated at every inflate/flatten
+        static std::mutex mu;
+        static std::vector<int> tuned;
+        std::lock_guard<std::mutex> lk(mu);
+        bool done = false;
+        for (int d : tuned) done |= d == c->device;
+        if (!done) {
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
+                uint64_t thr = UINT64_MAX;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+            }
+            tuned.push_back(c->device);
+        }
+    }
+    c->w = c->w0 = c->w_start = width;
+    c->h = c->h0 = c->h_start = height;
+    c->channels = channels;
+    c->alpha = (channels == 2 || channels == 4) ? channels - 1 : -1;
+    return c;
+}
+
+} // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+int b200c_abi_version(void) { return B200C_ABI_VERSION; }
+const char *b200c_last_error(void) { return g_err.c_str(); }
+
+int b200c_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int b200c_set_device(int device)
+{
+    int n = b200c_device_count();
+    if (device < 0 || device >= n) return fail(B200C_ERROR, "b200c_set_device: no such device");
+    g_device = device;
+    return B200C_OK;
+}
+
+B200Carver *b200c_carver_new(const unsigned char *rgb, int width, int height, int channels)
+{
+    if (!rgb) {
+        fail(B200C_ERROR, "carver_new: NULL image");
+        return nullptr;
+    }
+    B200Carver *c = carver_new_common(width, height, channels);
+    if (!c) return nullptr;
+    const size_t n = (size_t) width * height;
+    if (dalloc(c, &c->rgb, n * channels, false) != B200C_OK || dalloc(c, &c->vs, n, true) != B200C_OK ||
+        cudaMemcpyAsync(c->rgb, rgb, n * channels, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) { // the caller may free `rgb` right after we return
+        fail(B200C_NOMEM, "carver_new: device allocation / upload failed", cudaGetLastError());
+        b200c_carver_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+B200Carver *b200c_carver_new_device(const void *d_rgb, int width, int height, int channels)
+{
+    if (!d_rgb) {
+        fail(B200C_ERROR, "carver_new_device: NULL image");
+        return nullptr;
+    }
+    B200Carver *c = carver_new_common(width, height, channels);
+    if (!c) return nullptr;
+    const size_t n = (size_t) width * height;
+    if (dalloc(c, &c->rgb, n * channels, false) != B200C_OK || dalloc(c, &c->vs, n, true) != B200C_OK ||
+        cudaMemcpyAsync(c->rgb, d_rgb, n * channels, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess) {
+        fail(B200C_NOMEM, "carver_new_device: device allocation / copy failed", cudaGetLastError());
+        b200c_carver_destroy(c);
+        return nullptr;
+    }
+    return c;
+}
+
+void b200c_carver_destroy(B200Carver *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (B200Carver *a : c->attached) b200c_carver_destroy(a);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    const bool owns_stream = c->root == nullptr; // attached carvers run on their root's queue
+    dfree(c, c->rgb);
+    if (!c->root) dfree(c, c->vs);
+    dfree(c, c->en);
+    dfree(c, c->m);
+    dfree(c, c->least);
+    dfree(c, c->raw);
+    dfree(c, c->bias);
+    dfree(c, c->rigmask);
+    dfree(c, c->vpath);
+    dfree(c, c->vpath_x);
+    dfree(c, c->nrg_xmin);
+    dfree(c, c->nrg_xmax);
+    dfree(c, c->rigmap_d);
+    if (c->host_out) cudaFreeHost(c->host_out);
+    if (c->stream) {
+        cudaStreamSynchronize(c->stream);
+        if (owns_stream) cudaStreamDestroy(c->stream);
+    }
+    delete c;
+}
+
+int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
+{
+    if (!c || delta_x < 0) return fail(B200C_ERROR, "carver_init: bad arguments");
+    if (c->active) return fail(B200C_ERROR, "carver_init: already active");
+    B_TRY(use_device(c));
+    if (!c->nrg_active) B_TRY(init_energy_related(c));
+    const size_t n = (size_t) c->w * c->h;
+    B_TRY(dalloc(c, &c->m, n, true));
+    B_TRY(dalloc(c, &c->least, n, true));
+    B_TRY(dalloc(c, &c->vpath, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
+    c->delta_x = delta_x;
+    c->rigidity = rigidity;
+    c->rigmap_h.assign(2 * delta_x + 1, 0.f);
+    for (int x = -delta_x; x <= delta_x; ++x)
+        c->rigmap_h[x + delta_x] = c->rigidity * powf(fabsf((float) x), 1.5f) / c->h; // A.1 / A.4
+    B_TRY(dalloc(c, &c->rigmap_d, c->rigmap_h.size(), false));
+    B_TRY(upload_rigmap(c));
+    c->active = true;
+    return B200C_OK;
+}
+
+int b200c_carver_attach(B200Carver *root, B200Carver *aux)
+{
+    if (!root || !aux) return fail(B200C_ERROR, "carver_attach: NULL");
+    if (root->w0 != aux->w0 || root->h0 != aux->h0) return fail(B200C_ERROR, "carver_attach: size mismatch");
+    if (root->device != aux->device) return fail(B200C_ERROR, "carver_attach: carvers live on different devices");
+    B_TRY(use_device(root));
+    // the aux carver's own queue must be idle before it starts sharing the root's maps and stream
+    CU_TRY(cudaStreamSynchronize(aux->stream));
+    dfree(aux, aux->vs);
+    CU_TRY(cudaStreamSynchronize(aux->stream));
+    cudaStreamDestroy(aux->stream);
+    aux->stream = root->stream; // one queue per carver family keeps every structural op ordered
+    aux->vs = root->vs;
+    aux->root = root;
+    root->attached.push_back(aux);
+    return B200C_OK;
+}
+
+int b200c_carver_set_energy_function(B200Carver *c, int ef)
+{
+    if (!c) return fail(B200C_ERROR, "set_energy_function: NULL");
+    int grad, rd, rad = 1;
+    switch (ef) {
+        case 0: grad = GRAD_NORM; rd = READ_BRIGHTNESS; break;
+        case 1: grad = GRAD_SUMABS; rd = READ_BRIGHTNESS; break;
+        case 2: grad = GRAD_XABS; rd = READ_BRIGHTNESS; break;
+        case 3: grad = GRAD_NORM; rd = READ_LUMA; break;
+        case 4: grad = GRAD_SUMABS; rd = READ_LUMA; break;
+        case 5: grad = GRAD_XABS; rd = READ_LUMA; break;
+        case 6: grad = GRAD_NULL; rd = READ_BRIGHTNESS; rad = 0; break;
+        default: return fail(B200C_ERROR, "set_energy_function: unknown builtin");
+    }
+    c->ef = ef;
+    c->grad_kind = grad;
+    c->read_kind = rd;
+    c->nrg_radius = rad;
+    c->nrg_uptodate = false;
+    return B200C_OK;
+}
+
+int b200c_carver_set_side_switch_frequency(B200Carver *c, unsigned int f)
+{
+    if (!c) return fail(B200C_ERROR, "set_side_switch_frequency: NULL");
+    c->lr_freq = f;
+    return B200C_OK;
+}
+
+static int mask_common(B200Carver *c, const unsigned char *rgb, int channels, int width, int height, int x_off,
+                       int y_off, bool is_bias, int bias_factor)
+{
+    if (!c || !rgb || channels < 1 || width < 1 || height < 1) return fail(B200C_ERROR, "mask: bad arguments");
+    B_TRY(use_device(c));
+    if (!is_bias && !c->active) return fail(B200C_ERROR, "rigmask: carver not initialised");
+    if (not_at_reference(c)) B_TRY(flatten(c));
+    if (is_bias && bias_factor == 0) return B200C_OK;
+    const size_t n = (size_t) c->w0 * c->h0;
+    if (is_bias && !c->bias) B_TRY(dalloc(c, &c->bias, n, true));
+    if (!is_bias && !c->rigmask) B_TRY(dalloc(c, &c->rigmask, n, true));
+    const int was_transposed = c->transposed;
+    if (was_transposed) B_TRY(transpose(c));
+
+    const int x0 = x_off < 0 ? x_off : 0, y0 = y_off < 0 ? y_off : 0;
+    const int x1 = x_off > 0 ? x_off : 0, y1 = y_off > 0 ? y_off : 0;
+    const int x2 = c->w < width + x_off ? c->w : width + x_off;
+    const int y2 = c->h < height + y_off ? c->h : height + y_off;
+    const int nx = x2 - x1, ny = y2 - y1;
+    if (nx > 0 && ny > 0) {
+        uint8_t *d_mask = nullptr;
+        const size_t bytes = (size_t) width * height * channels;
+        B_TRY(dalloc(c, &d_mask, bytes, false));
+        CU_TRY(cudaMemcpyAsync(d_mask, rgb, bytes, cudaMemcpyHostToDevice, c->stream));
+        dim3 grid((nx + 255) / 256, ny);
+        {
+            StageScope sc("mask", c->stream);
+            if (is_bias)
+                k_bias_add<<<grid, 256, 0, c->stream>>>(c->bias, c->w0, d_mask, channels, width, bias_factor, x0, y0,
+                                                        x1, y1, nx, ny);
+            else
+                k_rigmask_set<<<grid, 256, 0, c->stream>>>(c->rigmask, c->w0, d_mask, channels, width, x0, y0, x1, y1,
+                                                           nx, ny);
+            B_TRY(check_launch("mask kernel"));
+        }
+        dfree(c, d_mask);
+        CU_TRY(cudaStreamSynchronize(c->stream)); // the caller frees the mask right after (io_functions.c:97,128)
+    }
+    if (is_bias) c->nrg_uptodate = false;
+    if (was_transposed != c->transposed) B_TRY(transpose(c));
+    return B200C_OK;
+}
+
+int b200c_carver_bias_add_rgb_area(B200Carver *c, const unsigned char *rgb, int bias_factor, int channels, int width,
+                                   int height, int x_off, int y_off)
+{
+    return mask_common(c, rgb, channels, width, height, x_off, y_off, true, bias_factor);
+}
+
+int b200c_carver_rigmask_add_rgb_area(B200Carver *c, const unsigned char *rgb, int channels, int width, int height,
+                                      int x_off, int y_off)
+{
+    return mask_common(c, rgb, channels, width, height, x_off, y_off, false, 0);
+}
+
+int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user)
+{
+    if (!c) return fail(B200C_ERROR, "build_maps: NULL");
+    if (depth <= c->max_level) return B200C_OK;
+    if (!c->active) return fail(B200C_ERROR, "build_maps: carver not initialised");
+    if (c->root) return fail(B200C_ERROR, "build_maps: attached carvers cannot be resized directly");
+    B_TRY(use_device(c));
+    set_width_one(c, c->w_start - c->max_level + 1);
+    B_TRY(build_emap(c));
+    B_TRY(build_mmap(c));
+    B_TRY(build_vsmap(c, depth, update_step, progress, user, true));
+    return B200C_OK;
+}
+
+int b200c_carver_set_width(B200Carver *c, int w1)
+{
+    if (!c) return fail(B200C_ERROR, "set_width: NULL");
+    set_width_rec(c, w1);
+    return B200C_OK;
+}
+
+int b200c_carver_flatten(B200Carver *c)
+{
+    if (!c) return fail(B200C_ERROR, "flatten: NULL");
+    B_TRY(use_device(c));
+    return flatten(c);
+}
+
+int b200c_carver_transpose(B200Carver *c)
+{
+    if (!c) return fail(B200C_ERROR, "transpose: NULL");
+    B_TRY(use_device(c));
+    return transpose(c);
+}
+
+int b200c_carver_get(const B200Carver *c, int field)
+{
+    if (!c) return -1;
+    switch (field) {
+        case B200C_W: return c->w;
+        case B200C_H: return c->h;
+        case B200C_W0: return c->w0;
+        case B200C_H0: return c->h0;
+        case B200C_W_START: return c->w_start;
+        case B200C_H_START: return c->h_start;
+        case B200C_LEVEL: return c->level;
+        case B200C_MAX_LEVEL: return c->max_level;
+        case B200C_TRANSPOSED: return c->transposed;
+        case B200C_CHANNELS: return c->channels;
+        case B200C_ACTIVE: return c->active ? 1 : 0;
+        case B200C_LEFTRIGHT: return c->leftright;
+        case B200C_DEVICE: return c->device;
+        default: return -1;
+    }
+}
+
+static int readout_to(B200Carver *c, uint8_t *d_out)
+{
+    StageScope sc("readout", c->stream);
+    k_compact_rows<<<c->h, B200C_ROW_THREADS, 0, c->stream>>>(c->rgb, c->vs, c->w0, c->w, c->channels, c->level, d_out,
+                                                              nullptr, nullptr, nullptr, nullptr);
+    return check_launch("k_compact_rows(readout)");
+}
+
+int b200c_carver_readout(B200Carver *c, const unsigned char **host_pixels)
+{
+    if (!c || !host_pixels) return fail(B200C_ERROR, "readout: NULL");
+    B_TRY(use_device(c));
+    const size_t bytes = (size_t) c->w * c->h * c->channels;
+    B_TRY(ensure_host_out(c, bytes));
+    uint8_t *d_out = nullptr;
+    B_TRY(dalloc(c, &d_out, bytes, false));
+    B_TRY(readout_to(c, d_out));
+    CU_TRY(cudaMemcpyAsync(c->host_out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    dfree(c, d_out);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    *host_pixels = c->host_out;
+    return B200C_OK;
+}
+
+int b200c_carver_readout_device(B200Carver *c, void *d_out)
+{
+    if (!c || !d_out) return fail(B200C_ERROR, "readout_device: NULL");
+    B_TRY(use_device(c));
+    return readout_to(c, (uint8_t *) d_out);
+}
+
+int b200c_carver_vmap(B200Carver *c, int *out_host)
+{
+    if (!c || !out_host) return fail(B200C_ERROR, "vmap: NULL");
+    B_TRY(use_device(c));
+    const int depth = c->w0 - c->w_start;
+    const size_t n = (size_t) c->w_start * c->h;
+    int *d_out = nullptr;
+    B_TRY(dalloc(c, &d_out, n, true));
+    {
+        StageScope sc("vmap", c->stream);
+        k_vmap_rows<<<c->h, B200C_ROW_THREADS, 0, c->stream>>>(c->vs, c->w0, c->w_start, c->h, depth, c->transposed,
+                                                               d_out);
+        B_TRY(check_launch("k_vmap_rows"));
+    }
+    CU_TRY(cudaMemcpyAsync(out_host, d_out, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    dfree(c, d_out);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return B200C_OK;
+}
+
+int b200c_carver_true_energy(B200Carver *c, float *out_host)
+{
+    if (!c || !out_host) return fail(B200C_ERROR, "true_energy: NULL");
+    B_TRY(use_device(c));
+    if (!c->nrg_active) B_TRY(init_energy_related(c));
+    B_TRY(build_emap(c));
+    const size_t n = (size_t) c->w * c->h;
+    float *d_out = nullptr;
+    B_TRY(dalloc(c, &d_out, n, false));
+    dim3 grid((c->w + 255) / 256, c->h);
+    {
+        StageScope sc("energy_export", c->stream);
+        k_energy_export<<<grid, 256, 0, c->stream>>>(view(c), c->transposed, d_out);
+        B_TRY(check_launch("k_energy_export"));
+    }
+    CU_TRY(cudaMemcpyAsync(out_host, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    dfree(c, d_out);
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return B200C_OK;
+}
+
+int b200c_carver_sync(B200Carver *c)
+{
+    if (!c) return fail(B200C_ERROR, "sync: NULL");
+    B_TRY(use_device(c));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return B200C_OK;
+}
+
+// ---- test / profiling hooks -----------------------------------------------------------------------------------
+int b200c_debug_build(B200Carver *c, int n_seams)
+{
+    if (!c || !c->active || c->root) return fail(B200C_ERROR, "debug_build: need an initialised root carver");
+    B_TRY(use_device(c));
+    set_width_one(c, c->w_start - c->max_level + 1);
+    B_TRY(build_emap(c));
+    B_TRY(build_mmap(c));
+    if (n_seams > 0) B_TRY(build_vsmap(c, c->max_level + n_seams, 1, nullptr, nullptr, false));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    return B200C_OK;
+}
+
+long b200c_debug_fetch(B200Carver *c, int what, void *out, long cap)
+{
+    if (!c || !out) return -1;
+    if (use_device(c) != B200C_OK) return -1;
+    const void *src = nullptr;
+    long n = (long) c->w0 * c->h0;
+    switch (what) {
+        case B200C_DBG_EN: src = c->en; break;
+        case B200C_DBG_M: src = c->m; break;
+        case B200C_DBG_LEAST: src = c->least; break;
+        case B200C_DBG_RAW: src = c->raw; n = (long) c->w_start * c->h_start; break;
+        case B200C_DBG_VS: src = c->vs; break;
+        case B200C_DBG_VPATH_X: src = c->vpath_x; n = c->h; break;
+        case B200C_DBG_BIAS: src = c->bias; break;
+        case B200C_DBG_RIGMASK: src = c->rigmask; break;
+        default: return -1;
+    }
+    if (!src) return 0;
+    if (n > cap) n = cap;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    if (cudaMemcpy(out, src, (size_t) n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    return n;
+}
+
+long b200c_launch_count(void) { return g_launches.load(); }
+
+double b200c_stage_ms(const char *stage, long *launches)
+{
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    auto it = g_stages.find(stage ? stage : "");
+    if (it == g_stages.end()) {
+        if (launches) *launches = 0;
+        return 0.0;
+    }
+    drain_stage(it->second);
+    if (launches) *launches = it->second.launches;
+    return it->second.ms;
+}
+
+void b200c_stage_reset(void)
+{
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    for (auto &kv : g_stages) drain_stage(kv.second);
+    g_stages.clear();
+}
+
+} // extern "C"

@@ -1,0 +1,554 @@
+// carver_kernels.cuh -- sm_100a kernels of the seam-carving hot path.
+//
+// Each kernel states which step of the liblqr algorithm (cited A.n) it performs.
+// Float discipline: every parity-critical float/double operation is written with the round-to-nearest
+// intrinsics (__fadd_rn, __fmul_rn, __dadd_rn, ...) so that nvcc can never contract a*b+c into an FMA --
+// the CPU reference path is compiled without FMA contraction and the seam choice depends on exact ties.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200c {
+
+enum { READ_BRIGHTNESS = 0, READ_LUMA = 1 };
+enum { GRAD_NORM = 0, GRAD_SUMABS = 1, GRAD_XABS = 2, GRAD_NULL = 3 };
+
+// Device view of one carver, passed by value to every kernel.
+struct DevP {
+    int w, h;          // current size (internal orientation)
+    int w0, h0;        // allocated map size
+    int w_start;       // reference width
+    int raw_stride;    // pitch of the raw index table (== w_start)
+    int channels, alpha;
+    int level;
+    int delta_x;
+    int leftright;
+    int grad_kind, read_kind, nrg_radius;
+    int use_rig;       // rigidity != 0
+    const uint8_t *rgb;
+    int *vs;
+    int *raw;
+    float *en;
+    float *m;
+    int *least;
+    const float *bias;
+    const float *rigmask;
+    const float *rigmap; // centred: rigmap[dx], dx in [-delta_x, delta_x]
+    int *vpath, *vpath_x, *nrg_xmin, *nrg_xmax;
+};
+
+// ------------------------------------------------------------------------------------------------
+// A.2 pixel reading: 8-bit channel / 255 in double; brightness = mean of colour channels, luma =
+// Rec.709 weights; both multiplied by alpha when the image has an alpha channel.
+__device__ __forceinline__ double px_scalar(const DevP &p, int z)
+{
+    const uint8_t *q = p.rgb + (size_t) z * p.channels;
+    double v;
+    if (p.channels <= 2) {
+        v = (double) q[0] / 255.0;
+    } else {
+        const double r = (double) q[0] / 255.0, g = (double) q[1] / 255.0, b = (double) q[2] / 255.0;
+        if (p.read_kind == READ_LUMA)
+            v = __dadd_rn(__dadd_rn(__dmul_rn(0.2126, r), __dmul_rn(0.7152, g)), __dmul_rn(0.0722, b));
+        else
+            v = __dadd_rn(__dadd_rn(r, g), b) / 3.0;
+    }
+    if (p.alpha >= 0) v = __dmul_rn(v, (double) q[p.alpha] / 255.0);
+    return v;
+}
+
+// A.3 energy of the pixel at current coordinates (x, y): central differences over the four nearest
+// neighbours in the CURRENT image (through the raw index table), one-sided at the borders.
+__device__ __forceinline__ float energy_at(const DevP &p, int x, int y)
+{
+    const int *row = p.raw + (size_t) y * p.raw_stride;
+    const int z = row[x];
+    float e = 0.f;
+    if (p.grad_kind != GRAD_NULL) {
+        const double b = px_scalar(p, z);
+        double gx, gy;
+        if (y == 0)
+            gy = __dsub_rn(p.h > 1 ? px_scalar(p, row[p.raw_stride + x]) : 0.0, b);
+        else if (y < p.h - 1)
+            gy = __dmul_rn(__dsub_rn(px_scalar(p, row[p.raw_stride + x]), px_scalar(p, row[x - p.raw_stride])), 0.5);
+        else
+            gy = __dsub_rn(b, px_scalar(p, row[x - p.raw_stride]));
+        if (x == 0)
+            gx = __dsub_rn(p.w > 1 ? px_scalar(p, row[x + 1]) : 0.0, b);
+        else if (x < p.w - 1)
+            gx = __dmul_rn(__dsub_rn(px_scalar(p, row[x + 1]), px_scalar(p, row[x - 1])), 0.5);
+        else
+            gx = __dsub_rn(b, px_scalar(p, row[x - 1]));
+        if (p.grad_kind == GRAD_NORM)
+            e = (float) sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
+        else if (p.grad_kind == GRAD_SUMABS)
+            e = (float) __dmul_rn(__dadd_rn(fabs(gx), fabs(gy)), 0.5);
+        else
+            e = (float) fabs(gx);
+    }
+    float b_add = 0.f;
+    if (p.bias) b_add = __fdiv_rn(p.bias[z], (float) p.w_start);
+    return __fadd_rn(e, b_add);
+}
+
+// A.5 best parent of cell (x, y): scan x+[-delta_x, delta_x] (clipped) left to right, strict '<' keeps the
+// leftmost minimum, leftright==1 turns ties to the right.  Returns the candidate value, parent pixel id.
+__device__ __forceinline__ float best_parent(const DevP &p, int x, int y, int z, int &parent)
+{
+    const int x1_min = max(-x, -p.delta_x);
+    const int x1_max = min(p.w - 1 - x, p.delta_x);
+    const int *up = p.raw + (size_t) (y - 1) * p.raw_stride;
+    int zd = up[x + x1_min];
+    int least = zd;
+    float best;
+    if (p.use_rig) {
+        const float rf = p.rigmask ? p.rigmask[z] : 1.f;
+        best = __fadd_rn(p.m[zd], __fmul_rn(rf, p.rigmap[x1_min]));
+        for (int x1 = x1_min + 1; x1 <= x1_max; ++x1) {
+            zd = up[x + x1];
+            const float cand = __fadd_rn(p.m[zd], __fmul_rn(rf, p.rigmap[x1]));
+            if (cand < best || (cand == best && p.leftright == 1)) {
+                best = cand;
+                least = zd;
+            }
+        }
+    } else {
+        best = p.m[zd];
+        for (int x1 = x1_min + 1; x1 <= x1_max; ++x1) {
+            zd = up[x + x1];
+            const float cand = p.m[zd];
+            if (cand < best || (cand == best && p.leftright == 1)) {
+                best = cand;
+                least = zd;
+            }
+        }
+    }
+    parent = least;
+    return best;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_init_raw(int *raw, int w, int h)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x < w && y < h) raw[(size_t) y * w + x] = y * w + x;
+}
+
+// K1 -- A.3 full energy map (lqr_carver_build_emap): one thread per visible pixel.
+__global__ void __launch_bounds__(256) k_energy_full(DevP p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= p.w || y >= p.h) return;
+    const int z = p.raw[(size_t) y * p.raw_stride + x];
+    p.en[z] = energy_at(p, x, y);
+}
+
+// K1b -- A.8 energy band after a carve (lqr_carver_update_emap): one warp per row derives the row's
+// [nrg_xmin, nrg_xmax] from the seam positions of rows y-radius..y+radius and recomputes that band.
+// p.w is the width AFTER the carve; vpath_x is in pre-carve coordinates.
+__global__ void __launch_bounds__(256) k_energy_band(DevP p)
+{
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (y >= p.h) return;
+    const int r = p.nrg_radius;
+    const int own = p.vpath_x[y];
+    int xmin = own, xmax = own - 1;
+    for (int y1 = max(y - r, 0); y1 <= min(y + r, p.h - 1); ++y1) {
+        const int x = p.vpath_x[y1];
+        xmin = min(xmin, x - r);
+        xmax = max(xmax, x + r - 1);
+    }
+    xmin = max(0, xmin);
+    xmax = min(p.w - 1, xmax);
+    if (lane == 0) {
+        p.nrg_xmin[y] = xmin;
+        p.nrg_xmax[y] = xmax;
+    }
+    for (int x = xmin + lane; x <= xmax; x += 32) {
+        const int z = p.raw[(size_t) y * p.raw_stride + x];
+        p.en[z] = energy_at(p, x, y);
+    }
+}
+
+// K2 (generic) -- A.5 full m-map DP (lqr_carver_build_mmap): one CTA walks the rows, the row is spread
+// over the threads, a block barrier separates dependent rows.  Correct for any width / delta_x; the
+// tiled multi-CTA version lives in mmap_tiled.cuh.
+__global__ void __launch_bounds__(1024) k_mmap_full(DevP p)
+{
+    for (int x = threadIdx.x; x < p.w; x += blockDim.x) {
+        const int z = p.raw[x];
+        p.m[z] = p.en[z];
+    }
+    __syncthreads();
+    for (int y = 1; y < p.h; ++y) {
+        const int *row = p.raw + (size_t) y * p.raw_stride;
+        for (int x = threadIdx.x; x < p.w; x += blockDim.x) {
+            const int z = row[x];
+            int parent;
+            const float best = best_parent(p, x, y, z, parent);
+            p.least[z] = parent;
+            p.m[z] = __fadd_rn(p.en[z], best);
+        }
+        __syncthreads();
+    }
+}
+
+// K2b (generic) -- A.8 incremental DP (lqr_carver_update_mmap) with the keep-old rule (same parent and
+// |m_old - m_new| < 1e-5 keeps m_old) and the self-trimming band: the leading run of kept cells advances
+// x_min, a trailing run pulls x_max back to its first cell.  One CTA, rows serial, band parallel.
+__global__ void __launch_bounds__(512) k_mmap_update(DevP p)
+{
+    __shared__ int s_first[2][16];
+    __shared__ int s_last[2][16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    int x_min = max(p.nrg_xmin[0], 0);
+    int x_max = min(p.nrg_xmax[0], p.w - 1);
+    for (int x = x_min + tid; x <= x_max; x += blockDim.x) {
+        const int z = p.raw[x];
+        p.m[z] = p.en[z];
+    }
+    __syncthreads();
+    for (int y = 1; y < p.h; ++y) {
+        x_min = min(x_min, p.nrg_xmin[y]);
+        x_max = max(x_max, p.nrg_xmax[y]);
+        x_min = max(x_min - p.delta_x, 0);
+        x_max = min(x_max + p.delta_x, p.w - 1);
+        const int *row = p.raw + (size_t) y * p.raw_stride;
+        int first = INT_MAX, last = INT_MIN; // extremes of the cells whose m changed (not kept)
+        for (int x = x_min + tid; x <= x_max; x += blockDim.x) {
+            const int z = row[x];
+            int parent;
+            const float new_m = __fadd_rn(p.en[z], best_parent(p, x, y, z, parent));
+            const bool keep = (p.least[z] == parent) && ((double) fabsf(__fsub_rn(p.m[z], new_m)) < 1e-5);
+            if (!keep) {
+                p.m[z] = new_m;
+                first = min(first, x);
+                last = max(last, x);
+            }
+            p.least[z] = parent;
+        }
+        first = __reduce_min_sync(0xffffffffu, first);
+        last = __reduce_max_sync(0xffffffffu, last);
+        const int buf = y & 1;
+        if (lane == 0) {
+            s_first[buf][warp] = first;
+            s_last[buf][warp] = last;
+        }
+        __syncthreads(); // publishes this row's m/least and the per-warp extremes
+        int F = INT_MAX, L = INT_MIN;
+        for (int i = 0; i < nwarp; ++i) {
+            F = min(F, s_first[buf][i]);
+            L = max(L, s_last[buf][i]);
+        }
+        if (x_max >= x_min) {
+            const int nx_min = (F != INT_MAX) ? F : x_max + 1;
+            const int nx_max = (L != INT_MIN) ? (L == x_max ? x_max : L + 1) : x_min;
+            x_min = nx_min;
+            x_max = nx_max;
+        }
+    }
+}
+
+// K3 (generic) -- A.6 seam: arg-min over the last row of m with the tie rule, then follow `least` upwards.
+__device__ __forceinline__ bool seam_better(float ov, int ox, float v, int x, int leftright)
+{
+    if (ox < 0) return false;
+    if (x < 0) return true;
+    if (ov < v) return true;
+    if (ov == v) return leftright ? (ox > x) : (ox < x);
+    return false;
+}
+
+__global__ void __launch_bounds__(1024) k_vpath(DevP p)
+{
+    __shared__ float s_v[32];
+    __shared__ int s_x[32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int *row = p.raw + (size_t) (p.h - 1) * p.raw_stride;
+    float best = 536870912.f; // (float)(1 << 29)
+    int bx = -1;
+    for (int x = tid; x < p.w; x += blockDim.x) {
+        const float v = p.m[row[x]];
+        if (v < best || (v == best && p.leftright == 1)) {
+            best = v;
+            bx = x;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        const float ov = __shfl_down_sync(0xffffffffu, best, off);
+        const int ox = __shfl_down_sync(0xffffffffu, bx, off);
+        if (seam_better(ov, ox, best, bx, p.leftright)) {
+            best = ov;
+            bx = ox;
+        }
+    }
+    if (lane == 0) {
+        s_v[warp] = best;
+        s_x[warp] = bx;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    for (int i = 1; i < nwarp; ++i)
+        if (seam_better(s_v[i], s_x[i], best, bx, p.leftright)) {
+            best = s_v[i];
+            bx = s_x[i];
+        }
+    int last_x = bx < 0 ? 0 : bx;
+    int last = row[last_x];
+    for (int y = p.h - 1; y >= 0; --y) {
+        p.vpath[y] = last;
+        p.vpath_x[y] = last_x;
+        if (y > 0) {
+            const int *cur = p.raw + (size_t) y * p.raw_stride;
+            const int *up = cur - p.raw_stride;
+            last = p.least[cur[last_x]];
+            const int x_lo = max(last_x - p.delta_x, 0), x_hi = min(last_x + p.delta_x, p.w - 1);
+            for (int x = x_lo; x <= x_hi; ++x)
+                if (up[x] == last) {
+                    last_x = x;
+                    break;
+                }
+        }
+    }
+}
+
+// K4 -- A.7 carve: mark the seam in the visibility map and shift the row's index table left by one past
+// the seam.  One CTA per row; p.w is the width AFTER the carve.  Loads of a chunk are parked in registers
+// before the barrier, so the in-place shift never reads a slot another thread already overwrote.
+#define B200C_CARVE_THREADS 256
+#define B200C_CARVE_ITEMS 8
+__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP p, int vs_value)
+{
+    const int y = blockIdx.x;
+    int *row = p.raw + (size_t) y * p.raw_stride;
+    const int vx = p.vpath_x[y];
+    if (threadIdx.x == 0) p.vs[p.vpath[y]] = vs_value;
+    for (int base = vx; base < p.w; base += B200C_CARVE_THREADS * B200C_CARVE_ITEMS) {
+        int v[B200C_CARVE_ITEMS];
+#pragma unroll
+        for (int i = 0; i < B200C_CARVE_ITEMS; ++i) {
+            const int x = base + i * B200C_CARVE_THREADS + threadIdx.x;
+            v[i] = (x < p.w) ? row[x + 1] : 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < B200C_CARVE_ITEMS; ++i) {
+            const int x = base + i * B200C_CARVE_THREADS + threadIdx.x;
+            if (x < p.w) row[x] = v[i];
+        }
+    }
+}
+
+// A.7 finish_vsmap: the image is one pixel wide; the survivors get the largest level.
+__global__ void k_finish_vsmap(DevP p)
+{
+    const int y = blockIdx.x * blockDim.x + threadIdx.x;
+    if (y < p.h) p.vs[p.raw[(size_t) y * p.raw_stride]] = p.w0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Block-wide exclusive scan of one int per thread (blockDim.x <= 1024, multiple of 32).
+// s_warp must hold 33 ints.  Returns the exclusive prefix; *total receives the block sum.
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int *total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int t = lane < nwarp ? s_warp[lane] : 0;
+        int ti = t;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, ti, off);
+            if (lane >= off) ti += u;
+        }
+        if (lane < nwarp) s_warp[lane] = ti - t; // exclusive warp offsets
+        if (lane == 31) s_warp[32] = ti;         // grand total
+    }
+    __syncthreads();
+    const int res = s_warp[warp] + incl - v;
+    *total = s_warp[32];
+    __syncthreads(); // s_warp may be reused right away
+    return res;
+}
+
+__device__ __forceinline__ bool is_visible(int vs, int level) { return vs == 0 || vs >= level; }
+
+// K6 / K7 -- A.12 read-out and A.11 flatten: per internal row, stream-compact the visible pixels
+// (vs == 0 or vs >= level) of the w0-wide row into a dense w-wide row; optionally the float maps too.
+#define B200C_ROW_THREADS 256
+__global__ void __launch_bounds__(B200C_ROW_THREADS)
+k_compact_rows(const uint8_t *rgb, const int *vs, int w0, int w, int channels, int level, uint8_t *out_rgb,
+               const float *bias, float *out_bias, const float *rigmask, float *out_rigmask)
+{
+    __shared__ int s_warp[33];
+    const int y = blockIdx.x;
+    const size_t in0 = (size_t) y * w0, out0 = (size_t) y * w;
+    int base = 0;
+    for (int c0 = 0; c0 < w0; c0 += B200C_ROW_THREADS) {
+        const int x = c0 + threadIdx.x;
+        const bool vis = x < w0 && is_visible(vs[in0 + x], level);
+        int total;
+        const int pos = base + block_excl_scan(vis ? 1 : 0, s_warp, &total);
+        if (vis && pos < w) {
+            const uint8_t *src = rgb + (in0 + x) * channels;
+            uint8_t *dst = out_rgb + (out0 + pos) * channels;
+            for (int k = 0; k < channels; ++k) dst[k] = src[k];
+            if (out_bias) out_bias[out0 + pos] = bias[in0 + x];
+            if (out_rigmask) out_rigmask[out0 + pos] = rigmask[in0 + x];
+        }
+        base += total;
+    }
+}
+
+// K10 -- A.13 visibility-map dump: at the reference width (level = depth + 1) the visible pixels of row y,
+// in order, get vs == 0 ? 0 : vs - depth, written in image orientation.
+__global__ void __launch_bounds__(B200C_ROW_THREADS)
+k_vmap_rows(const int *vs, int w0, int w_ref, int h, int depth, int transposed, int *out)
+{
+    __shared__ int s_warp[33];
+    const int y = blockIdx.x;
+    const size_t in0 = (size_t) y * w0;
+    const int level = depth + 1;
+    int base = 0;
+    for (int c0 = 0; c0 < w0; c0 += B200C_ROW_THREADS) {
+        const int x = c0 + threadIdx.x;
+        const int v = x < w0 ? vs[in0 + x] : 1;
+        const bool vis = x < w0 && is_visible(v, level);
+        int total;
+        const int pos = base + block_excl_scan(vis ? 1 : 0, s_warp, &total);
+        if (vis && pos < w_ref) {
+            const size_t o = transposed ? (size_t) pos * h + y : (size_t) y * w_ref + pos;
+            out[o] = v == 0 ? 0 : v - depth;
+        }
+        base += total;
+    }
+}
+
+// K5 -- A.9 inflate: walk the w0-wide row (all pixels visible at level 1); a pixel that belongs to a seam
+// found in this session (vs in [2*max_level-1, l+max_level-1]) is preceded by a new pixel whose channels
+// are the integer mean of it and its left neighbour; vs is remapped; never-carved pixels refill the raw
+// index table.  new_vs / raw may be NULL (attached carvers only carry pixels).
+__global__ void __launch_bounds__(B200C_ROW_THREADS)
+k_inflate_rows(const uint8_t *rgb, const int *vs, int w0, int w1, int channels, int l, int max_level,
+               uint8_t *new_rgb, int *new_vs, const float *bias, float *new_bias, const float *rigmask,
+               float *new_rigmask, int *raw, int raw_stride)
+{
+    __shared__ int s_warp[33];
+    const int y = blockIdx.x;
+    const size_t in0 = (size_t) y * w0, out0 = (size_t) y * w1;
+    int base = 0, zbase = 0;
+    for (int c0 = 0; c0 < w0; c0 += B200C_ROW_THREADS) {
+        const int x = c0 + threadIdx.x;
+        const bool in = x < w0;
+        const int v = in ? vs[in0 + x] : 1;
+        const bool dup = in && v != 0 && v <= l + max_level - 1 && v >= 2 * max_level - 1;
+        int total, ztotal;
+        int pos = base + block_excl_scan(in ? (dup ? 2 : 1) : 0, s_warp, &total);
+        const int zpos = zbase + block_excl_scan(in && v == 0 ? 1 : 0, s_warp, &ztotal);
+        if (in) {
+            const size_t now = in0 + x;
+            if (dup) {
+                const size_t left = x > 0 ? now - 1 : now;
+                const size_t z0 = out0 + pos;
+                for (int k = 0; k < channels; ++k)
+                    new_rgb[z0 * channels + k] =
+                        (uint8_t) (((int) rgb[left * channels + k] + (int) rgb[now * channels + k]) / 2);
+                if (new_bias) new_bias[z0] = __fmul_rn(__fadd_rn(bias[left], bias[now]), 0.5f);
+                if (new_rigmask) new_rigmask[z0] = __fmul_rn(__fadd_rn(rigmask[left], rigmask[now]), 0.5f);
+                if (new_vs) new_vs[z0] = l - v + max_level;
+                ++pos;
+            }
+            const size_t z0 = out0 + pos;
+            for (int k = 0; k < channels; ++k) new_rgb[z0 * channels + k] = rgb[now * channels + k];
+            if (new_bias) new_bias[z0] = bias[now];
+            if (new_rigmask) new_rigmask[z0] = rigmask[now];
+            if (v != 0) {
+                if (new_vs) new_vs[z0] = v + l - max_level + 1;
+            } else if (raw) {
+                raw[(size_t) y * raw_stride + zpos] = (int) z0;
+            }
+        }
+        base += total;
+        zbase += ztotal;
+    }
+}
+
+// K8 -- A.11 transpose of a (h x w) array of ELEM-byte elements through a 32x32 shared-memory tile.
+template <int ELEM>
+struct Elem {
+    uint8_t b[ELEM];
+};
+template <int ELEM>
+__global__ void __launch_bounds__(256) k_transpose(const uint8_t *in, uint8_t *out, int w, int h)
+{
+    __shared__ Elem<ELEM> tile[32][33];
+    const Elem<ELEM> *src = reinterpret_cast<const Elem<ELEM> *>(in);
+    Elem<ELEM> *dst = reinterpret_cast<Elem<ELEM> *>(out);
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5; // 32 x 8
+    for (int j = ty; j < 32; j += 8) {
+        const int x = x0 + tx, y = y0 + j;
+        if (x < w && y < h) tile[j][tx] = src[(size_t) y * w + x];
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+        const int y = y0 + tx, x = x0 + j; // out is (w x h): out[x][y]
+        if (x < w && y < h) dst[(size_t) x * h + y] = tile[tx][j];
+    }
+}
+
+// K9 -- A.4 preservation / discard bias and rigidity mask from an 8-bit mask layer placed at (x_off, y_off).
+__global__ void k_bias_add(float *bias, int w0, const uint8_t *mask, int channels, int mw, int bias_factor,
+                           int x0, int y0, int x1, int y1, int nx, int ny)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const int has_alpha = (channels == 2 || channels >= 4);
+    const int cc = channels - has_alpha;
+    const size_t px = (size_t) (y - y0) * mw + (x - x0);
+    int sum = 0;
+    for (int k = 0; k < cc; ++k) sum += mask[px * channels + k];
+    float b = (float) (__dmul_rn((double) bias_factor, (double) sum) / (double) (2 * 255 * cc));
+    if (has_alpha) b = __fmul_rn(b, __fdiv_rn((float) mask[(px + 1) * channels - 1], 255.f));
+    float *dst = bias + (size_t) (y + y1) * w0 + (x + x1);
+    *dst = __fadd_rn(*dst, b);
+}
+
+__global__ void k_rigmask_set(float *rigmask, int w0, const uint8_t *mask, int channels, int mw, int x0, int y0,
+                              int x1, int y1, int nx, int ny)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= nx || y >= ny) return;
+    const int has_alpha = (channels == 2 || channels >= 4);
+    const int cc = channels - has_alpha;
+    const size_t px = (size_t) (y - y0) * mw + (x - x0);
+    int sum = 0;
+    for (int k = 0; k < cc; ++k) sum += mask[px * channels + k];
+    float v = __fdiv_rn((float) sum, (float) (255 * cc));
+    if (has_alpha) v = __fmul_rn(v, __fdiv_rn((float) mask[(px + 1) * channels - 1], 255.f));
+    rigmask[(size_t) (y + y1) * w0 + (x + x1)] = v;
+}
+
+// energy read-back in image orientation (internal row i, column j)
+__global__ void k_energy_export(DevP p, int transposed, float *out)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (j >= p.w || i >= p.h) return;
+    const float v = p.en[p.raw[(size_t) i * p.raw_stride + j]];
+    out[transposed ? (size_t) j * p.h + i : (size_t) i * p.w + j] = v;
+}
+
+} // namespace b200c

@@ -1238,3 +1238,58 @@ LQR_PUBLIC void lqr_oracle_update_stats(LqrCarver *r, long out[3])
     out[1] = r->stat_update_cells;
     out[2] = r->stat_update_maxband;
 }
+
+/* state after `n_seams` iterations of the per-seam loop WITHOUT the final inflate, so that the maps can
+ * be compared with the CUDA engine's (mirrors b200c_debug_build); the carver is not resizable afterwards */
+LQR_PUBLIC LqrRetVal lqr_oracle_debug_build(LqrCarver *r, gint n_seams)
+{
+    gint l, depth, lr_switch_interval = 0, first;
+    LQR_CATCH_F(r != NULL && r->active && r->root == NULL);
+    set_width(r, r->w_start - r->max_level + 1);
+    LQR_CATCH(build_emap(r));
+    LQR_CATCH(build_mmap(r));
+    first = r->max_level;
+    depth = first + n_seams;
+    if (r->lr_switch_frequency) lr_switch_interval = (depth - r->max_level - 1) / (gint) r->lr_switch_frequency + 1;
+    for (l = first; l < depth; l++) {
+        build_vpath(r);
+        update_vsmap(r, l + r->max_level - 1);
+        r->level++;
+        r->w--;
+        carve(r);
+        if (r->w > 1) {
+            LQR_CATCH(update_emap(r));
+            if (r->lr_switch_frequency && ((l - r->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0) {
+                r->leftright ^= 1;
+                LQR_CATCH(build_mmap(r));
+            } else {
+                LQR_CATCH(update_mmap(r));
+            }
+        } else {
+            finish_vsmap(r);
+        }
+    }
+    return LQR_OK;
+}
+
+/* what: 0 en, 1 m, 2 least, 3 raw (w_start*h_start, row pitch w_start), 4 vs, 5 vpath_x, 6 bias, 7 rigmask */
+LQR_PUBLIC long lqr_oracle_debug_fetch(LqrCarver *r, gint what, void *out, long cap)
+{
+    const void *src = NULL;
+    long n = (long) r->w0 * r->h0;
+    switch (what) {
+        case 0: src = r->en; break;
+        case 1: src = r->m; break;
+        case 2: src = r->least; break;
+        case 3: src = r->raw_store; n = (long) r->w_start * r->h_start; break;
+        case 4: src = r->vs; break;
+        case 5: src = r->vpath_x; n = r->h; break;
+        case 6: src = r->bias; break;
+        case 7: src = r->rigmask; break;
+        default: return -1;
+    }
+    if (!src) return 0;
+    if (n > cap) n = cap;
+    memcpy(out, src, (size_t) n * 4);
+    return n;
+}
