@@ -21,6 +21,8 @@
 
 #include "b200carve.h"
 #include "carver_kernels.cuh"
+#include "mmap_update_fast.cuh"
+#include "vpath_mmap_tiled.cuh"
 
 using namespace b200c;
 
@@ -28,6 +30,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long> g_launches{0};
+std::atomic<unsigned long long> g_update_cells{0};
 
 int fail(int code, const char *what, cudaError_t e = cudaSuccess)
 {
@@ -99,6 +102,8 @@ void drain_stage(StageStat &st)
 
 int g_device_tls_default = 0;
 thread_local int g_device = -1;
+thread_local cudaStream_t g_ext_stream = nullptr;
+thread_local bool g_use_ext_stream = false;
 
 } // namespace
 
@@ -117,6 +122,11 @@ struct B200Carver {
     float *en = nullptr, *m = nullptr, *bias = nullptr, *rigmask = nullptr;
     int *least = nullptr, *raw = nullptr;
     int *vpath = nullptr, *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
+    int *err_d = nullptr;                     // device error word (see DevP::err)
+    unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
+    bool owns_stream = true;
+    int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
+    bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
 
     float rigidity = 0.f;
     int delta_x = 1;
@@ -194,6 +204,8 @@ DevP view(const B200Carver *c)
     p.vpath_x = c->vpath_x;
     p.nrg_xmin = c->nrg_xmin;
     p.nrg_xmax = c->nrg_xmax;
+    p.err = c->err_d;
+    p.cells = c->cells_d;
     return p;
 }
 
@@ -257,8 +269,43 @@ int build_emap(B200Carver *c)
     return B200C_OK;
 }
 
+constexpr int kUpdatePrefetchRows = 6; // KP of k_mmap_update_fast
+
+bool fast_path(const B200Carver *c) { return !c->generic && c->delta_x <= UF_MAX_DELTA; }
+
+int raise_smem_limits()
+{
+    static std::once_flag once;
+    static cudaError_t err = cudaSuccess;
+    std::call_once(once, [] {
+        auto set = [](const void *fn, size_t bytes) {
+            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+            if (e != cudaSuccess && err == cudaSuccess) err = e;
+        };
+        set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, false>, UfLayout<kUpdatePrefetchRows, false>::bytes);
+        set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, true>, UfLayout<kUpdatePrefetchRows, true>::bytes);
+        set((const void *) k_vpath_fast, vp_smem_bytes());
+        set((const void *) k_mmap_full_tile, 200 * 1024);
+    });
+    if (err != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", err);
+    return B200C_OK;
+}
+
 int build_mmap(B200Carver *c)
 {
+    if (fast_path(c)) {
+        const MfGeom g = mf_geometry(c->delta_x, c->w, c->rigidity != 0.f && c->rigmask != nullptr);
+        if (g.T <= 1024 && g.smem <= 200 * 1024) {
+            B_TRY(raise_smem_limits());
+            const int grid = (c->w + g.S - 1) / g.S;
+            const int launches = (c->h + g.K - 1) / g.K;
+            StageScope sc("mmap_full", c->stream, launches);
+            const DevP p = view(c);
+            for (int y0 = 0; y0 < c->h; y0 += g.K)
+                k_mmap_full_tile<<<grid, g.T, g.smem, c->stream>>>(p, y0, g.K, g.S);
+            return check_launch("k_mmap_full_tile");
+        }
+    }
     StageScope sc("mmap_full", c->stream);
     k_mmap_full<<<1, 1024, 0, c->stream>>>(view(c));
     return check_launch("k_mmap_full");
@@ -319,9 +366,14 @@ int inflate(B200Carver *c, int l)
 int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
 {
     cudaStream_t s = c->stream;
+    const bool fast = fast_path(c);
+    if (fast) B_TRY(raise_smem_limits());
     {
         StageScope sc("vpath", s);
-        k_vpath<<<1, 1024, 0, s>>>(view(c));
+        if (fast)
+            k_vpath_fast<<<1, VP_THREADS, vp_smem_bytes(), s>>>(view(c));
+        else
+            k_vpath<<<1, 1024, 0, s>>>(view(c));
         B_TRY(check_launch("k_vpath"));
     }
     const int vs_value = l + c->max_level - 1;
@@ -336,7 +388,10 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (c->w > 1) {
         {
             StageScope sc("energy_band", s);
-            k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
+            if (fast)
+                k_energy_band_pre<<<(c->h + 7) / 8, 256, 0, s>>>(view(c), 2 * kUpdatePrefetchRows, c->pre_lo, c->pre_hi);
+            else
+                k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
             B_TRY(check_launch("k_energy_band"));
         }
         c->nrg_uptodate = true;
@@ -345,7 +400,14 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             B_TRY(build_mmap(c));
         } else {
             StageScope sc("mmap_update", s);
-            k_mmap_update<<<1, 512, 0, s>>>(view(c));
+            if (fast && c->rigidity != 0.f)
+                k_mmap_update_fast<kUpdatePrefetchRows, true>
+                    <<<1, UF_THREADS, UfLayout<kUpdatePrefetchRows, true>::bytes, s>>>(view(c), c->pre_lo, c->pre_hi);
+            else if (fast)
+                k_mmap_update_fast<kUpdatePrefetchRows, false>
+                    <<<1, UF_THREADS, UfLayout<kUpdatePrefetchRows, false>::bytes, s>>>(view(c), c->pre_lo, c->pre_hi);
+            else
+                k_mmap_update<<<1, 512, 0, s>>>(view(c));
             B_TRY(check_launch("k_mmap_update"));
         }
     } else {
@@ -368,6 +430,17 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
             if (progress(user, l - first)) return fail(B200C_CANCEL, "cancelled by progress callback");
         }
         B_TRY(seam_iteration(c, l, lr_switch_interval));
+    }
+    {
+        // the staged kernels check their own window invariants on the device; a violation is a hard error
+        int err = 0;
+        CU_TRY(cudaMemcpyAsync(&err, c->err_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+        if (err) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "seam loop: device invariant violated (code %d)", err);
+            return fail(B200C_ERROR, msg);
+        }
     }
     if (!do_inflate) return B200C_OK;
     B_TRY(inflate(c, depth - 1));
@@ -510,6 +583,10 @@ int transpose(B200Carver *c)
         dfree(c, c->vpath_x);
         dfree(c, c->nrg_xmin);
         dfree(c, c->nrg_xmax);
+        dfree(c, c->pre_lo);
+        dfree(c, c->pre_hi);
+        B_TRY(dalloc(c, &c->pre_lo, (size_t) c->h, true));
+        B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->vpath, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
@@ -555,16 +632,24 @@ B200Carver *carver_new_common(int width, int height, int channels)
     static std::once_flag once;
     std::call_once(once, [] {
         const char *t = getenv("B200C_TIMING");
-        g_timing = t && atoi(t) != 0;
+        if (t) g_timing = atoi(t) != 0;
     });
     B200Carver *c = new (std::nothrow) B200Carver();
     if (!c) {
         fail(B200C_NOMEM, "carver_new: host allocation");
         return nullptr;
     }
+    {
+        const char *g = getenv("B200C_GENERIC");
+        c->generic = g && atoi(g) != 0;
+    }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
+    if (g_use_ext_stream) {
+        c->stream = g_ext_stream;
+        c->owns_stream = false;
+    }
     if (cudaSetDevice(c->device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        (c->owns_stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)) {
         fail(B200C_ERROR, "carver_new: cannot create stream", cudaGetLastError());
         delete c;
         return nullptr;
@@ -661,7 +746,7 @@ void b200c_carver_destroy(B200Carver *c)
     cudaSetDevice(c->device);
     for (B200Carver *a : c->attached) b200c_carver_destroy(a);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    const bool owns_stream = c->root == nullptr; // attached carvers run on their root's queue
+    const bool owns_stream = c->root == nullptr && c->owns_stream; // attached carvers run on their root's queue
     dfree(c, c->rgb);
     if (!c->root) dfree(c, c->vs);
     dfree(c, c->en);
@@ -674,6 +759,16 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->vpath_x);
     dfree(c, c->nrg_xmin);
     dfree(c, c->nrg_xmax);
+    dfree(c, c->pre_lo);
+    dfree(c, c->pre_hi);
+    dfree(c, c->err_d);
+    if (c->cells_d) {
+        unsigned long long n = 0;
+        if (cudaMemcpyAsync(&n, c->cells_d, sizeof n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+            cudaStreamSynchronize(c->stream) == cudaSuccess)
+            g_update_cells += n;
+    }
+    dfree(c, c->cells_d);
     dfree(c, c->rigmap_d);
     if (c->host_out) cudaFreeHost(c->host_out);
     if (c->stream) {
@@ -696,6 +791,10 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->pre_lo, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->err_d, 1, true));
+    B_TRY(dalloc(c, &c->cells_d, 1, true));
     c->delta_x = delta_x;
     c->rigidity = rigidity;
     c->rigmap_h.assign(2 * delta_x + 1, 0.f);
@@ -717,7 +816,8 @@ int b200c_carver_attach(B200Carver *root, B200Carver *aux)
     CU_TRY(cudaStreamSynchronize(aux->stream));
     dfree(aux, aux->vs);
     CU_TRY(cudaStreamSynchronize(aux->stream));
-    cudaStreamDestroy(aux->stream);
+    if (aux->owns_stream) cudaStreamDestroy(aux->stream);
+    aux->owns_stream = false;
     aux->stream = root->stream; // one queue per carver family keeps every structural op ordered
     aux->vs = root->vs;
     aux->root = root;
@@ -936,6 +1036,17 @@ int b200c_carver_true_energy(B200Carver *c, float *out_host)
     CU_TRY(cudaStreamSynchronize(c->stream));
     return B200C_OK;
 }
+
+int b200c_set_stream(void *stream)
+{
+    g_ext_stream = (cudaStream_t) stream;
+    g_use_ext_stream = stream != nullptr;
+    return B200C_OK;
+}
+
+void b200c_set_timing(int on) { g_timing = on != 0; }
+
+unsigned long long b200c_update_cells(void) { return g_update_cells.load(); }
 
 int b200c_carver_sync(B200Carver *c)
 {

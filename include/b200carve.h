@@ -90,6 +90,15 @@ B200C_API int b200c_carver_vmap(B200Carver *c, int *out_host);
 /* lqr_carver_get_true_energy: out = w*h floats in image orientation (carver must be in reference state) */
 B200C_API int b200c_carver_true_energy(B200Carver *c, float *out_host);
 
+/* carvers created afterwards on this thread queue their work on `stream` (a cudaStream_t; NULL restores the
+ * default of one private non-blocking stream per carver).  Lets a host program bracket the engine's kernels
+ * with its own CUDA events (bench.py passes torch's current stream). */
+B200C_API int b200c_set_stream(void *stream);
+/* switches the per-stage CUDA-event timing on/off (same as B200C_TIMING=1 in the environment) */
+B200C_API void b200c_set_timing(int on);
+/* cumulative count of band cells the incremental DP visited in this process (algorithmic-bytes accounting) */
+B200C_API unsigned long long b200c_update_cells(void);
+
 /* waits for all queued device work of this carver */
 B200C_API int b200c_carver_sync(B200Carver *c);
 

@@ -93,6 +93,24 @@ CASES = [
     case("tiny_3x3", "iid", 3, 3, 1, V(new_width=2, new_height=2, output_seams=True)),
     case("wide_band", "smooth_noise", 700, 40, 4, V(new_width=690, new_height=40, output_seams=True)),
 ]
+# medium sizes: exercise the staged/windowed kernels (window prediction, capacity fallback, chunked backtrack)
+CASES += [
+    case("mid_dx8_fallback", "smooth_noise", 1500, 160, 4, V(new_width=1494, new_height=160, delta_x=8, output_seams=True)),
+    case("mid_dx3_rigmask", "smooth_noise", 900, 200, 4,
+         V(new_width=888, new_height=200, delta_x=3, rigidity=5.0, output_seams=True), rig=("band", 900, 200, 4, 0, 0)),
+    case("mid_null_dx0", "smooth_noise", 300, 100, 4,
+         V(new_width=290, new_height=100, delta_x=0, nrg_func=6, output_seams=True), pres=("noiseB", 300, 100, 2, 0, 0)),
+    case("mid_null_dx1", "smooth_noise", 300, 100, 4,
+         V(new_width=290, new_height=100, delta_x=1, nrg_func=6, output_seams=True), pres=("noiseB", 300, 100, 2, 0, 0)),
+    case("mid_iid_dx2", "iid", 1200, 150, 4, V(new_width=1190, new_height=150, delta_x=2, output_seams=True)),
+    case("mid_dx32", "smooth_noise", 400, 120, 3, V(new_width=394, new_height=120, delta_x=32, output_seams=True)),
+    case("mid_dx40_generic", "smooth_noise", 400, 120, 3, V(new_width=396, new_height=120, delta_x=40, output_seams=True)),
+    case("tall", "smooth_noise", 60, 900, 4, V(new_width=52, new_height=900, output_seams=True)),
+    case("tall_dx0", "smooth_noise", 60, 500, 4, V(new_width=54, new_height=500, delta_x=0, output_seams=True)),
+    case("wide_shrink_h", "smooth_noise", 900, 60, 4, V(new_width=900, new_height=52, output_seams=True)),
+    case("mid_flat_ties", "flat", 500, 300, 4, V(new_width=470, new_height=300, output_seams=True)),
+    case("mid_enlarge", "smooth_noise", 640, 360, 4, V(new_width=700, new_height=380, output_seams=True)),
+]
 for _ef in range(7):
     CASES.append(case(f"energy_fn_{_ef}", "smooth_noise", 64, 48, 4,
                       V(new_width=52, new_height=44, nrg_func=_ef, output_seams=True), alpha="random"))

@@ -28,13 +28,26 @@ def engine(pkg, product):
     return eng
 
 
+@pytest.fixture(params=["fast", "generic"])
+def kernel_mode(request):
+    """Both kernel sets must match the oracle: the staged / windowed / tiled sm_100a kernels ("fast", the
+    default) and the generic single-CTA kernels they fall back to (B200C_GENERIC=1, read at carver creation)."""
+    old = os.environ.get("B200C_GENERIC")
+    os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
+    yield request.param
+    if old is None:
+        os.environ.pop("B200C_GENERIC", None)
+    else:
+        os.environ["B200C_GENERIC"] = old
+
+
 def test_device_is_blackwell(engine):
     engine.b200c_device_count.restype = C.c_int
     assert engine.b200c_device_count() >= 1
 
 
 @pytest.mark.parametrize("cs", CASES, ids=CASE_IDS)
-def test_case_parity(product, oracle, cs):
+def test_case_parity(product, oracle, cs, kernel_mode):
     want = cases.run_case(oracle, cs)
     got = cases.run_case(product, cs)
     diffs = cases.results_equal(got, want)
@@ -66,7 +79,7 @@ def _fetch(fn, handle, what, n, dtype):
 
 @pytest.mark.parametrize("n_seams,delta_x,rigidity,freq", [(0, 1, 0.0, 0), (1, 1, 0.0, 0), (7, 1, 0.0, 2),
                                                            (9, 2, 0.3, 2), (12, 3, 0.0, 0)])
-def test_internal_maps_after_k_seams(product, oracle, engine, n_seams, delta_x, rigidity, freq):
+def test_internal_maps_after_k_seams(product, oracle, engine, n_seams, delta_x, rigidity, freq, kernel_mode):
     """Energy, cumulative m-map (floats, bit-exact), parent map, index table, visibility map and the last
     seam after k iterations of the per-seam loop, before any inflate."""
     w, h = 150, 90
@@ -103,7 +116,7 @@ def test_internal_maps_after_k_seams(product, oracle, engine, n_seams, delta_x, 
     cp.destroy()
 
 
-def test_interactive_sequence(product, oracle):
+def test_interactive_sequence(product, oracle, kernel_mode):
     """interface_I.c:504-529,615-633: one carver, many resizes, flatten in between, seam map dumps."""
     img = synth.smooth_noise(120, 90, 4)
     outs = []
