@@ -23,6 +23,7 @@
 #include "carver_kernels.cuh"
 #include "mmap_update_fast.cuh"
 #include "vpath_mmap_tiled.cuh"
+#include "mmap_update_spec.cuh"
 
 using namespace b200c;
 
@@ -127,6 +128,7 @@ struct B200Carver {
     bool owns_stream = true;
     int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
+    int update_kernel = 3;                    // B200C_UPDATE=2: staged kernel instead of the speculative one
 
     float rigidity = 0.f;
     int delta_x = 1;
@@ -284,6 +286,8 @@ int raise_smem_limits()
         };
         set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, false>, UfLayout<kUpdatePrefetchRows, false>::bytes);
         set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, true>, UfLayout<kUpdatePrefetchRows, true>::bytes);
+        set((const void *) k_mmap_update_spec<true>, us_smem_bytes());
+        set((const void *) k_mmap_update_spec<false>, us_smem_bytes());
         set((const void *) k_vpath_fast, vp_smem_bytes());
         set((const void *) k_mmap_full_tile, 200 * 1024);
     });
@@ -400,7 +404,11 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             B_TRY(build_mmap(c));
         } else {
             StageScope sc("mmap_update", s);
-            if (fast && c->rigidity != 0.f)
+            if (fast && c->rigidity == 0.f && c->update_kernel == 3 && c->delta_x == 1)
+                k_mmap_update_spec<true><<<1, US_THREADS, us_smem_bytes(), s>>>(view(c));
+            else if (fast && c->rigidity == 0.f && c->update_kernel == 3)
+                k_mmap_update_spec<false><<<1, US_THREADS, us_smem_bytes(), s>>>(view(c));
+            else if (fast && c->rigidity != 0.f)
                 k_mmap_update_fast<kUpdatePrefetchRows, true>
                     <<<1, UF_THREADS, UfLayout<kUpdatePrefetchRows, true>::bytes, s>>>(view(c), c->pre_lo, c->pre_hi);
             else if (fast)
@@ -642,6 +650,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
     {
         const char *g = getenv("B200C_GENERIC");
         c->generic = g && atoi(g) != 0;
+        const char *u = getenv("B200C_UPDATE");
+        if (u && atoi(u) == 2) c->update_kernel = 2;
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
     if (g_use_ext_stream) {

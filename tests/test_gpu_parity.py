@@ -28,17 +28,20 @@ def engine(pkg, product):
     return eng
 
 
-@pytest.fixture(params=["fast", "generic"])
+@pytest.fixture(params=["fast", "staged", "generic"])
 def kernel_mode(request):
-    """Both kernel sets must match the oracle: the staged / windowed / tiled sm_100a kernels ("fast", the
-    default) and the generic single-CTA kernels they fall back to (B200C_GENERIC=1, read at carver creation)."""
-    old = os.environ.get("B200C_GENERIC")
+    """Every kernel set must match the oracle: "fast" (default: warp-specialised speculative band DP, windowed
+    backtrack, tiled full DP), "staged" (B200C_UPDATE=2: the cp.async-staged band DP that also serves rigidity),
+    and "generic" (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at carver creation."""
+    old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_UPDATE")}
     os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
+    os.environ["B200C_UPDATE"] = "2" if request.param == "staged" else "3"
     yield request.param
-    if old is None:
-        os.environ.pop("B200C_GENERIC", None)
-    else:
-        os.environ["B200C_GENERIC"] = old
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def test_device_is_blackwell(engine):
