@@ -1,27 +1,28 @@
-// mmap_update_spec.cuh -- K2b v3: incremental m-map DP (liblqr lqr_carver_update_mmap) as a
+// mmap_update_spec.cuh -- K2b: incremental m-map DP (liblqr lqr_carver_update_mmap) as a
 // warp-specialised, verified-speculative kernel.  One CTA of 13 warps:
 //
-//   * 8 COMPUTE warps walk the rows.  Per row a thread does one cell (up to 4 for very wide bands) entirely
+//   * 8 COMPUTE warps walk the rows.  Per row a thread does one cell (2 or 4 for very wide bands) entirely
 //     from shared memory: parents from the previous row's ring (mrow/zrow), the cell's own id / energy /
 //     old m / old parent from a tile the producers staged.  They do NOT wait for the exact band limits of
-//     the row: they process a slightly wider ACTIVE range (the limits verified two rows earlier, grown by
-//     2*delta_x and the energy bands in between) and apply the keep-old rule to every cell in it.
-//   * 1 CONTROL warp runs one row behind.  From the ballot words of "value changed" cells it recomputes
-//     liblqr's exact band limits (leading kept run advances x_min, trailing kept run pulls x_max back) and
-//     VERIFIES the speculation: every changed cell must lie inside the exact band.  It publishes the active
-//     range two rows ahead.  If the algorithm's band logic is sound -- a cell outside the band has unchanged
+//     the row: they recompute a slightly wider ACTIVE range (the limits verified two rows earlier, grown by
+//     2*delta_x and the energy bands in between), apply the keep-old rule to every cell in it and leave the
+//     result in place in the tile, plus one ballot word per warp marking the cells whose value changed.
+//   * 1 CONTROL warp runs one row behind.  From the ballot words it recomputes liblqr's exact band limits
+//     (the leading kept run advances x_min, a trailing kept run pulls x_max back) and VERIFIES the
+//     speculation: every changed cell must lie inside the exact band.  It publishes the active / guard
+//     ranges two rows ahead.  If the algorithm's band logic is sound -- a cell outside the band has unchanged
 //     parents, so recomputing it reproduces the stored value within the keep tolerance -- the check never
-//     fires.  If it ever does, nothing wrong has been written: results are COMMITTED to HBM by the compute
-//     threads two rows late, only for verified rows, and the kernel finishes the remaining rows with the
-//     exact generic row loop from the control warp's exact limits.  Results are therefore bit-identical to
-//     liblqr's band algorithm in every case.
-//   * 4 PRODUCER warps gather whole chunks of rows (8 rows, or 4 when the window is wider than 512 columns)
-//     two chunks ahead with cp.async: pixel ids through the raw index table first, then en / m / least
-//     through those ids.  A chunk's column window is a provable superset of every band (and active range,
-//     and parent halo) its rows can have, computed from the limits verified at planning time.
+//     fires.  If it ever does, nothing wrong has reached HBM: rows are COMMITTED only after verification,
+//     and the kernel finishes the remaining rows with the exact generic row loop from the control warp's
+//     exact limits.  Results are bit-identical to liblqr's band algorithm in every case.
+//   * 4 PRODUCER warps work around the chain: two chunks AHEAD they gather whole chunks of rows (8 rows, or
+//     4 when the window is wider than 512 columns) with cp.async -- pixel ids through the raw index table
+//     first, then en / m / least through those ids -- and one chunk BEHIND they commit the verified results
+//     (m, least of the changed cells) from the tile to HBM.  A chunk's column window is a provable superset
+//     of every band, active range, guard range and parent halo its rows can have.
 //
-// Dependent chain per row on the compute warps: LDS parents -> compare/select -> FADD -> keep test -> STS
-// -> named barrier (288 threads).  No global memory, no band bookkeeping, no window arithmetic on the chain.
+// Dependent chain per row on the compute warps: LDS parents -> min/select -> FADD -> keep test -> STS ->
+// named barrier (288 threads).  No global memory, no band bookkeeping, no commit, no window arithmetic.
 #pragma once
 #include "carver_kernels.cuh"
 #include "mmap_update_fast.cuh"
@@ -36,15 +37,117 @@ namespace b200c {
 #define US_TILE 4096
 #define US_RW 2048
 #define US_RWM (US_RW - 1)
-#define US_NSLOT 4
-#define US_MAXCW (US_CT * US_NSLOT)
+#define US_MAXROWS 8
+#define US_MAXCW (US_CT * 4)
 
+// shared-memory words after the tiles and row rings
+#define US_NKW (2 * US_MAXROWS * 32) // ballot words  [chunk parity][row][32]
+#define US_RIW (2 * US_MAXROWS * 4)  // row info      [chunk parity][row]{guard base, nslots, -, -}
 static constexpr size_t us_smem_bytes()
 {
-    return sizeof(int) * ((size_t) 3 * US_TILE + 6 * US_TILE + 4 * US_RW + 64 + 8 + 16 + 8 + 8 + 128);
+    return sizeof(int) * ((size_t) 3 * US_TILE + 6 * US_TILE + 4 * US_RW + US_NKW + US_RIW + 16 + 16 + 8 + 8 + 128);
 }
 
 __device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(US_CT + 32) : "memory"); }
+
+// One row of the compute warps.  Thread t handles the columns gr_lo + t + 256*j (j < NS) of the row's guard
+// range [gr_lo, gr_hi]: cells inside the active range are recomputed (parents from the previous row's ring),
+// the others only forward their old value / id to the ring for the next row's parents.  The new value and
+// parent are left in place in the tile (mt / lt) for the commit; `changed` bits go to nkrow.
+template <int NS, bool D1>
+__device__ __forceinline__ void us_row(const DevP &p, int y, int rbm, const int *__restrict__ zt,
+                                       const float *__restrict__ et, float *__restrict__ mt, int *__restrict__ lt,
+                                       float *mrow, int *zrow, int cur, int prev, int act_lo, int act_hi, int gr_lo,
+                                       int gr_hi, unsigned *nkrow, int tid, int lane, int warp)
+{
+    const int w = p.w;
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int x = gr_lo + j * US_CT + tid;
+        bool changed = false;
+        if (x <= gr_hi) {
+            const int idx = rbm + x;
+            const int rb = x & US_RWM;
+            const int z = zt[idx];
+            const float mo = mt[idx];
+            float val = mo;
+            if (x >= act_lo && x <= act_hi) {
+                const float e = et[idx];
+                if (y == 0) {
+                    val = e; // row 0: m = en over the (exact) band
+                    changed = true;
+                    mt[idx] = e;
+                } else {
+                    float best;
+                    int parent;
+                    if (D1) {
+                        const float inf = __int_as_float(0x7f800000);
+                        const float m0 = mrow[prev + rb];
+                        const int z0 = zrow[prev + rb];
+                        float ml = mrow[prev + ((rb - 1) & US_RWM)];
+                        const int zl = zrow[prev + ((rb - 1) & US_RWM)];
+                        float mr = mrow[prev + ((rb + 1) & US_RWM)];
+                        const int zr = zrow[prev + ((rb + 1) & US_RWM)];
+                        // left-to-right scan with strict '<' == leftmost minimum; ties go right when leftright == 1.
+                        // (all m are finite: an out-of-image neighbour is replaced by +inf and can never win)
+                        ml = x > 0 ? ml : inf;
+                        mr = x < w - 1 ? mr : inf;
+                        best = fminf(fminf(ml, m0), mr);
+                        if (p.leftright)
+                            parent = mr == best ? zr : (m0 == best ? z0 : zl);
+                        else
+                            parent = ml == best ? zl : (m0 == best ? z0 : zr);
+                    } else {
+                        const int D = p.delta_x;
+                        const int dlo = max(-x, -D), dhi = min(w - 1 - x, D);
+                        int bdx = dlo;
+                        best = mrow[prev + ((x + dlo) & US_RWM)];
+                        for (int dx = dlo + 1; dx <= dhi; ++dx) {
+                            const float cand = mrow[prev + ((x + dx) & US_RWM)];
+                            if (cand < best || (cand == best && p.leftright == 1)) {
+                                best = cand;
+                                bdx = dx;
+                            }
+                        }
+                        parent = zrow[prev + ((x + bdx) & US_RWM)];
+                    }
+                    const float new_m = __fadd_rn(e, best);
+                    const bool keep = (lt[idx] == parent) && ((double) fabsf(__fsub_rn(mo, new_m)) < 1e-5);
+                    if (!keep) {
+                        val = new_m;
+                        changed = true;
+                        mt[idx] = new_m;
+                        lt[idx] = parent;
+                    }
+                }
+            }
+            mrow[cur + rb] = val;
+            zrow[cur + rb] = z;
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, changed);
+        if (lane == 0) nkrow[j * US_NCW + warp] = word;
+    }
+}
+
+// commit rows [r_begin, r_end) of a chunk: m (and least, below row 0) of every changed cell, tile -> HBM
+__device__ __forceinline__ void us_commit(const DevP &p, const int *dsc, const int *zt, const float *mt, const int *lt,
+                                          const unsigned *nkc, const int *ric, int r_begin, int r_end, int t, int nt)
+{
+    const int y0 = dsc[0], clo = dsc[2], cw = dsc[3];
+    for (int r = r_begin; r < r_end; ++r) {
+        const int gb = ric[r * 4 + 0], ns = ric[r * 4 + 1];
+        const int ncols = ns * US_CT;
+        const int rbm = r * cw - clo;
+        for (int c = t; c < ncols; c += nt) {
+            if ((nkc[r * 32 + (c >> 5)] >> (c & 31)) & 1u) {
+                const int idx = rbm + gb + c;
+                const int z = zt[idx];
+                p.m[z] = mt[idx];
+                if (y0 + r > 0) p.least[z] = lt[idx];
+            }
+        }
+    }
+}
 
 template <bool D1>
 __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
@@ -52,32 +155,32 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
     extern __shared__ __align__(16) unsigned char us_smem[];
     int *ztile = reinterpret_cast<int *>(us_smem);                    // [3][TILE] pixel ids
     float *etile = reinterpret_cast<float *>(ztile + 3 * US_TILE);    // [2][TILE] energy
-    float *mtile = etile + 2 * US_TILE;                               // [2][TILE] old m
-    int *ltile = reinterpret_cast<int *>(mtile + 2 * US_TILE);        // [2][TILE] old parent
+    float *mtile = etile + 2 * US_TILE;                               // [2][TILE] old m -> new m of changed cells
+    int *ltile = reinterpret_cast<int *>(mtile + 2 * US_TILE);        // [2][TILE] old parent -> new parent
     float *mrow = reinterpret_cast<float *>(ltile + 2 * US_TILE);     // [2][RW] previous / current row values
     int *zrow = reinterpret_cast<int *>(mrow + 2 * US_RW);            // [2][RW] previous / current row ids
-    unsigned *nk = reinterpret_cast<unsigned *>(zrow + 2 * US_RW);    // [2][32] "changed" ballot words
-    int *pub = reinterpret_cast<int *>(nk + 64);                      // [2][4] act_lo, act_hi, fail_row
-    int *cdesc = pub + 8;                                             // [4][4] y0, rows, clo, cw
+    unsigned *nk = reinterpret_cast<unsigned *>(zrow + 2 * US_RW);    // [2][8][32] "changed" ballot words
+    int *rinfo = reinterpret_cast<int *>(nk + US_NKW);                // [2][8][4] guard base, slots
+    int *pub = rinfo + US_RIW;                                        // [2][8] act_lo, act_hi, fail_row, -, gr_lo, gr_hi
+    int *cdesc = pub + 16;                                            // [4][4] y0, rows, clo, cw
     int *clim = cdesc + 16;                                           // [2][4] x_min, x_max, y_v at chunk starts
-    int *misc = clim + 8;                                             // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax
-    int *s_red = misc + 8;                                            // [128] generic fallback scratch
+    volatile int *misc = clim + 8;                                    // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax,
+                                                                      //     4 last chunk entered, 5 rows verified
+    int *s_red = const_cast<int *>(misc) + 8;                         // [128] generic fallback scratch
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int D = p.delta_x, w = p.w, h = p.h, lr = p.leftright;
+    const int D = p.delta_x, w = p.w, h = p.h;
     const bool is_compute = tid < US_CT, is_control = warp == US_NCW;
 
     if (tid == 0) {
         misc[0] = 0;
         misc[1] = h;
+        misc[4] = -1;
+        misc[5] = 0;
     }
 
     if (is_compute) {
         // =============================================================================== COMPUTE
-        int hz1[US_NSLOT], hp1[US_NSLOT], hz2[US_NSLOT], hp2[US_NSLOT];
-        float hm1[US_NSLOT], hm2[US_NSLOT];
-#pragma unroll
-        for (int j = 0; j < US_NSLOT; ++j) hz1[j] = hz2[j] = -1, hp1[j] = hp2[j] = -2, hm1[j] = hm2[j] = 0.f;
         __syncthreads(); // start: prologue chunks staged, pub[0] published
         int y = 0;
         bool failed = false;
@@ -85,128 +188,51 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
-            const int nslot = (cw + US_CT - 1) / US_CT;
+            if (tid == 0) misc[4] = k;
             const int *zt = ztile + (k % 3) * US_TILE;
             const float *et = etile + (k & 1) * US_TILE;
-            const float *mt = mtile + (k & 1) * US_TILE;
-            const int *lt = ltile + (k & 1) * US_TILE;
+            float *mt = mtile + (k & 1) * US_TILE;
+            int *lt = ltile + (k & 1) * US_TILE;
+            unsigned *nkc = nk + (k & 1) * US_MAXROWS * 32;
+            int *ric = rinfo + (k & 1) * US_MAXROWS * 4;
             for (int r = 0; r < rows; ++r, ++y) {
                 const int par = y & 1;
-                const int act_lo = pub[par * 4 + 0], act_hi = pub[par * 4 + 1], fail_row = pub[par * 4 + 2];
-                if (fail_row <= y - 2) {
+                const int4 pa = *reinterpret_cast<const int4 *>(pub + par * 8);
+                const int2 pg = *reinterpret_cast<const int2 *>(pub + par * 8 + 4);
+                if (pa.z <= y - 2) {
                     failed = true;
                     break;
                 }
-                // commit the results of row y-2 (verified by now), then age the history
-#pragma unroll
-                for (int j = 0; j < US_NSLOT; ++j) {
-                    if (hz2[j] >= 0) {
-                        p.m[hz2[j]] = hm2[j];
-                        if (hp2[j] != -2) p.least[hz2[j]] = hp2[j];
-                    }
-                    hz2[j] = hz1[j];
-                    hm2[j] = hm1[j];
-                    hp2[j] = hp1[j];
-                    hz1[j] = -1;
-                }
+                // the guard range always lies inside the staged window (see the planning bound); clamp anyway
+                const int gr_lo = max(pg.x, clo), gr_hi = min(pg.y, clo + cw - 1);
+                const int act_lo = max(pa.x, gr_lo), act_hi = min(pa.y, gr_hi);
+                const int gw = gr_hi - gr_lo + 1;
                 const int cur = par * US_RW, prev = (par ^ 1) * US_RW;
-                const int rbase = r * cw;
-#pragma unroll
-                for (int j = 0; j < US_NSLOT; ++j) {
-                    if (j < nslot) {
-                        const int c = j * US_CT + tid;
-                        bool changed = false;
-                        if (c < cw) {
-                            const int x = clo + c;
-                            const int rb = x & US_RWM;
-                            const int z = zt[rbase + c];
-                            const float mo = mt[rbase + c];
-                            float val = mo;
-                            if (x >= act_lo && x <= act_hi) {
-                                const float e = et[rbase + c];
-                                if (y == 0) {
-                                    val = e;
-                                    hz1[j] = z;
-                                    hm1[j] = e;
-                                    hp1[j] = -2;
-                                } else {
-                                    float best;
-                                    int parent;
-                                    if (D1) {
-                                        const float m0 = mrow[prev + rb];
-                                        const int z0 = zrow[prev + rb];
-                                        const float ml = mrow[prev + ((rb - 1) & US_RWM)];
-                                        const int zl = zrow[prev + ((rb - 1) & US_RWM)];
-                                        const float mr = mrow[prev + ((rb + 1) & US_RWM)];
-                                        const int zr = zrow[prev + ((rb + 1) & US_RWM)];
-                                        best = m0;
-                                        parent = z0;
-                                        if (x > 0) {
-                                            best = ml;
-                                            parent = zl;
-                                            if (m0 < best || (m0 == best && lr == 1)) {
-                                                best = m0;
-                                                parent = z0;
-                                            }
-                                        }
-                                        if (x < w - 1 && (mr < best || (mr == best && lr == 1))) {
-                                            best = mr;
-                                            parent = zr;
-                                        }
-                                    } else {
-                                        const int dlo = max(-x, -D), dhi = min(w - 1 - x, D);
-                                        int bdx = dlo;
-                                        best = mrow[prev + ((x + dlo) & US_RWM)];
-                                        for (int dx = dlo + 1; dx <= dhi; ++dx) {
-                                            const float cand = mrow[prev + ((x + dx) & US_RWM)];
-                                            if (cand < best || (cand == best && lr == 1)) {
-                                                best = cand;
-                                                bdx = dx;
-                                            }
-                                        }
-                                        parent = zrow[prev + ((x + bdx) & US_RWM)];
-                                    }
-                                    const float new_m = __fadd_rn(e, best);
-                                    const bool keep =
-                                        (lt[rbase + c] == parent) && ((double) fabsf(__fsub_rn(mo, new_m)) < 1e-5);
-                                    if (!keep) {
-                                        val = new_m;
-                                        changed = true;
-                                        hz1[j] = z;
-                                        hm1[j] = new_m;
-                                        hp1[j] = parent;
-                                    }
-                                }
-                            }
-                            mrow[cur + rb] = val;
-                            zrow[cur + rb] = z;
-                        }
-                        const unsigned word = __ballot_sync(0xffffffffu, changed);
-                        if (lane == 0) nk[par * 32 + j * US_NCW + warp] = word;
-                    }
+                const int rbm = r * cw - clo;
+                unsigned *nkrow = nkc + r * 32;
+                const int ns = gw <= US_CT ? 1 : (gw <= 2 * US_CT ? 2 : 4);
+                if (tid == 0) {
+                    ric[r * 4 + 0] = gr_lo;
+                    ric[r * 4 + 1] = ns;
                 }
+                if (ns == 1)
+                    us_row<1, D1>(p, y, rbm, zt, et, mt, lt, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid,
+                                  lane, warp);
+                else if (ns == 2)
+                    us_row<2, D1>(p, y, rbm, zt, et, mt, lt, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid,
+                                  lane, warp);
+                else
+                    us_row<4, D1>(p, y, rbm, zt, et, mt, lt, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid,
+                                  lane, warp);
                 bar_rows();
             }
             if (failed) break;
             __syncthreads(); // chunk end: next chunk's tiles are complete
         }
         if (!failed) {
-            // drain: rows y_end-2 and y_end-1 still wait for verification
+            // drain: the last two rows still wait for verification
             for (int d = 0; d < 2; ++d, ++y) {
-                const int par = y & 1;
-                const int fail_row = pub[par * 4 + 2];
-                if (fail_row <= y - 2) break;
-#pragma unroll
-                for (int j = 0; j < US_NSLOT; ++j) {
-                    if (hz2[j] >= 0) {
-                        p.m[hz2[j]] = hm2[j];
-                        if (hp2[j] != -2) p.least[hz2[j]] = hp2[j];
-                    }
-                    hz2[j] = hz1[j];
-                    hm2[j] = hm1[j];
-                    hp2[j] = hp1[j];
-                    hz1[j] = -1;
-                }
+                if (pub[(y & 1) * 8 + 2] <= y - 2) break;
                 bar_rows();
             }
         }
@@ -215,41 +241,46 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
         int x_min = max(p.nrg_xmin[0], 0), x_max = min(p.nrg_xmax[0], w - 1);
         int fail_row = INT_MAX;
         unsigned long long cells = 0;
+        // guard range of a row: every column the NEXT row's active range (+- delta_x parents) can need
+        auto guard_lo = [&](int xm, int a, int b, int c) { return max(0, min(xm, min(a, min(b, c))) - 4 * D); };
+        auto guard_hi = [&](int xm, int a, int b, int c) { return min(w - 1, max(xm, max(a, max(b, c))) + 4 * D); };
+        const int n0 = p.nrg_xmin[0], n1 = p.nrg_xmin[min(1, h - 1)], n2 = p.nrg_xmin[min(2, h - 1)];
+        const int m0 = p.nrg_xmax[0], m1 = p.nrg_xmax[min(1, h - 1)], m2 = p.nrg_xmax[min(2, h - 1)];
         if (lane == 0) {
             pub[0] = x_min; // row 0: the active range is the exact band (m = en there)
             pub[1] = x_max;
             pub[2] = INT_MAX;
+            pub[4] = guard_lo(x_min, n0, n0, n1);
+            pub[5] = guard_hi(x_max, m0, m0, m1);
             clim[0] = x_min;
             clim[1] = x_max;
             clim[2] = 0;
         }
-        // rolling window of the energy-band limits: a*[0] = row y-1, [1] = row y, [2] = row y+1
-        int an0 = 0, an1 = p.nrg_xmin[0], an2 = p.nrg_xmin[min(1, h - 1)];
-        int ax0 = 0, ax1 = p.nrg_xmax[0], ax2 = p.nrg_xmax[min(1, h - 1)];
+        // rolling window of the energy-band limits: a*0 = row y-1, a*1 = row y, a*2 = row y+1, a*3 = row y+2
+        int an0 = 0, an1 = n0, an2 = n1, an3 = n2;
+        int ax0 = 0, ax1 = m0, ax2 = m1, ax3 = m2;
         __syncthreads(); // start
         int y = 0;
-        int clo_prev = 0, cw_prev = 0;
         bool stop = false;
-        int fb_xmin = x_min, fb_xmax = x_max;
-        auto iteration = [&](int clo_v, int cw_v, int y_lim) {
-            // runs while the compute warps process row y: verify row y-1, publish the active range of row y+1
-            const int an3 = p.nrg_xmin[min(y + 2, h - 1)], ax3 = p.nrg_xmax[min(y + 2, h - 1)];
+        // nkv / riv: ballot words and row info of the row being verified (row y-1)
+        auto iteration = [&](const unsigned *nkv, const int *riv, int y_lim) {
+            // runs while the compute warps process row y: verify row y-1, publish the ranges of row y+1
+            const int an4 = p.nrg_xmin[min(y + 3, h - 1)], ax4 = p.nrg_xmax[min(y + 3, h - 1)];
             const int yv = y - 1;
             if (yv >= 1 && yv < h && yv < y_lim && fail_row == INT_MAX) {
                 const int bmin = max(min(x_min, an0) - D, 0);
                 const int bmax = min(max(x_max, ax0) + D, w - 1);
-                const int nwords = (cw_v + 31) >> 5;
-                const unsigned wv = lane < nwords ? nk[(yv & 1) * 32 + lane] : 0u;
+                const int gb = riv[0], nwords = riv[1] * US_NCW;
+                const unsigned wv = lane < nwords ? nkv[lane] : 0u;
                 const unsigned any = __ballot_sync(0xffffffffu, wv != 0u);
                 int F = INT_MAX, L = INT_MIN;
                 if (any) {
                     const int lf = __ffs(any) - 1, ll = 31 - __clz(any);
                     const unsigned wf = __shfl_sync(0xffffffffu, wv, lf), wl = __shfl_sync(0xffffffffu, wv, ll);
-                    F = clo_v + 32 * lf + (__ffs(wf) - 1);
-                    L = clo_v + 32 * ll + (31 - __clz(wl));
+                    F = gb + 32 * lf + (__ffs(wf) - 1);
+                    L = gb + 32 * ll + (31 - __clz(wl));
                 }
-                fb_xmin = x_min;
-                fb_xmax = x_max;
+                const int old_min = x_min, old_max = x_max;
                 bool violation;
                 if (bmax >= bmin) {
                     cells += (unsigned long long) (bmax - bmin + 1);
@@ -264,39 +295,47 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                 if (violation) {
                     fail_row = yv;
                     if (lane == 0) {
-                        misc[0] = 1;
                         misc[1] = yv;
-                        misc[2] = fb_xmin;
-                        misc[3] = fb_xmax;
+                        misc[2] = old_min;
+                        misc[3] = old_max;
+                        __threadfence_block();
+                        misc[0] = 1;
                     }
                 }
             }
+            // active range of row y+1 from the limits after row y-1 (two rows of growth) and its guard range
             if (lane == 0) {
-                // active range of row y+1 from the limits after row y-1: two rows of growth
-                int *pb = pub + ((y + 1) & 1) * 4;
+                int *pb = pub + ((y + 1) & 1) * 8;
                 pb[0] = max(0, min(x_min, min(an1, an2)) - 2 * D);
                 pb[1] = min(w - 1, max(x_max, max(ax1, ax2)) + 2 * D);
                 pb[2] = fail_row;
+                pb[4] = guard_lo(x_min, an1, an2, an3);
+                pb[5] = guard_hi(x_max, ax1, ax2, ax3);
+                if (fail_row == INT_MAX) misc[5] = min(y, y_lim); // rows [0, y) are verified (producers commit them)
+                __threadfence_block();
             }
-            an0 = an1, an1 = an2, an2 = an3;
-            ax0 = ax1, ax1 = ax2, ax2 = ax3;
+            an0 = an1, an1 = an2, an2 = an3, an3 = an4;
+            ax0 = ax1, ax1 = ax2, ax2 = ax3, ax3 = ax4;
         };
         // The loop mirrors the compute warps' exactly (same stop predicate at the top of every row), so both
         // roles execute the same sequence of row and chunk barriers.
-        int y_end = INT_MAX;
+        const unsigned *nk_last = nk;
+        const int *ri_last = rinfo;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
-            const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
+            const int rows = dsc[1];
             if (rows == 0) break;
+            const unsigned *nkc = nk + (k & 1) * US_MAXROWS * 32;
+            const int *ric = rinfo + (k & 1) * US_MAXROWS * 4;
             for (int r = 0; r < rows; ++r, ++y) {
                 if (fail_row <= y - 2) {
                     stop = true;
                     break;
                 }
                 if (r == 0)
-                    iteration(clo_prev, cw_prev, y_end);
+                    iteration(nk_last, ri_last, INT_MAX); // row y-1 is the last row of the previous chunk
                 else
-                    iteration(clo, cw, y_end);
+                    iteration(nkc + (r - 1) * 32, ric + (r - 1) * 4, INT_MAX);
                 if (r == rows - 1 && lane == 0) {
                     // limits the producers plan chunk k+3 from (they read them after the chunk barrier)
                     int *cl = clim + ((k + 1) & 1) * 4;
@@ -307,22 +346,22 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                 bar_rows();
             }
             if (stop) break;
-            clo_prev = clo;
-            cw_prev = cw;
+            nk_last = nkc + (rows - 1) * 32;
+            ri_last = ric + (rows - 1) * 4;
             __syncthreads(); // chunk end
         }
         if (!stop) {
-            y_end = y;
+            const int y_end = y;
             for (int d = 0; d < 2; ++d, ++y) {
                 if (fail_row <= y - 2) {
                     stop = true;
                     break;
                 }
-                iteration(clo_prev, cw_prev, y_end);
+                iteration(nk_last, ri_last, y_end); // d == 0 verifies row y_end-1; d == 1 has nothing to verify
                 bar_rows();
             }
             if (fail_row == INT_MAX && lane == 0 && y_end < h) {
-                // capacity stop: rows below y_end are exact and committed; hand over the exact limits
+                // capacity stop: rows below y_end are exact; hand the exact limits to the generic loop
                 misc[1] = y_end;
                 misc[2] = x_min;
                 misc[3] = x_max;
@@ -339,21 +378,22 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
             rows = 0, lo = 0, cw = 0;
             if (ya >= h) return;
             for (int attempt = 0; attempt < 2; ++attempt) {
-                const int want = attempt == 0 ? 8 : 4;
+                const int want = attempt == 0 ? US_MAXROWS : 4;
                 const int yb = min(ya + want, h) - 1;
-                // energy-band extremes over rows [yv+1, yb+1] (one row per lane)
+                // energy-band extremes over rows [yv+1, yb+2] (one row per lane)
                 const int j = yv + 1 + lane;
-                const bool in = j <= min(yb + 1, h - 1);
+                const bool in = j <= min(yb + 2, h - 1);
                 int nlo = in ? p.nrg_xmin[j] : INT_MAX, nhi = in ? p.nrg_xmax[j] : INT_MIN;
                 nlo = __reduce_min_sync(0xffffffffu, nlo);
                 nhi = __reduce_max_sync(0xffffffffu, nhi);
-                // a band grows by at most delta_x per row beyond the energy bands; +1 row for the parent halo
-                const int dist = (yb + 2 - yv) * D;
+                // a band grows by at most delta_x per row beyond the energy bands; the guard range of the last
+                // row reaches 4 rows of growth past the limits verified two rows before it
+                const int dist = (yb + 3 - yv) * D;
                 lo = max(0, min(xv_min, nlo) - dist);
                 const int hi = min(w - 1, max(xv_max, nhi) + dist);
                 cw = max(hi - lo + 1, 0);
                 rows = yb - ya + 1;
-                if (cw <= (attempt == 0 ? 512 : US_MAXCW) && yb - yv <= 31) return;
+                if (cw <= (attempt == 0 ? 512 : US_MAXCW) && yb + 1 - yv <= 31) return;
                 rows = 0;
             }
         };
@@ -387,17 +427,16 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                 }
         };
         const int b0min = max(p.nrg_xmin[0], 0), b0max = min(p.nrg_xmax[0], w - 1);
-        int ya0, rows0, lo0, cw0, ya1, rows1, lo1, cw1;
-        // ---- prologue
-        ya0 = 0;
-        plan_regs(ya0, b0min, b0max, 0, rows0, lo0, cw0);
-        put_desc(0, ya0, rows0, lo0, cw0);
-        stage_a(0, ya0, rows0, lo0, cw0);
+        int rows0, lo0, cw0, ya1, rows1, lo1, cw1;
+        // ---- prologue: chunk 0 fully staged, ids of chunk 1 staged
+        plan_regs(0, b0min, b0max, 0, rows0, lo0, cw0);
+        put_desc(0, 0, rows0, lo0, cw0);
+        stage_a(0, 0, rows0, lo0, cw0);
         cp_async_commit();
         cp_async_wait<0>();
         stage_b(0, 0, rows0, cw0);
         cp_async_commit();
-        ya1 = ya0 + rows0;
+        ya1 = rows0;
         rows1 = 0, lo1 = 0, cw1 = 0;
         if (rows0 > 0) plan_regs(ya1, b0min, b0max, 0, rows1, lo1, cw1);
         put_desc(1, ya1, rows1, lo1, cw1);
@@ -405,14 +444,26 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
         cp_async_commit();
         cp_async_wait<0>();
         __syncthreads(); // start
-        // ---- steady state: during chunk k, stage en/m/least of chunk k+1 and the ids of chunk k+2
-        int rows_k = rows0; // chunk k
+        // ---- steady state, during chunk k: commit chunk k-1, stage en/m/least of chunk k+1 and ids of chunk k+2
+        int rows_k = rows0;
         for (int k = 0;; ++k) {
             if (rows_k == 0) {
                 __syncthreads(); // matches the exit barrier of the other roles
                 break;
             }
-            // chunk k+1: ids are complete (waited before the last barrier)
+            if (k > 0) {
+                // chunk k-1: its tiles are about to be recycled (data tile by stage_b(k+1), id tile by stage_a(k+2)),
+                // so its verified rows go to HBM first.  Its last row is verified during row 0 of chunk k.
+                const int *dp = cdesc + ((k - 1) & 3) * 4;
+                const int yp0 = dp[0], prow = dp[1];
+                int done;
+                while ((done = misc[5]) < yp0 + prow && misc[0] == 0) __nanosleep(64);
+                const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
+                us_commit(p, dp, ztile + ((k - 1) % 3) * US_TILE, mtile + ((k - 1) & 1) * US_TILE,
+                          ltile + ((k - 1) & 1) * US_TILE, nk + ((k - 1) & 1) * US_MAXROWS * 32,
+                          rinfo + ((k - 1) & 1) * US_MAXROWS * 4, 0, r_end, pt, US_PT);
+                asm volatile("bar.sync 2, %0;" ::"n"(US_PT) : "memory"); // all producers done reading the old tiles
+            }
             stage_b((k + 1) % 3, (k + 1) & 1, rows1, cw1);
             cp_async_commit();
             // chunk k+2: plan from the limits published at the end of chunk k-1 (or the initial band)
@@ -433,9 +484,19 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
     }
 
     // =================================================================================== exit / fallback
-    if (!(tid >= US_CT + 32)) __syncthreads(); // compute + control: exit barrier (producers already passed theirs)
-    const int fb_row = misc[1];
-    if (fb_row < h) update_rows_generic(p, fb_row, misc[2], misc[3], s_red);
+    if (tid < US_CT + 32) __syncthreads(); // compute + control: exit barrier (the producers already passed theirs)
+    // commit what the producers have not: the verified rows of the last chunk the compute warps entered
+    const int fb_row = misc[1], klast = misc[4];
+    if (klast >= 0) {
+        const int *dl = cdesc + (klast & 3) * 4;
+        const int r_end = min(dl[1], max(min(fb_row, h) - dl[0], 0));
+        us_commit(p, dl, ztile + (klast % 3) * US_TILE, mtile + (klast & 1) * US_TILE, ltile + (klast & 1) * US_TILE,
+                  nk + (klast & 1) * US_MAXROWS * 32, rinfo + (klast & 1) * US_MAXROWS * 4, 0, r_end, tid, US_THREADS);
+    }
+    if (fb_row < h) {
+        __syncthreads();
+        update_rows_generic(p, fb_row, misc[2], misc[3], s_red);
+    }
 }
 
 } // namespace b200c
