@@ -34,7 +34,7 @@ namespace b200c {
 #define US_NPW 4
 #define US_PT (US_NPW * 32)
 #define US_THREADS (US_CT + 32 + US_PT)
-#define US_TILE 4096
+#define US_TILE 3072
 #define US_RW 2048
 #define US_RWM (US_RW - 1)
 #define US_MAXROWS 8
@@ -45,7 +45,7 @@ namespace b200c {
 #define US_RIW (2 * US_MAXROWS * 4)  // row info      [chunk parity][row]{guard base, nslots, -, -}
 static constexpr size_t us_smem_bytes()
 {
-    return sizeof(int) * ((size_t) 3 * US_TILE + 6 * US_TILE + 4 * US_RW + US_NKW + US_RIW + 16 + 16 + 8 + 8 + 128);
+    return sizeof(int) * ((size_t) 4 * US_TILE + 9 * US_TILE + 4 * US_RW + US_NKW + US_RIW + 16 + 16 + 8 + 8 + 128);
 }
 
 __device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(US_CT + 32) : "memory"); }
@@ -112,7 +112,8 @@ __device__ __forceinline__ void us_row(const DevP &p, int y, int rbm, const int 
                         parent = zrow[prev + ((x + bdx) & US_RWM)];
                     }
                     const float new_m = __fadd_rn(e, best);
-                    const bool keep = (lt[idx] == parent) && ((double) fabsf(__fsub_rn(mo, new_m)) < 1e-5);
+                    // (double) |d| < 1e-5  <=>  |d| <= 0x3727C5AC: that float is the largest one below the double 1e-5
+                    const bool keep = (lt[idx] == parent) && (fabsf(__fsub_rn(mo, new_m)) <= __int_as_float(0x3727C5AC));
                     if (!keep) {
                         val = new_m;
                         changed = true;
@@ -153,15 +154,15 @@ template <bool D1>
 __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
 {
     extern __shared__ __align__(16) unsigned char us_smem[];
-    int *ztile = reinterpret_cast<int *>(us_smem);                    // [3][TILE] pixel ids
-    float *etile = reinterpret_cast<float *>(ztile + 3 * US_TILE);    // [2][TILE] energy
-    float *mtile = etile + 2 * US_TILE;                               // [2][TILE] old m -> new m of changed cells
-    int *ltile = reinterpret_cast<int *>(mtile + 2 * US_TILE);        // [2][TILE] old parent -> new parent
-    float *mrow = reinterpret_cast<float *>(ltile + 2 * US_TILE);     // [2][RW] previous / current row values
+    int *ztile = reinterpret_cast<int *>(us_smem);                    // [4][TILE] pixel ids
+    float *etile = reinterpret_cast<float *>(ztile + 4 * US_TILE);    // [3][TILE] energy
+    float *mtile = etile + 3 * US_TILE;                               // [3][TILE] old m -> new m of changed cells
+    int *ltile = reinterpret_cast<int *>(mtile + 3 * US_TILE);        // [3][TILE] old parent -> new parent
+    float *mrow = reinterpret_cast<float *>(ltile + 3 * US_TILE);     // [2][RW] previous / current row values
     int *zrow = reinterpret_cast<int *>(mrow + 2 * US_RW);            // [2][RW] previous / current row ids
     unsigned *nk = reinterpret_cast<unsigned *>(zrow + 2 * US_RW);    // [2][8][32] "changed" ballot words
     int *rinfo = reinterpret_cast<int *>(nk + US_NKW);                // [2][8][4] guard base, slots
-    int *pub = rinfo + US_RIW;                                        // [2][8] act_lo, act_hi, fail_row, -, gr_lo, gr_hi
+    int *pub = rinfo + US_RIW;                                        // [2][8] act_lo, act_hi, fail_row, slots, gr_lo, gr_hi
     int *cdesc = pub + 16;                                            // [4][4] y0, rows, clo, cw
     int *clim = cdesc + 16;                                           // [2][4] x_min, x_max, y_v at chunk starts
     volatile int *misc = clim + 8;                                    // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax,
@@ -181,7 +182,8 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
 
     if (is_compute) {
         // =============================================================================== COMPUTE
-        __syncthreads(); // start: prologue chunks staged, pub[0] published
+        __syncthreads(); // start 1: prologue chunks staged and described
+        __syncthreads(); // start 2: ranges of row 0 published
         int y = 0;
         bool failed = false;
         for (int k = 0;; ++k) {
@@ -189,28 +191,25 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
             if (tid == 0) misc[4] = k;
-            const int *zt = ztile + (k % 3) * US_TILE;
-            const float *et = etile + (k & 1) * US_TILE;
-            float *mt = mtile + (k & 1) * US_TILE;
-            int *lt = ltile + (k & 1) * US_TILE;
+            const int *zt = ztile + (k & 3) * US_TILE;
+            const float *et = etile + (k % 3) * US_TILE;
+            float *mt = mtile + (k % 3) * US_TILE;
+            int *lt = ltile + (k % 3) * US_TILE;
             unsigned *nkc = nk + (k & 1) * US_MAXROWS * 32;
             int *ric = rinfo + (k & 1) * US_MAXROWS * 4;
             for (int r = 0; r < rows; ++r, ++y) {
                 const int par = y & 1;
+                // ranges of this row, already clamped to the chunk window by the control warp
                 const int4 pa = *reinterpret_cast<const int4 *>(pub + par * 8);
                 const int2 pg = *reinterpret_cast<const int2 *>(pub + par * 8 + 4);
                 if (pa.z <= y - 2) {
                     failed = true;
                     break;
                 }
-                // the guard range always lies inside the staged window (see the planning bound); clamp anyway
-                const int gr_lo = max(pg.x, clo), gr_hi = min(pg.y, clo + cw - 1);
-                const int act_lo = max(pa.x, gr_lo), act_hi = min(pa.y, gr_hi);
-                const int gw = gr_hi - gr_lo + 1;
+                const int act_lo = pa.x, act_hi = pa.y, ns = pa.w, gr_lo = pg.x, gr_hi = pg.y;
                 const int cur = par * US_RW, prev = (par ^ 1) * US_RW;
                 const int rbm = r * cw - clo;
                 unsigned *nkrow = nkc + r * 32;
-                const int ns = gw <= US_CT ? 1 : (gw <= 2 * US_CT ? 2 : 4);
                 if (tid == 0) {
                     ric[r * 4 + 0] = gr_lo;
                     ric[r * 4 + 1] = ns;
@@ -246,12 +245,20 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
         auto guard_hi = [&](int xm, int a, int b, int c) { return min(w - 1, max(xm, max(a, max(b, c))) + 4 * D); };
         const int n0 = p.nrg_xmin[0], n1 = p.nrg_xmin[min(1, h - 1)], n2 = p.nrg_xmin[min(2, h - 1)];
         const int m0 = p.nrg_xmax[0], m1 = p.nrg_xmax[min(1, h - 1)], m2 = p.nrg_xmax[min(2, h - 1)];
+        // publish the ranges of row `yr` (window clo/cw of its chunk): active range from limits + two rows of
+        // growth, guard range from four; both clamped to the staged window; slots per thread from the guard width
+        auto publish = [&](int yr, int a_lo, int a_hi, int g_lo, int g_hi, int clo_r, int cw_r, int fail) {
+            const int gl = max(g_lo, clo_r), gh = min(g_hi, clo_r + cw_r - 1);
+            const int gw = gh - gl + 1;
+            int *pb = pub + (yr & 1) * 8;
+            pb[0] = max(a_lo, gl);
+            pb[1] = min(a_hi, gh);
+            pb[2] = fail;
+            pb[3] = gw <= US_CT ? 1 : (gw <= 2 * US_CT ? 2 : 4);
+            pb[4] = gl;
+            pb[5] = gh;
+        };
         if (lane == 0) {
-            pub[0] = x_min; // row 0: the active range is the exact band (m = en there)
-            pub[1] = x_max;
-            pub[2] = INT_MAX;
-            pub[4] = guard_lo(x_min, n0, n0, n1);
-            pub[5] = guard_hi(x_max, m0, m0, m1);
             clim[0] = x_min;
             clim[1] = x_max;
             clim[2] = 0;
@@ -259,11 +266,15 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
         // rolling window of the energy-band limits: a*0 = row y-1, a*1 = row y, a*2 = row y+1, a*3 = row y+2
         int an0 = 0, an1 = n0, an2 = n1, an3 = n2;
         int ax0 = 0, ax1 = m0, ax2 = m1, ax3 = m2;
-        __syncthreads(); // start
+        __syncthreads(); // start 1: the producers described chunks 0..2
+        if (lane == 0) // row 0: the active range is the exact band (m = en there)
+            publish(0, x_min, x_max, guard_lo(x_min, n0, n0, n1), guard_hi(x_max, m0, m0, m1), cdesc[2], cdesc[3], INT_MAX);
+        __syncthreads(); // start 2
         int y = 0;
         bool stop = false;
-        // nkv / riv: ballot words and row info of the row being verified (row y-1)
-        auto iteration = [&](const unsigned *nkv, const int *riv, int y_lim) {
+        // nkv / riv: ballot words and row info of the row being verified (row y-1); clo_n / cw_n: window of the
+        // chunk that holds row y+1
+        auto iteration = [&](const unsigned *nkv, const int *riv, int y_lim, int clo_n, int cw_n) {
             // runs while the compute warps process row y: verify row y-1, publish the ranges of row y+1
             const int an4 = p.nrg_xmin[min(y + 3, h - 1)], ax4 = p.nrg_xmax[min(y + 3, h - 1)];
             const int yv = y - 1;
@@ -305,12 +316,8 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
             }
             // active range of row y+1 from the limits after row y-1 (two rows of growth) and its guard range
             if (lane == 0) {
-                int *pb = pub + ((y + 1) & 1) * 8;
-                pb[0] = max(0, min(x_min, min(an1, an2)) - 2 * D);
-                pb[1] = min(w - 1, max(x_max, max(ax1, ax2)) + 2 * D);
-                pb[2] = fail_row;
-                pb[4] = guard_lo(x_min, an1, an2, an3);
-                pb[5] = guard_hi(x_max, ax1, ax2, ax3);
+                publish(y + 1, max(0, min(x_min, min(an1, an2)) - 2 * D), min(w - 1, max(x_max, max(ax1, ax2)) + 2 * D),
+                        guard_lo(x_min, an1, an2, an3), guard_hi(x_max, ax1, ax2, ax3), clo_n, cw_n, fail_row);
                 if (fail_row == INT_MAX) misc[5] = min(y, y_lim); // rows [0, y) are verified (producers commit them)
                 __threadfence_block();
             }
@@ -323,8 +330,10 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
         const int *ri_last = rinfo;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
-            const int rows = dsc[1];
+            const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
+            const int *dn = cdesc + ((k + 1) & 3) * 4; // next chunk (described at least one chunk ago)
+            const int clo_nx = dn[2], cw_nx = dn[3];
             const unsigned *nkc = nk + (k & 1) * US_MAXROWS * 32;
             const int *ric = rinfo + (k & 1) * US_MAXROWS * 4;
             for (int r = 0; r < rows; ++r, ++y) {
@@ -332,10 +341,11 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                     stop = true;
                     break;
                 }
-                if (r == 0)
-                    iteration(nk_last, ri_last, INT_MAX); // row y-1 is the last row of the previous chunk
+                const bool nx = r + 1 >= rows; // row y+1 opens the next chunk
+                if (r == 0) // row y-1 is the last row of the previous chunk
+                    iteration(nk_last, ri_last, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
                 else
-                    iteration(nkc + (r - 1) * 32, ric + (r - 1) * 4, INT_MAX);
+                    iteration(nkc + (r - 1) * 32, ric + (r - 1) * 4, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
                 if (r == rows - 1 && lane == 0) {
                     // limits the producers plan chunk k+3 from (they read them after the chunk barrier)
                     int *cl = clim + ((k + 1) & 1) * 4;
@@ -357,7 +367,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                     stop = true;
                     break;
                 }
-                iteration(nk_last, ri_last, y_end); // d == 0 verifies row y_end-1; d == 1 has nothing to verify
+                iteration(nk_last, ri_last, y_end, 0, 0); // d == 0 verifies row y_end-1; d == 1 has nothing to verify
                 bar_rows();
             }
             if (fail_row == INT_MAX && lane == 0 && y_end < h) {
@@ -377,13 +387,16 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
         auto plan_regs = [&](int ya, int xv_min, int xv_max, int yv, int &rows, int &lo, int &cw) {
             rows = 0, lo = 0, cw = 0;
             if (ya >= h) return;
-            for (int attempt = 0; attempt < 2; ++attempt) {
-                const int want = attempt == 0 ? US_MAXROWS : 4;
+            for (int want = US_MAXROWS; want >= 2; want >>= 1) {
                 const int yb = min(ya + want, h) - 1;
-                // energy-band extremes over rows [yv+1, yb+2] (one row per lane)
-                const int j = yv + 1 + lane;
-                const bool in = j <= min(yb + 2, h - 1);
-                int nlo = in ? p.nrg_xmin[j] : INT_MAX, nhi = in ? p.nrg_xmax[j] : INT_MIN;
+                // energy-band extremes over rows [yv+1, yb+2] (two rows per lane: up to 64 rows)
+                const int last = min(yb + 2, h - 1);
+                const int j0 = yv + 1 + lane, j1 = j0 + 32;
+                int nlo = j0 <= last ? p.nrg_xmin[j0] : INT_MAX, nhi = j0 <= last ? p.nrg_xmax[j0] : INT_MIN;
+                if (j1 <= last) {
+                    nlo = min(nlo, p.nrg_xmin[j1]);
+                    nhi = max(nhi, p.nrg_xmax[j1]);
+                }
                 nlo = __reduce_min_sync(0xffffffffu, nlo);
                 nhi = __reduce_max_sync(0xffffffffu, nhi);
                 // a band grows by at most delta_x per row beyond the energy bands; the guard range of the last
@@ -393,7 +406,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                 const int hi = min(w - 1, max(xv_max, nhi) + dist);
                 cw = max(hi - lo + 1, 0);
                 rows = yb - ya + 1;
-                if (cw <= (attempt == 0 ? 512 : US_MAXCW) && yb + 1 - yv <= 31) return;
+                if (rows * cw <= US_TILE && cw <= US_MAXCW && yb + 1 - yv <= 63) return;
                 rows = 0;
             }
         };
@@ -406,17 +419,17 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                 d[3] = cw;
             }
         };
-        auto stage_a = [&](int ztile_idx, int ya, int rows, int lo, int cw) {
-            int *zt = ztile + ztile_idx * US_TILE;
+        auto stage_a = [&](int kk, int ya, int rows, int lo, int cw) {
+            int *zt = ztile + (kk & 3) * US_TILE;
             for (int r = 0; r < rows; ++r) {
                 const int *src = p.raw + (size_t) (ya + r) * p.raw_stride + lo;
                 for (int c = pt; c < cw; c += US_PT) cp_async4(&zt[r * cw + c], src + c);
             }
         };
-        auto stage_b = [&](int ztile_idx, int dtile_idx, int rows, int cw) {
-            const int *zt = ztile + ztile_idx * US_TILE;
-            float *et = etile + dtile_idx * US_TILE, *mt = mtile + dtile_idx * US_TILE;
-            int *lt = ltile + dtile_idx * US_TILE;
+        auto stage_b = [&](int kk, int rows, int cw) {
+            const int *zt = ztile + (kk & 3) * US_TILE;
+            float *et = etile + (kk % 3) * US_TILE, *mt = mtile + (kk % 3) * US_TILE;
+            int *lt = ltile + (kk % 3) * US_TILE;
             for (int r = 0; r < rows; ++r)
                 for (int c = pt; c < cw; c += US_PT) {
                     const int i = r * cw + c;
@@ -427,60 +440,76 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
                 }
         };
         const int b0min = max(p.nrg_xmin[0], 0), b0max = min(p.nrg_xmax[0], w - 1);
-        int rows0, lo0, cw0, ya1, rows1, lo1, cw1;
-        // ---- prologue: chunk 0 fully staged, ids of chunk 1 staged
-        plan_regs(0, b0min, b0max, 0, rows0, lo0, cw0);
-        put_desc(0, 0, rows0, lo0, cw0);
-        stage_a(0, 0, rows0, lo0, cw0);
-        cp_async_commit();
-        cp_async_wait<0>();
-        stage_b(0, 0, rows0, cw0);
-        cp_async_commit();
-        ya1 = rows0;
-        rows1 = 0, lo1 = 0, cw1 = 0;
-        if (rows0 > 0) plan_regs(ya1, b0min, b0max, 0, rows1, lo1, cw1);
-        put_desc(1, ya1, rows1, lo1, cw1);
-        stage_a(1, ya1, rows1, lo1, cw1);
-        cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads(); // start
-        // ---- steady state, during chunk k: commit chunk k-1, stage en/m/least of chunk k+1 and ids of chunk k+2
-        int rows_k = rows0;
-        for (int k = 0;; ++k) {
-            if (rows_k == 0) {
-                __syncthreads(); // matches the exit barrier of the other roles
-                break;
-            }
-            if (k > 0) {
-                // chunk k-1: its tiles are about to be recycled (data tile by stage_b(k+1), id tile by stage_a(k+2)),
-                // so its verified rows go to HBM first.  Its last row is verified during row 0 of chunk k.
-                const int *dp = cdesc + ((k - 1) & 3) * 4;
-                const int yp0 = dp[0], prow = dp[1];
-                int done;
-                while ((done = misc[5]) < yp0 + prow && misc[0] == 0) __nanosleep(64);
-                const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
-                us_commit(p, dp, ztile + ((k - 1) % 3) * US_TILE, mtile + ((k - 1) & 1) * US_TILE,
-                          ltile + ((k - 1) & 1) * US_TILE, nk + ((k - 1) & 1) * US_MAXROWS * 32,
-                          rinfo + ((k - 1) & 1) * US_MAXROWS * 4, 0, r_end, pt, US_PT);
-                asm volatile("bar.sync 2, %0;" ::"n"(US_PT) : "memory"); // all producers done reading the old tiles
-            }
-            stage_b((k + 1) % 3, (k + 1) & 1, rows1, cw1);
+        // geometry of the chunks in flight: c1 = chunk k+1 (data being staged), c2 = chunk k+2 (ids staged)
+        int ya1, rows1, lo1, cw1, ya2, rows2, lo2, cw2;
+        {
+            // ---- prologue: chunk 0 and 1 fully staged, ids of chunk 2 staged
+            int rows0, lo0, cw0;
+            plan_regs(0, b0min, b0max, 0, rows0, lo0, cw0);
+            put_desc(0, 0, rows0, lo0, cw0);
+            stage_a(0, 0, rows0, lo0, cw0);
             cp_async_commit();
-            // chunk k+2: plan from the limits published at the end of chunk k-1 (or the initial band)
-            const int *cl = clim + (k & 1) * 4;
-            const int ya2 = ya1 + rows1;
-            int rows2 = 0, lo2 = 0, cw2 = 0;
-            if (rows1 > 0) plan_regs(ya2, cl[0], cl[1], cl[2], rows2, lo2, cw2);
-            stage_a((k + 2) % 3, ya2, rows2, lo2, cw2);
+            ya1 = rows0, rows1 = 0, lo1 = 0, cw1 = 0;
+            if (rows0 > 0) plan_regs(ya1, b0min, b0max, 0, rows1, lo1, cw1);
+            put_desc(1, ya1, rows1, lo1, cw1);
+            stage_a(1, ya1, rows1, lo1, cw1);
             cp_async_commit();
-            put_desc((k + 2) & 3, ya2, rows2, lo2, cw2);
+            ya2 = ya1 + rows1, rows2 = 0, lo2 = 0, cw2 = 0;
+            if (rows1 > 0) plan_regs(ya2, b0min, b0max, 0, rows2, lo2, cw2);
+            put_desc(2, ya2, rows2, lo2, cw2);
+            stage_a(2, ya2, rows2, lo2, cw2);
+            cp_async_commit();
             cp_async_wait<0>();
-            __syncthreads(); // chunk k end (or the exit barrier of a failed speculation)
-            if (misc[0]) break;
-            rows_k = rows1;
-            ya1 = ya2, rows1 = rows2, lo1 = lo2, cw1 = cw2;
+            stage_b(0, rows0, cw0);
+            stage_b(1, rows1, cw1);
+            cp_async_commit();
+            cp_async_wait<0>();
+            __syncthreads(); // start 1
+            __syncthreads(); // start 2
+            // ---- steady state.  During chunk k: commit chunk k-1 (verified), then stage en/m/least of chunk k+2 and
+            // the ids of chunk k+3.  The loads waited for were issued a whole chunk earlier.
+            int rows_k = rows0;
+            for (int k = 0;; ++k) {
+                if (rows_k == 0) {
+                    __syncthreads(); // matches the exit barrier of the other roles
+                    break;
+                }
+                if (k > 0) {
+                    // chunk k-1: its tiles are about to be recycled (data tile by stage_b(k+2), id tile by
+                    // stage_a(k+3)), so its verified rows go to HBM first.  Its last row is verified during row 0
+                    // of chunk k.
+                    const int *dp = cdesc + ((k - 1) & 3) * 4;
+                    const int yp0 = dp[0], prow = dp[1];
+                    int done;
+                    while ((done = misc[5]) < yp0 + prow && misc[0] == 0) __nanosleep(32);
+                    const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
+                    us_commit(p, dp, ztile + ((k - 1) & 3) * US_TILE, mtile + ((k - 1) % 3) * US_TILE,
+                              ltile + ((k - 1) % 3) * US_TILE, nk + ((k - 1) & 1) * US_MAXROWS * 32,
+                              rinfo + ((k - 1) & 1) * US_MAXROWS * 4, 0, r_end, pt, US_PT);
+                    asm volatile("bar.sync 2, %0;" ::"n"(US_PT) : "memory"); // every producer is done with the old tiles
+                }
+                cp_async_wait<0>(); // ids of chunk k+2 and data of chunk k+1, issued during chunk k-1
+                stage_b(k + 2, rows2, cw2);
+                cp_async_commit();
+                // chunk k+3: plan from the limits published at the end of chunk k-1 (or the initial band)
+                const int *cl = clim + (k & 1) * 4;
+                const int ya3 = ya2 + rows2;
+                int rows3 = 0, lo3 = 0, cw3 = 0;
+                if (rows2 > 0) plan_regs(ya3, cl[0], cl[1], cl[2], rows3, lo3, cw3);
+                stage_a(k + 3, ya3, rows3, lo3, cw3);
+                cp_async_commit();
+                put_desc((k + 3) & 3, ya3, rows3, lo3, cw3);
+                __syncthreads(); // chunk k end (or the exit barrier of a failed speculation)
+                if (misc[0]) break;
+                rows_k = rows1;
+                ya1 = ya2, rows1 = rows2, lo1 = lo2, cw1 = cw2;
+                ya2 = ya3, rows2 = rows3, lo2 = lo3, cw2 = cw3;
+            }
         }
         cp_async_wait<0>();
+        (void) lo1;
+        (void) cw1;
+        (void) ya1;
     }
 
     // =================================================================================== exit / fallback
@@ -490,7 +519,7 @@ __global__ void __launch_bounds__(US_THREADS, 1) k_mmap_update_spec(DevP p)
     if (klast >= 0) {
         const int *dl = cdesc + (klast & 3) * 4;
         const int r_end = min(dl[1], max(min(fb_row, h) - dl[0], 0));
-        us_commit(p, dl, ztile + (klast % 3) * US_TILE, mtile + (klast & 1) * US_TILE, ltile + (klast & 1) * US_TILE,
+        us_commit(p, dl, ztile + (klast & 3) * US_TILE, mtile + (klast % 3) * US_TILE, ltile + (klast % 3) * US_TILE,
                   nk + (klast & 1) * US_MAXROWS * 32, rinfo + (klast & 1) * US_MAXROWS * 4, 0, r_end, tid, US_THREADS);
     }
     if (fb_row < h) {
