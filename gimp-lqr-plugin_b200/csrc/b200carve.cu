@@ -24,6 +24,7 @@
 #include "mmap_update_fast.cuh"
 #include "vpath_mmap_tiled.cuh"
 #include "mmap_update_spec.cuh"
+#include "mmap_update_tma.cuh"
 
 using namespace b200c;
 
@@ -128,7 +129,7 @@ struct B200Carver {
     bool owns_stream = true;
     int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
-    int update_kernel = 3;                    // B200C_UPDATE=2: staged kernel instead of the speculative one
+    int update_kernel = 4;                    // B200C_UPDATE=3: cp.async-staged speculative kernel, 2: staged exact kernel
 
     float rigidity = 0.f;
     int delta_x = 1;
@@ -149,7 +150,7 @@ template <class T>
 int dalloc(B200Carver *c, T **p, size_t n, bool zero)
 {
     *p = nullptr;
-    if (n == 0) n = 1;
+    n += 8; // slack: the TMA staging reads 16-byte aligned spans that may end a few elements past the map
     CU_TRY(cudaMallocAsync((void **) p, n * sizeof(T), c->stream));
     if (zero) CU_TRY(cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream));
     return B200C_OK;
@@ -286,6 +287,8 @@ int raise_smem_limits()
         };
         set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, false>, UfLayout<kUpdatePrefetchRows, false>::bytes);
         set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, true>, UfLayout<kUpdatePrefetchRows, true>::bytes);
+        set((const void *) k_mmap_update_tma<true>, ut_smem_bytes());
+        set((const void *) k_mmap_update_tma<false>, ut_smem_bytes());
         set((const void *) k_mmap_update_spec<true>, us_smem_bytes());
         set((const void *) k_mmap_update_spec<false>, us_smem_bytes());
         set((const void *) k_vpath_fast, vp_smem_bytes());
@@ -404,7 +407,11 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             B_TRY(build_mmap(c));
         } else {
             StageScope sc("mmap_update", s);
-            if (fast && c->rigidity == 0.f && c->update_kernel == 3 && c->delta_x == 1)
+            if (fast && c->rigidity == 0.f && c->update_kernel == 4 && c->delta_x == 1)
+                k_mmap_update_tma<true><<<1, UT_THREADS, ut_smem_bytes(), s>>>(view(c));
+            else if (fast && c->rigidity == 0.f && c->update_kernel == 4)
+                k_mmap_update_tma<false><<<1, UT_THREADS, ut_smem_bytes(), s>>>(view(c));
+            else if (fast && c->rigidity == 0.f && c->update_kernel == 3 && c->delta_x == 1)
                 k_mmap_update_spec<true><<<1, US_THREADS, us_smem_bytes(), s>>>(view(c));
             else if (fast && c->rigidity == 0.f && c->update_kernel == 3)
                 k_mmap_update_spec<false><<<1, US_THREADS, us_smem_bytes(), s>>>(view(c));
@@ -651,7 +658,7 @@ B200Carver *carver_new_common(int width, int height, int channels)
         const char *g = getenv("B200C_GENERIC");
         c->generic = g && atoi(g) != 0;
         const char *u = getenv("B200C_UPDATE");
-        if (u && atoi(u) == 2) c->update_kernel = 2;
+        if (u && atoi(u) >= 2 && atoi(u) <= 4) c->update_kernel = atoi(u);
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
     if (g_use_ext_stream) {

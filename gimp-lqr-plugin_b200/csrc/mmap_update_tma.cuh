@@ -1,0 +1,626 @@
+// mmap_update_tma.cuh -- K2b, the incremental m-map DP after one carve (liblqr lqr_carver_update_mmap,
+// SURVEY.md A.8): warp-specialised, verified-speculative, staged and committed with TMA bulk copies.
+//
+// One CTA of 10 warps on one SM (the algorithm is a row-serial chain):
+//
+//   * 8 COMPUTE warps walk the rows.  Per row a thread does one cell (2 or 4 for very wide bands) entirely from
+//     shared memory: parents from the previous row's ring (mrow/zrow), the cell's own id / energy / old m / old
+//     parent from the chunk tile.  They do NOT wait for the exact band limits of the row: they recompute a
+//     slightly wider ACTIVE range (the limits verified two rows earlier, grown by 2*delta_x and the energy bands
+//     in between), apply liblqr's keep-old rule to every cell in it, leave the result in place in the tile and
+//     emit one ballot word per warp marking the cells whose value changed.
+//   * 1 CONTROL warp runs one row behind.  From the ballot words it recomputes liblqr's exact band limits (the
+//     leading kept run advances x_min, a trailing kept run pulls x_max back) and VERIFIES the speculation:
+//     every changed cell must lie inside the exact band.  It publishes the active / guard ranges two rows ahead.
+//     If the band logic is sound -- a cell outside the band has unchanged parents, so recomputing it reproduces
+//     the stored value within the keep tolerance -- the check never fires.  If it ever does, nothing wrong has
+//     reached HBM: rows are COMMITTED only after verification, and the kernel finishes the remaining rows with
+//     the exact generic row loop from the control warp's exact limits.  Bit-identical to liblqr in every case.
+//   * 1 DMA warp moves the data with the TMA.  Pixel ids along a row are increasing and nearly contiguous (the
+//     x-th visible pixel of row y is y*w0 + x + #seams removed on its left), so the en / m / least values of a
+//     row window occupy one nearly contiguous PHYSICAL span.  Per row the warp issues four cp.async.bulk loads
+//     (the raw-id window and the three spans, 16-byte aligned) two chunks ahead, completing on an mbarrier, and
+//     -- one chunk behind, once verified -- two cp.async.bulk stores that write the m / least spans back.
+//     No per-cell staging or commit instruction exists anywhere.
+//
+// Dependent chain per row on the compute warps: LDS parents -> min/select -> FADD -> keep test -> STS -> named
+// barrier (288 threads).
+#pragma once
+#include "carver_kernels.cuh"
+#include "mmap_update_fast.cuh"
+
+namespace b200c {
+
+#define UT_NCW 8
+#define UT_CT (UT_NCW * 32)
+#define UT_THREADS (UT_CT + 64)
+#define UT_TILE 13312 // words per chunk tile (3 tiles)
+#define UT_RW 2048
+#define UT_RWM (UT_RW - 1)
+#define UT_MAXROWS 8
+#define UT_MAXCW (UT_CT * 4)
+
+#define UT_NKW (2 * UT_MAXROWS * 32) // ballot words [chunk parity][row][32]
+#define UT_RIW (2 * UT_MAXROWS * 4)  // row info     [chunk parity][row]{guard base, slots}
+#define UT_RTW (3 * UT_MAXROWS * 8)  // row tables   [tile][row]{xadd, eadd, madd, ladd, zlo, zhi, -, -}
+static constexpr size_t ut_smem_bytes()
+{
+    return sizeof(int) * ((size_t) 3 * UT_TILE + 4 * UT_RW + UT_NKW + UT_RIW + UT_RTW + 16 + 16 + 8 + 8 + 8 + 128);
+}
+
+__device__ __forceinline__ void ut_bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(UT_CT + 32) : "memory"); }
+__device__ __forceinline__ unsigned ut_saddr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ut_mbar_init(void *mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(ut_saddr(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void ut_mbar_expect(void *mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ut_saddr(mbar)), "r"(bytes) : "memory");
+}
+// bounded wait: a bulk copy that never completes is a bug, not a reason to hang the GPU
+__device__ __forceinline__ bool ut_mbar_wait(void *mbar, unsigned parity)
+{
+    const unsigned a = ut_saddr(mbar);
+    for (int tries = 0; tries < (1 << 22); ++tries) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+// global -> shared bulk copy (TMA), completion counted in bytes on `mbar`
+__device__ __forceinline__ void ut_bulk_load(void *dst_smem, const void *src, unsigned bytes, void *mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     ut_saddr(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(ut_saddr(mbar))
+                 : "memory");
+}
+// shared -> global bulk copy (TMA), tracked by the thread's bulk async-group
+__device__ __forceinline__ void ut_bulk_store(void *dst, const void *src_smem, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(ut_saddr(src_smem)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void ut_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void ut_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ut_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void ut_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// One row of the compute warps.  Thread t handles the columns gr_lo + t + 256*j (j < NS) of the row's guard
+// range [gr_lo, gr_hi]: cells inside the active range are recomputed (parents from the previous row's ring),
+// the others only forward their old value / id to the ring for the next row's parents.  New value / parent are
+// left in place in the tile; `changed` bits go to nkrow.  rt = {xadd, eadd, madd, ladd}: tile word offsets.
+template <int NS, bool D1>
+__device__ __forceinline__ void ut_row(const DevP &p, int y, int4 rt, int *__restrict__ tile, float *mrow, int *zrow,
+                                       int cur, int prev, int act_lo, int act_hi, int gr_lo, int gr_hi, unsigned *nkrow,
+                                       int tid, int lane, int warp)
+{
+    const int w = p.w;
+    float *tilef = reinterpret_cast<float *>(tile);
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+        const int x = gr_lo + j * UT_CT + tid;
+        bool changed = false;
+        if (x <= gr_hi) {
+            const int rb = x & UT_RWM;
+            const int z = tile[rt.x + x];
+            const float mo = tilef[rt.z + z];
+            float val = mo;
+            if (x >= act_lo && x <= act_hi) {
+                const float e = tilef[rt.y + z];
+                if (y == 0) {
+                    val = e; // row 0: m = en over the (exact) band
+                    tilef[rt.z + z] = e;
+                } else {
+                    float best;
+                    int parent;
+                    if (D1) {
+                        const float inf = __int_as_float(0x7f800000);
+                        const float m0 = mrow[prev + rb];
+                        const int z0 = zrow[prev + rb];
+                        float ml = mrow[prev + ((rb - 1) & UT_RWM)];
+                        const int zl = zrow[prev + ((rb - 1) & UT_RWM)];
+                        float mr = mrow[prev + ((rb + 1) & UT_RWM)];
+                        const int zr = zrow[prev + ((rb + 1) & UT_RWM)];
+                        // left-to-right scan with strict '<' == leftmost minimum; ties go right when leftright == 1.
+                        // (all m are finite: an out-of-image neighbour is replaced by +inf and can never win)
+                        ml = x > 0 ? ml : inf;
+                        mr = x < w - 1 ? mr : inf;
+                        best = fminf(fminf(ml, m0), mr);
+                        if (p.leftright)
+                            parent = mr == best ? zr : (m0 == best ? z0 : zl);
+                        else
+                            parent = ml == best ? zl : (m0 == best ? z0 : zr);
+                    } else {
+                        const int D = p.delta_x;
+                        const int dlo = max(-x, -D), dhi = min(w - 1 - x, D);
+                        int bdx = dlo;
+                        best = mrow[prev + ((x + dlo) & UT_RWM)];
+                        for (int dx = dlo + 1; dx <= dhi; ++dx) {
+                            const float cand = mrow[prev + ((x + dx) & UT_RWM)];
+                            if (cand < best || (cand == best && p.leftright == 1)) {
+                                best = cand;
+                                bdx = dx;
+                            }
+                        }
+                        parent = zrow[prev + ((x + bdx) & UT_RWM)];
+                    }
+                    const float new_m = __fadd_rn(e, best);
+                    // (double) |d| < 1e-5  <=>  |d| <= 0x3727C5AC: that float is the largest one below the double 1e-5
+                    const bool keep =
+                        (tile[rt.w + z] == parent) && (fabsf(__fsub_rn(mo, new_m)) <= __int_as_float(0x3727C5AC));
+                    if (!keep) {
+                        val = new_m;
+                        changed = true;
+                        tilef[rt.z + z] = new_m;
+                        tile[rt.w + z] = parent;
+                    }
+                }
+            }
+            mrow[cur + rb] = val;
+            zrow[cur + rb] = z;
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, changed);
+        if (lane == 0) nkrow[j * UT_NCW + warp] = word;
+    }
+}
+
+// Write the m / least spans of one verified row back to HBM: 16-byte aligned interior with a TMA bulk store,
+// the (at most three) head / tail elements with plain stores.  Called by one lane per row.
+__device__ __forceinline__ void ut_commit_row(const DevP &p, int y, const int *tile, const int *rtab)
+{
+    const int madd = rtab[2], ladd = rtab[3], zlo = rtab[4], zhi = rtab[5];
+    const int a = (zlo + 3) & ~3, b = (zhi + 1) & ~3; // aligned interior [a, b)
+    const float *tilef = reinterpret_cast<const float *>(tile);
+    if (b > a) {
+        ut_bulk_store(p.m + a, tilef + madd + a, (unsigned) (b - a) * 4u);
+        if (y > 0) ut_bulk_store(p.least + a, tile + ladd + a, (unsigned) (b - a) * 4u);
+        for (int z = zlo; z < a; ++z) {
+            p.m[z] = tilef[madd + z];
+            if (y > 0) p.least[z] = tile[ladd + z];
+        }
+        for (int z = b; z <= zhi; ++z) {
+            p.m[z] = tilef[madd + z];
+            if (y > 0) p.least[z] = tile[ladd + z];
+        }
+    } else {
+        for (int z = zlo; z <= zhi; ++z) {
+            p.m[z] = tilef[madd + z];
+            if (y > 0) p.least[z] = tile[ladd + z];
+        }
+    }
+}
+
+template <bool D1>
+__global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
+{
+    extern __shared__ __align__(128) unsigned char ut_smem[];
+    int *tiles = reinterpret_cast<int *>(ut_smem);                    // [3][UT_TILE] chunk tiles
+    float *mrow = reinterpret_cast<float *>(tiles + 3 * UT_TILE);     // [2][RW] previous / current row values
+    int *zrow = reinterpret_cast<int *>(mrow + 2 * UT_RW);            // [2][RW] previous / current row ids
+    unsigned *nk = reinterpret_cast<unsigned *>(zrow + 2 * UT_RW);    // [2][8][32] "changed" ballot words
+    int *rinfo = reinterpret_cast<int *>(nk + UT_NKW);                // [2][8][4] guard base, slots
+    int *rtab = rinfo + UT_RIW;                                       // [3][8][8] row tables of the tiles
+    int *pub = rtab + UT_RTW;                                         // [2][8] act_lo, act_hi, fail_row, slots, gr_lo, gr_hi
+    int *cdesc = pub + 16;                                            // [4][4] y0, rows, clo, cw
+    int *clim = cdesc + 16;                                           // [2][4] x_min, x_max, y_v at chunk starts
+    volatile int *misc = clim + 8;                                    // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax,
+                                                                      //     4 last chunk entered, 5 rows verified, 6 last chunk issued
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(const_cast<int *>(misc) + 8); // [3] (+pad)
+    int *s_red = const_cast<int *>(misc) + 16;                        // [128] generic fallback scratch
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int D = p.delta_x, w = p.w, h = p.h;
+    const bool is_compute = tid < UT_CT, is_control = warp == UT_NCW;
+
+    if (tid == 0) {
+        misc[0] = 0;
+        misc[1] = h;
+        misc[4] = -1;
+        misc[5] = 0;
+        misc[6] = -1;
+        for (int i = 0; i < 3; ++i) ut_mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads(); // mbarriers initialised
+
+    if (is_compute) {
+        // =============================================================================== COMPUTE
+        __syncthreads(); // start 1: prologue chunks described, their loads issued
+        __syncthreads(); // start 2: ranges of row 0 published
+        int y = 0;
+        bool failed = false;
+        for (int k = 0;; ++k) {
+            const int *dsc = cdesc + (k & 3) * 4;
+            const int rows = dsc[1];
+            if (rows == 0) break;
+            if (tid == 0) misc[4] = k;
+            int *tile = tiles + (k % 3) * UT_TILE;
+            const int *rtc = rtab + (k % 3) * UT_MAXROWS * 8;
+            unsigned *nkc = nk + (k & 1) * UT_MAXROWS * 32;
+            int *ric = rinfo + (k & 1) * UT_MAXROWS * 4;
+            if (!ut_mbar_wait(&mbar[k % 3], (unsigned) ((k / 3) & 1))) // the chunk's bulk loads have landed
+                atomicOr(p.err, 4);
+            for (int r = 0; r < rows; ++r, ++y) {
+                const int par = y & 1;
+                // ranges of this row, already clamped to the chunk window by the control warp
+                const int4 pa = *reinterpret_cast<const int4 *>(pub + par * 8);
+                const int2 pg = *reinterpret_cast<const int2 *>(pub + par * 8 + 4);
+                const int4 rt = *reinterpret_cast<const int4 *>(rtc + r * 8);
+                if (pa.z <= y - 2) {
+                    failed = true;
+                    break;
+                }
+                const int act_lo = pa.x, act_hi = pa.y, ns = pa.w, gr_lo = pg.x, gr_hi = pg.y;
+                const int cur = par * UT_RW, prev = (par ^ 1) * UT_RW;
+                unsigned *nkrow = nkc + r * 32;
+                if (tid == 0) {
+                    ric[r * 4 + 0] = gr_lo;
+                    ric[r * 4 + 1] = ns;
+                }
+                if (ns == 1)
+                    ut_row<1, D1>(p, y, rt, tile, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                else if (ns == 2)
+                    ut_row<2, D1>(p, y, rt, tile, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                else
+                    ut_row<4, D1>(p, y, rt, tile, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                ut_bar_rows();
+            }
+            ut_fence_async(); // tile writes (generic proxy) -> visible to the TMA stores (async proxy)
+            if (failed) break;
+            __syncthreads(); // chunk end
+        }
+        if (!failed) {
+            // drain: the last two rows still wait for verification
+            for (int d = 0; d < 2; ++d, ++y) {
+                if (pub[(y & 1) * 8 + 2] <= y - 2) break;
+                ut_bar_rows();
+            }
+        }
+    } else if (is_control) {
+        // =============================================================================== CONTROL
+        int x_min = max(p.nrg_xmin[0], 0), x_max = min(p.nrg_xmax[0], w - 1);
+        int fail_row = INT_MAX;
+        unsigned long long cells = 0;
+        // guard range of a row: every column the NEXT row's active range (+- delta_x parents) can need
+        auto guard_lo = [&](int xm, int a, int b, int c) { return max(0, min(xm, min(a, min(b, c))) - 4 * D); };
+        auto guard_hi = [&](int xm, int a, int b, int c) { return min(w - 1, max(xm, max(a, max(b, c))) + 4 * D); };
+        const int n0 = p.nrg_xmin[0], n1 = p.nrg_xmin[min(1, h - 1)], n2 = p.nrg_xmin[min(2, h - 1)];
+        const int m0 = p.nrg_xmax[0], m1 = p.nrg_xmax[min(1, h - 1)], m2 = p.nrg_xmax[min(2, h - 1)];
+        // publish the ranges of row `yr` (window clo/cw of its chunk): active range from limits + two rows of
+        // growth, guard range from four; both clamped to the staged window; slots per thread from the guard width
+        auto publish = [&](int yr, int a_lo, int a_hi, int g_lo, int g_hi, int clo_r, int cw_r, int fail) {
+            const int gl = max(g_lo, clo_r), gh = min(g_hi, clo_r + cw_r - 1);
+            const int gw = gh - gl + 1;
+            int *pb = pub + (yr & 1) * 8;
+            pb[0] = max(a_lo, gl);
+            pb[1] = min(a_hi, gh);
+            pb[2] = fail;
+            pb[3] = gw <= UT_CT ? 1 : (gw <= 2 * UT_CT ? 2 : 4);
+            pb[4] = gl;
+            pb[5] = gh;
+        };
+        if (lane == 0) {
+            clim[0] = x_min;
+            clim[1] = x_max;
+            clim[2] = 0;
+        }
+        // rolling window of the energy-band limits: a*0 = row y-1, a*1 = row y, a*2 = row y+1, a*3 = row y+2
+        int an0 = 0, an1 = n0, an2 = n1, an3 = n2;
+        int ax0 = 0, ax1 = m0, ax2 = m1, ax3 = m2;
+        __syncthreads(); // start 1: the DMA warp described chunks 0..2
+        if (lane == 0) // row 0: the active range is the exact band (m = en there)
+            publish(0, x_min, x_max, guard_lo(x_min, n0, n0, n1), guard_hi(x_max, m0, m0, m1), cdesc[2], cdesc[3], INT_MAX);
+        __syncthreads(); // start 2
+        int y = 0;
+        bool stop = false;
+        // nkv / riv: ballot words and row info of the row being verified (row y-1); clo_n / cw_n: window of the
+        // chunk that holds row y+1
+        auto iteration = [&](const unsigned *nkv, const int *riv, int y_lim, int clo_n, int cw_n) {
+            // runs while the compute warps process row y: verify row y-1, publish the ranges of row y+1
+            const int an4 = p.nrg_xmin[min(y + 3, h - 1)], ax4 = p.nrg_xmax[min(y + 3, h - 1)];
+            const int yv = y - 1;
+            if (yv >= 1 && yv < h && yv < y_lim && fail_row == INT_MAX) {
+                const int bmin = max(min(x_min, an0) - D, 0);
+                const int bmax = min(max(x_max, ax0) + D, w - 1);
+                const int gb = riv[0], nwords = riv[1] * UT_NCW;
+                const unsigned wv = lane < nwords ? nkv[lane] : 0u;
+                const unsigned any = __ballot_sync(0xffffffffu, wv != 0u);
+                int F = INT_MAX, L = INT_MIN;
+                if (any) {
+                    const int lf = __ffs(any) - 1, ll = 31 - __clz(any);
+                    const unsigned wf = __shfl_sync(0xffffffffu, wv, lf), wl = __shfl_sync(0xffffffffu, wv, ll);
+                    F = gb + 32 * lf + (__ffs(wf) - 1);
+                    L = gb + 32 * ll + (31 - __clz(wl));
+                }
+                const int old_min = x_min, old_max = x_max;
+                bool violation;
+                if (bmax >= bmin) {
+                    cells += (unsigned long long) (bmax - bmin + 1);
+                    violation = any && (F < bmin || L > bmax);
+                    x_min = any ? F : bmax + 1;
+                    x_max = any ? (L == bmax ? bmax : L + 1) : bmin;
+                } else {
+                    violation = any != 0u;
+                    x_min = bmin;
+                    x_max = bmax;
+                }
+                if (violation) {
+                    fail_row = yv;
+                    if (lane == 0) {
+                        misc[1] = yv;
+                        misc[2] = old_min;
+                        misc[3] = old_max;
+                        __threadfence_block();
+                        misc[0] = 1;
+                    }
+                }
+            }
+            // active range of row y+1 from the limits after row y-1 (two rows of growth) and its guard range
+            if (lane == 0) {
+                publish(y + 1, max(0, min(x_min, min(an1, an2)) - 2 * D), min(w - 1, max(x_max, max(ax1, ax2)) + 2 * D),
+                        guard_lo(x_min, an1, an2, an3), guard_hi(x_max, ax1, ax2, ax3), clo_n, cw_n, fail_row);
+                if (fail_row == INT_MAX) misc[5] = min(y, y_lim); // rows [0, y) are verified (the DMA warp commits them)
+                __threadfence_block();
+            }
+            an0 = an1, an1 = an2, an2 = an3, an3 = an4;
+            ax0 = ax1, ax1 = ax2, ax2 = ax3, ax3 = ax4;
+        };
+        // The loop mirrors the compute warps' exactly (same stop predicate at the top of every row), so both
+        // roles execute the same sequence of row and chunk barriers.
+        const unsigned *nk_last = nk;
+        const int *ri_last = rinfo;
+        for (int k = 0;; ++k) {
+            const int *dsc = cdesc + (k & 3) * 4;
+            const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
+            if (rows == 0) break;
+            const int *dn = cdesc + ((k + 1) & 3) * 4; // next chunk (described at least one chunk ago)
+            const int clo_nx = dn[2], cw_nx = dn[3];
+            const unsigned *nkc = nk + (k & 1) * UT_MAXROWS * 32;
+            const int *ric = rinfo + (k & 1) * UT_MAXROWS * 4;
+            for (int r = 0; r < rows; ++r, ++y) {
+                if (fail_row <= y - 2) {
+                    stop = true;
+                    break;
+                }
+                const bool nx = r + 1 >= rows; // row y+1 opens the next chunk
+                if (r == 0) // row y-1 is the last row of the previous chunk
+                    iteration(nk_last, ri_last, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
+                else
+                    iteration(nkc + (r - 1) * 32, ric + (r - 1) * 4, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
+                if (r == rows - 1 && lane == 0) {
+                    // limits the DMA warp plans chunk k+3 from (it reads them after the chunk barrier)
+                    int *cl = clim + ((k + 1) & 1) * 4;
+                    cl[0] = x_min;
+                    cl[1] = x_max;
+                    cl[2] = max(y - 1, 0);
+                }
+                ut_bar_rows();
+            }
+            if (stop) break;
+            nk_last = nkc + (rows - 1) * 32;
+            ri_last = ric + (rows - 1) * 4;
+            __syncthreads(); // chunk end
+        }
+        if (!stop) {
+            const int y_end = y;
+            for (int d = 0; d < 2; ++d, ++y) {
+                if (fail_row <= y - 2) {
+                    stop = true;
+                    break;
+                }
+                iteration(nk_last, ri_last, y_end, 0, 0); // d == 0 verifies row y_end-1; d == 1 has nothing to verify
+                ut_bar_rows();
+            }
+            if (fail_row == INT_MAX && lane == 0 && y_end < h) {
+                // capacity stop: rows below y_end are exact; hand the exact limits to the generic loop
+                misc[1] = y_end;
+                misc[2] = x_min;
+                misc[3] = x_max;
+            }
+        }
+        if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
+    } else {
+        // =============================================================================== DMA warp
+        // Lane r owns row r of the chunk being handled (chunks have at most 8 rows).
+        // plan: rows / window of the chunk starting at row ya, from the limits (xv_min, xv_max) valid after row yv
+        auto plan = [&](int ya, int xv_min, int xv_max, int yv, int &rows, int &lo, int &cw) {
+            rows = 0, lo = 0, cw = 0;
+            if (ya >= h) return;
+            for (int want = UT_MAXROWS; want >= 2; want >>= 1) {
+                const int yb = min(ya + want, h) - 1;
+                // energy-band extremes over rows [yv+1, yb+2] (two rows per lane: up to 64 rows)
+                const int last = min(yb + 2, h - 1);
+                const int j0 = yv + 1 + lane, j1 = j0 + 32;
+                int nlo = j0 <= last ? p.nrg_xmin[j0] : INT_MAX, nhi = j0 <= last ? p.nrg_xmax[j0] : INT_MIN;
+                if (j1 <= last) {
+                    nlo = min(nlo, p.nrg_xmin[j1]);
+                    nhi = max(nhi, p.nrg_xmax[j1]);
+                }
+                nlo = __reduce_min_sync(0xffffffffu, nlo);
+                nhi = __reduce_max_sync(0xffffffffu, nhi);
+                // a band grows by at most delta_x per row beyond the energy bands; the guard range of the last
+                // row reaches 4 rows of growth past the limits verified two rows before it
+                const int dist = (yb + 3 - yv) * D;
+                lo = max(0, min(xv_min, nlo) - dist);
+                const int hi = min(w - 1, max(xv_max, nhi) + dist);
+                cw = max(hi - lo + 1, 0);
+                rows = yb - ya + 1;
+                // capacity: ids (cw+6) + three spans (each about cw + removed pixels inside, checked at issue time)
+                if (rows * (4 * cw + 64) <= UT_TILE && cw <= UT_MAXCW && yb + 1 - yv <= 63) return;
+                rows = 0;
+            }
+        };
+        // ids of the window ends of row ya + lane: the physical span [zlo, zhi] its en / m / least values occupy
+        auto span_ends = [&](int ya, int rows, int lo, int cw, int &zlo, int &zhi) {
+            zlo = 0, zhi = -1;
+            if (lane < rows && cw > 0) {
+                const int *rr = p.raw + (size_t) (ya + lane) * p.raw_stride;
+                zlo = rr[lo];
+                zhi = rr[lo + cw - 1];
+            }
+        };
+        // lay the chunk out in its tile, write the row tables and issue the bulk loads.  Returns the number of
+        // rows that fit (the spans are only known now); the chunk is cut there.
+        int issued_upto = -1; // last chunk whose bulk loads were issued
+        auto issue = [&](int kk, int ya, int rows, int lo, int cw, int zlo, int zhi) -> int {
+            int *tile = tiles + (kk % 3) * UT_TILE;
+            int *rtk = rtab + (kk % 3) * UT_MAXROWS * 8;
+            const int y = ya + lane;
+            const long long rawpos = (long long) y * p.raw_stride + lo;
+            const int rawbase = (int) (rawpos & ~3LL), nraw = (int) ((rawpos + cw - rawbase + 3) & ~3LL);
+            const int zbase = zlo & ~3, nsp = (zhi - zbase + 1 + 3) & ~3;
+            const int need = lane < rows ? nraw + 3 * nsp : 0;
+            // exclusive prefix of the per-row sizes -> word offset of each row in the tile
+            int off = need;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, off, s);
+                if (lane >= s) off += t;
+            }
+            const int fits = __popc(__ballot_sync(0xffffffffu, lane < rows && off <= UT_TILE));
+            const int nrows = fits; // rows are laid out in order, so the ones that fit form a prefix
+            off -= need;
+            unsigned bytes = 0;
+            if (lane < nrows) {
+                rtk[lane * 8 + 0] = off + (int) ((long long) y * p.raw_stride - rawbase); // id of column x: tile[xadd + x]
+                rtk[lane * 8 + 1] = off + nraw - zbase;                                    // e:     tile[eadd + z]
+                rtk[lane * 8 + 2] = off + nraw + nsp - zbase;                              // m:     tile[madd + z]
+                rtk[lane * 8 + 3] = off + nraw + 2 * nsp - zbase;                          // least: tile[ladd + z]
+                rtk[lane * 8 + 4] = zlo;
+                rtk[lane * 8 + 5] = zhi;
+                bytes = (unsigned) (nraw + 3 * nsp) * 4u;
+            }
+            unsigned total = bytes;
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
+            if (lane == 0 && nrows > 0) ut_mbar_expect(&mbar[kk % 3], total);
+            __syncwarp();
+            if (lane < nrows) {
+                if (nraw > 0) ut_bulk_load(tile + off, p.raw + rawbase, (unsigned) nraw * 4u, &mbar[kk % 3]);
+                if (nsp > 0) {
+                    ut_bulk_load(tile + off + nraw, p.en + zbase, (unsigned) nsp * 4u, &mbar[kk % 3]);
+                    ut_bulk_load(tile + off + nraw + nsp, p.m + zbase, (unsigned) nsp * 4u, &mbar[kk % 3]);
+                    ut_bulk_load(tile + off + nraw + 2 * nsp, p.least + zbase, (unsigned) nsp * 4u, &mbar[kk % 3]);
+                }
+            }
+            if (nrows > 0) issued_upto = kk;
+            return nrows;
+        };
+        auto put_desc = [&](int slot, int ya, int rows, int lo, int cw) {
+            if (lane == 0) {
+                int *d = cdesc + slot * 4;
+                d[0] = ya;
+                d[1] = rows;
+                d[2] = lo;
+                d[3] = cw;
+            }
+        };
+        const int b0min = max(p.nrg_xmin[0], 0), b0max = min(p.nrg_xmax[0], w - 1);
+        // c1 = chunk k+1 (loads in flight), c2 = chunk k+2 (planned, span ends loaded, loads not yet issued)
+        int ya1 = 0, rows1 = 0, ya2, rows2, lo2, cw2, zlo2, zhi2;
+        int rows_k;
+        {
+            // ---- prologue: chunks 0 and 1 loading, chunk 2 planned
+            int rows0, lo0, cw0, z0lo, z0hi;
+            plan(0, b0min, b0max, 0, rows0, lo0, cw0);
+            span_ends(0, rows0, lo0, cw0, z0lo, z0hi);
+            rows0 = issue(0, 0, rows0, lo0, cw0, z0lo, z0hi);
+            put_desc(0, 0, rows0, lo0, cw0);
+            int lo1 = 0, cw1 = 0, z1lo, z1hi;
+            ya1 = rows0;
+            if (rows0 > 0) plan(ya1, b0min, b0max, 0, rows1, lo1, cw1);
+            span_ends(ya1, rows1, lo1, cw1, z1lo, z1hi);
+            rows1 = issue(1, ya1, rows1, lo1, cw1, z1lo, z1hi);
+            put_desc(1, ya1, rows1, lo1, cw1);
+            ya2 = ya1 + rows1, rows2 = 0, lo2 = 0, cw2 = 0;
+            if (rows1 > 0) plan(ya2, b0min, b0max, 0, rows2, lo2, cw2);
+            span_ends(ya2, rows2, lo2, cw2, zlo2, zhi2);
+            rows_k = rows0; // chunk 2 is issued (and described) in iteration 0, before chunk 0 ends
+        }
+        __syncthreads(); // start 1
+        __syncthreads(); // start 2
+        // ---- steady state.  During chunk k: commit chunk k-1 (verified), issue the loads of chunk k+2, plan chunk
+        // k+3 and fetch its span ends.  Everything waited for was issued a whole chunk earlier.
+        for (int k = 0;; ++k) {
+            if (rows_k == 0) {
+                __syncthreads(); // matches the exit barrier of the other roles
+                break;
+            }
+            if (k > 0) {
+                // chunk k-1: its tile is recycled by chunk k+2, so its verified rows go back to HBM first.  Its last
+                // row is verified during row 0 of chunk k.
+                const int *dp = cdesc + ((k - 1) & 3) * 4;
+                const int yp0 = dp[0], prow = dp[1];
+                int done;
+                for (int spin = 0; (done = misc[5]) < yp0 + prow && misc[0] == 0; ++spin) {
+                    if (spin > (1 << 24)) {
+                        atomicOr(p.err, 8);
+                        break;
+                    }
+                    __nanosleep(32);
+                }
+                const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
+                if (lane < r_end)
+                    ut_commit_row(p, yp0 + lane, tiles + ((k - 1) % 3) * UT_TILE, rtab + ((k - 1) % 3) * UT_MAXROWS * 8 + lane * 8);
+                ut_bulk_commit();
+                ut_bulk_wait_read(); // the stores have read the tile: it may be overwritten
+                __syncwarp();
+            }
+            // chunk k+2: spans are known now (loaded during chunk k-1)
+            const int nrows2 = issue(k + 2, ya2, rows2, lo2, cw2, zlo2, zhi2);
+            if (nrows2 != rows2) {
+                rows2 = nrows2; // cut by the tile capacity: the next chunk starts right after the cut
+            }
+            put_desc((k + 2) & 3, ya2, rows2, lo2, cw2);
+            // chunk k+3: plan from the limits published at the end of chunk k-1 (or the initial band)
+            const int *cl = clim + (k & 1) * 4;
+            const int ya3 = ya2 + rows2;
+            int rows3 = 0, lo3 = 0, cw3 = 0, zlo3, zhi3;
+            if (rows2 > 0) plan(ya3, cl[0], cl[1], cl[2], rows3, lo3, cw3);
+            span_ends(ya3, rows3, lo3, cw3, zlo3, zhi3);
+            __syncthreads(); // chunk k end (or the exit barrier of a failed speculation)
+            if (misc[0]) break;
+            rows_k = rows1;
+            ya1 = ya2, rows1 = rows2;
+            ya2 = ya3, rows2 = rows3, lo2 = lo3, cw2 = cw3, zlo2 = zlo3, zhi2 = zhi3;
+        }
+        (void) ya1;
+        // bulk loads the compute warps will never wait for must still land before the CTA's shared memory goes away
+        if (lane == 0) misc[6] = issued_upto;
+    }
+
+    // =================================================================================== exit / fallback
+    if (tid < UT_CT + 32) __syncthreads(); // compute + control: exit barrier (the DMA warp already passed its own)
+    // commit what the DMA warp has not: the verified rows of the last chunk the compute warps entered
+    const int fb_row = misc[1], klast = misc[4];
+    if (warp == UT_NCW + 1) {
+        if (klast >= 0) {
+            const int *dl = cdesc + (klast & 3) * 4;
+            const int r_end = min(dl[1], max(min(fb_row, h) - dl[0], 0));
+            if (lane < r_end)
+                ut_commit_row(p, dl[0] + lane, tiles + (klast % 3) * UT_TILE, rtab + (klast % 3) * UT_MAXROWS * 8 + lane * 8);
+        }
+        ut_bulk_commit();
+        ut_bulk_wait_all(); // results are in HBM before the kernel ends / the generic loop reads them
+        for (int kk = klast + 1; kk <= (int) misc[6]; ++kk) // chunks staged ahead that nobody consumed
+            ut_mbar_wait(&mbar[kk % 3], (unsigned) ((kk / 3) & 1));
+    }
+    if (fb_row < h) {
+        __syncthreads();
+        update_rows_generic(p, fb_row, misc[2], misc[3], s_red);
+    }
+}
+
+} // namespace b200c

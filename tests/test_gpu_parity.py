@@ -28,14 +28,15 @@ def engine(pkg, product):
     return eng
 
 
-@pytest.fixture(params=["fast", "staged", "generic"])
+@pytest.fixture(params=["fast", "spec", "staged", "generic"])
 def kernel_mode(request):
-    """Every kernel set must match the oracle: "fast" (default: warp-specialised speculative band DP, windowed
-    backtrack, tiled full DP), "staged" (B200C_UPDATE=2: the cp.async-staged band DP that also serves rigidity),
+    """Every kernel set must match the oracle: "fast" (default: warp-specialised speculative band DP staged
+    and committed with TMA bulk copies, windowed backtrack, tiled full DP), "spec" (B200C_UPDATE=3: the same
+    band DP staged with cp.async gathers), "staged" (B200C_UPDATE=2: the cp.async-staged band DP that also serves rigidity),
     and "generic" (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at carver creation."""
     old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_UPDATE")}
     os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
-    os.environ["B200C_UPDATE"] = "2" if request.param == "staged" else "3"
+    os.environ["B200C_UPDATE"] = {"staged": "2", "spec": "3"}.get(request.param, "4")
     yield request.param
     for k, v in old.items():
         if v is None:
