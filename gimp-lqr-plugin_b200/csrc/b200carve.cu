@@ -126,6 +126,7 @@ struct B200Carver {
     int *vpath = nullptr, *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
+    long long *dbg_d = nullptr;               // role cycle counters (B200C_DBG=1)
     bool owns_stream = true;
     int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
@@ -209,6 +210,7 @@ DevP view(const B200Carver *c)
     p.nrg_xmax = c->nrg_xmax;
     p.err = c->err_d;
     p.cells = c->cells_d;
+    p.dbg = c->dbg_d;
     return p;
 }
 
@@ -786,6 +788,16 @@ void b200c_carver_destroy(B200Carver *c)
             g_update_cells += n;
     }
     dfree(c, c->cells_d);
+    if (c->dbg_d) {
+        long long v[16];
+        if (cudaMemcpyAsync(v, c->dbg_d, sizeof v, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+            cudaStreamSynchronize(c->stream) == cudaSuccess) {
+            fprintf(stderr, "b200c dbg:");
+            for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", v[i]);
+            fprintf(stderr, "\n");
+        }
+    }
+    dfree(c, c->dbg_d);
     dfree(c, c->rigmap_d);
     if (c->host_out) cudaFreeHost(c->host_out);
     if (c->stream) {
@@ -812,6 +824,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
+    if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));
     c->delta_x = delta_x;
     c->rigidity = rigidity;
     c->rigmap_h.assign(2 * delta_x + 1, 0.f);

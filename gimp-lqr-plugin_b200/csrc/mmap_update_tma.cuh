@@ -49,6 +49,9 @@ static constexpr size_t ut_smem_bytes()
 }
 
 __device__ __forceinline__ void ut_bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(UT_CT + 32) : "memory"); }
+// control -> DMA hand-shake, once per chunk: "the previous chunk is verified" (arrive: control, sync: DMA warp)
+__device__ __forceinline__ void ut_bar_commit_arrive() { asm volatile("bar.arrive 3, 64;" ::: "memory"); }
+__device__ __forceinline__ void ut_bar_commit_wait() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
 __device__ __forceinline__ unsigned ut_saddr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void ut_mbar_init(void *mbar, unsigned count)
 {
@@ -101,76 +104,66 @@ __device__ __forceinline__ void ut_fence_async() { asm volatile("fence.proxy.asy
 // range [gr_lo, gr_hi]: cells inside the active range are recomputed (parents from the previous row's ring),
 // the others only forward their old value / id to the ring for the next row's parents.  New value / parent are
 // left in place in the tile; `changed` bits go to nkrow.  rt = {xadd, eadd, madd, ladd}: tile word offsets.
+// The body is branch-free (out-of-range threads work on a clamped column, only the stores are predicated) so
+// that every shared-memory load of the cell is issued up front instead of one round trip after the other.
 template <int NS, bool D1>
-__device__ __forceinline__ void ut_row(const DevP &p, int y, int4 rt, int *__restrict__ tile, float *mrow, int *zrow,
-                                       int cur, int prev, int act_lo, int act_hi, int gr_lo, int gr_hi, unsigned *nkrow,
-                                       int tid, int lane, int warp)
+__device__ __forceinline__ void ut_row(const DevP &p, int y, int4 rt, int *__restrict__ tile, int2 *ring, int cur,
+                                       int prev, int act_lo, int act_hi, int gr_lo, int gr_hi, unsigned *nkrow, int tid,
+                                       int lane, int warp)
 {
     const int w = p.w;
     float *tilef = reinterpret_cast<float *>(tile);
+    const bool row0 = y == 0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
         const int x = gr_lo + j * UT_CT + tid;
-        bool changed = false;
-        if (x <= gr_hi) {
-            const int rb = x & UT_RWM;
-            const int z = tile[rt.x + x];
-            const float mo = tilef[rt.z + z];
-            float val = mo;
-            if (x >= act_lo && x <= act_hi) {
-                const float e = tilef[rt.y + z];
-                if (y == 0) {
-                    val = e; // row 0: m = en over the (exact) band
-                    tilef[rt.z + z] = e;
-                } else {
-                    float best;
-                    int parent;
-                    if (D1) {
-                        const float inf = __int_as_float(0x7f800000);
-                        const float m0 = mrow[prev + rb];
-                        const int z0 = zrow[prev + rb];
-                        float ml = mrow[prev + ((rb - 1) & UT_RWM)];
-                        const int zl = zrow[prev + ((rb - 1) & UT_RWM)];
-                        float mr = mrow[prev + ((rb + 1) & UT_RWM)];
-                        const int zr = zrow[prev + ((rb + 1) & UT_RWM)];
-                        // left-to-right scan with strict '<' == leftmost minimum; ties go right when leftright == 1.
-                        // (all m are finite: an out-of-image neighbour is replaced by +inf and can never win)
-                        ml = x > 0 ? ml : inf;
-                        mr = x < w - 1 ? mr : inf;
-                        best = fminf(fminf(ml, m0), mr);
-                        if (p.leftright)
-                            parent = mr == best ? zr : (m0 == best ? z0 : zl);
-                        else
-                            parent = ml == best ? zl : (m0 == best ? z0 : zr);
-                    } else {
-                        const int D = p.delta_x;
-                        const int dlo = max(-x, -D), dhi = min(w - 1 - x, D);
-                        int bdx = dlo;
-                        best = mrow[prev + ((x + dlo) & UT_RWM)];
-                        for (int dx = dlo + 1; dx <= dhi; ++dx) {
-                            const float cand = mrow[prev + ((x + dx) & UT_RWM)];
-                            if (cand < best || (cand == best && p.leftright == 1)) {
-                                best = cand;
-                                bdx = dx;
-                            }
-                        }
-                        parent = zrow[prev + ((x + bdx) & UT_RWM)];
-                    }
-                    const float new_m = __fadd_rn(e, best);
-                    // (double) |d| < 1e-5  <=>  |d| <= 0x3727C5AC: that float is the largest one below the double 1e-5
-                    const bool keep =
-                        (tile[rt.w + z] == parent) && (fabsf(__fsub_rn(mo, new_m)) <= __int_as_float(0x3727C5AC));
-                    if (!keep) {
-                        val = new_m;
-                        changed = true;
-                        tilef[rt.z + z] = new_m;
-                        tile[rt.w + z] = parent;
-                    }
+        const bool valid = x <= gr_hi;
+        const int xc = min(x, gr_hi); // a column that is certainly staged
+        const int rb = xc & UT_RWM;
+        const int z = tile[rt.x + xc];
+        float best;
+        int parent;
+        if (D1) {
+            const int2 c0 = ring[prev + rb];
+            const int2 cl = ring[prev + ((rb - 1) & UT_RWM)];
+            const int2 cr = ring[prev + ((rb + 1) & UT_RWM)];
+            const float inf = __int_as_float(0x7f800000);
+            // left-to-right scan with strict '<' == leftmost minimum; ties go right when leftright == 1.
+            // (all m are finite: an out-of-image neighbour is replaced by +inf and can never win)
+            const float m0 = __int_as_float(c0.x);
+            const float ml = xc > 0 ? __int_as_float(cl.x) : inf;
+            const float mr = xc < w - 1 ? __int_as_float(cr.x) : inf;
+            best = fminf(fminf(ml, m0), mr);
+            if (p.leftright)
+                parent = mr == best ? cr.y : (m0 == best ? c0.y : cl.y);
+            else
+                parent = ml == best ? cl.y : (m0 == best ? c0.y : cr.y);
+        } else {
+            const int D = p.delta_x;
+            const int dlo = max(-xc, -D), dhi = min(w - 1 - xc, D);
+            int bdx = dlo;
+            best = __int_as_float(ring[prev + ((xc + dlo) & UT_RWM)].x);
+            for (int dx = dlo + 1; dx <= dhi; ++dx) {
+                const float cand = __int_as_float(ring[prev + ((xc + dx) & UT_RWM)].x);
+                if (cand < best || (cand == best && p.leftright == 1)) {
+                    best = cand;
+                    bdx = dx;
                 }
             }
-            mrow[cur + rb] = val;
-            zrow[cur + rb] = z;
+            parent = ring[prev + ((xc + bdx) & UT_RWM)].y;
         }
+        const float mo = tilef[rt.z + z];
+        const float e = tilef[rt.y + z];
+        const int lold = tile[rt.w + z];
+        const bool in_act = valid && x >= act_lo && x <= act_hi;
+        const float new_m = __fadd_rn(e, best);
+        // (double) |d| < 1e-5  <=>  |d| <= 0x3727C5AC: that float is the largest one below the double 1e-5
+        const bool keep = (lold == parent) && (fabsf(__fsub_rn(mo, new_m)) <= __int_as_float(0x3727C5AC));
+        const bool changed = in_act && !row0 && !keep;
+        const float val = in_act ? (row0 ? e : (keep ? mo : new_m)) : mo; // row 0: m = en over the (exact) band
+        if (changed || (in_act && row0)) tilef[rt.z + z] = val;
+        if (changed) tile[rt.w + z] = parent;
+        if (valid) ring[cur + rb] = make_int2(__float_as_int(val), z);
         const unsigned word = __ballot_sync(0xffffffffu, changed);
         if (lane == 0) nkrow[j * UT_NCW + warp] = word;
     }
@@ -207,9 +200,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
 {
     extern __shared__ __align__(128) unsigned char ut_smem[];
     int *tiles = reinterpret_cast<int *>(ut_smem);                    // [3][UT_TILE] chunk tiles
-    float *mrow = reinterpret_cast<float *>(tiles + 3 * UT_TILE);     // [2][RW] previous / current row values
-    int *zrow = reinterpret_cast<int *>(mrow + 2 * UT_RW);            // [2][RW] previous / current row ids
-    unsigned *nk = reinterpret_cast<unsigned *>(zrow + 2 * UT_RW);    // [2][8][32] "changed" ballot words
+    int2 *ring = reinterpret_cast<int2 *>(tiles + 3 * UT_TILE);       // [2][RW] {m bits, id} of the previous / current row
+    unsigned *nk = reinterpret_cast<unsigned *>(ring + 2 * UT_RW);    // [2][8][32] "changed" ballot words
     int *rinfo = reinterpret_cast<int *>(nk + UT_NKW);                // [2][8][4] guard base, slots
     int *rtab = rinfo + UT_RIW;                                       // [3][8][8] row tables of the tiles
     int *pub = rtab + UT_RTW;                                         // [2][8] act_lo, act_hi, fail_row, slots, gr_lo, gr_hi
@@ -241,6 +233,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         __syncthreads(); // start 2: ranges of row 0 published
         int y = 0;
         bool failed = false;
+        long long dbg_work = 0, dbg_bar = 0, dbg_chunk = 0, dbg_mb = 0;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1];
@@ -250,10 +243,13 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int *rtc = rtab + (k % 3) * UT_MAXROWS * 8;
             unsigned *nkc = nk + (k & 1) * UT_MAXROWS * 32;
             int *ric = rinfo + (k & 1) * UT_MAXROWS * 4;
+            long long t0 = clock64();
             if (!ut_mbar_wait(&mbar[k % 3], (unsigned) ((k / 3) & 1))) // the chunk's bulk loads have landed
                 atomicOr(p.err, 4);
+            dbg_mb += clock64() - t0;
             for (int r = 0; r < rows; ++r, ++y) {
                 const int par = y & 1;
+                const long long t1 = clock64();
                 // ranges of this row, already clamped to the chunk window by the control warp
                 const int4 pa = *reinterpret_cast<const int4 *>(pub + par * 8);
                 const int2 pg = *reinterpret_cast<const int2 *>(pub + par * 8 + 4);
@@ -265,21 +261,33 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 const int act_lo = pa.x, act_hi = pa.y, ns = pa.w, gr_lo = pg.x, gr_hi = pg.y;
                 const int cur = par * UT_RW, prev = (par ^ 1) * UT_RW;
                 unsigned *nkrow = nkc + r * 32;
-                if (tid == 0) {
-                    ric[r * 4 + 0] = gr_lo;
-                    ric[r * 4 + 1] = ns;
-                }
-                if (ns == 1)
-                    ut_row<1, D1>(p, y, rt, tile, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                if (tid == 0) *reinterpret_cast<int2 *>(ric + r * 4) = make_int2(gr_lo, ns);
+                if (gr_hi < gr_lo) {
+                    if (lane == 0) // nothing staged is needed by the next row: no cell, no changed bit
+                        for (int j = 0; j < ns; ++j) nkrow[j * UT_NCW + warp] = 0u;
+                } else if (ns == 1)
+                    ut_row<1, D1>(p, y, rt, tile, ring, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
                 else if (ns == 2)
-                    ut_row<2, D1>(p, y, rt, tile, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                    ut_row<2, D1>(p, y, rt, tile, ring, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
                 else
-                    ut_row<4, D1>(p, y, rt, tile, mrow, zrow, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                    ut_row<4, D1>(p, y, rt, tile, ring, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                const long long t2 = clock64();
                 ut_bar_rows();
+                const long long t3 = clock64();
+                dbg_work += t2 - t1;
+                dbg_bar += t3 - t2;
             }
             ut_fence_async(); // tile writes (generic proxy) -> visible to the TMA stores (async proxy)
             if (failed) break;
+            const long long t4 = clock64();
             __syncthreads(); // chunk end
+            dbg_chunk += clock64() - t4;
+        }
+        if (p.dbg && lane == 0) {
+            atomicAdd((unsigned long long *) &p.dbg[0 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_work);
+            atomicAdd((unsigned long long *) &p.dbg[1 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_bar);
+            atomicAdd((unsigned long long *) &p.dbg[2 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_chunk);
+            atomicAdd((unsigned long long *) &p.dbg[3 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_mb);
         }
         if (!failed) {
             // drain: the last two rows still wait for verification
@@ -304,12 +312,9 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int gl = max(g_lo, clo_r), gh = min(g_hi, clo_r + cw_r - 1);
             const int gw = gh - gl + 1;
             int *pb = pub + (yr & 1) * 8;
-            pb[0] = max(a_lo, gl);
-            pb[1] = min(a_hi, gh);
-            pb[2] = fail;
-            pb[3] = gw <= UT_CT ? 1 : (gw <= 2 * UT_CT ? 2 : 4);
-            pb[4] = gl;
-            pb[5] = gh;
+            *reinterpret_cast<int4 *>(pb) =
+                make_int4(max(a_lo, gl), min(a_hi, gh), fail, gw <= UT_CT ? 1 : (gw <= 2 * UT_CT ? 2 : 4));
+            *reinterpret_cast<int2 *>(pb + 4) = make_int2(gl, gh);
         };
         if (lane == 0) {
             clim[0] = x_min;
@@ -372,7 +377,6 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 publish(y + 1, max(0, min(x_min, min(an1, an2)) - 2 * D), min(w - 1, max(x_max, max(ax1, ax2)) + 2 * D),
                         guard_lo(x_min, an1, an2, an3), guard_hi(x_max, ax1, ax2, ax3), clo_n, cw_n, fail_row);
                 if (fail_row == INT_MAX) misc[5] = min(y, y_lim); // rows [0, y) are verified (the DMA warp commits them)
-                __threadfence_block();
             }
             an0 = an1, an1 = an2, an2 = an3, an3 = an4;
             ax0 = ax1, ax1 = ax2, ax2 = ax3, ax3 = ax4;
@@ -381,6 +385,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         // roles execute the same sequence of row and chunk barriers.
         const unsigned *nk_last = nk;
         const int *ri_last = rinfo;
+        long long ctl_bar = 0, ctl_t0 = clock64();
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
@@ -392,6 +397,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             for (int r = 0; r < rows; ++r, ++y) {
                 if (fail_row <= y - 2) {
                     stop = true;
+                    if (r == 0 && k > 0) ut_bar_commit_arrive(); // the DMA warp waits for this chunk's hand-shake
                     break;
                 }
                 const bool nx = r + 1 >= rows; // row y+1 opens the next chunk
@@ -399,6 +405,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                     iteration(nk_last, ri_last, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
                 else
                     iteration(nkc + (r - 1) * 32, ric + (r - 1) * 4, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
+                if (r == 0 && k > 0) ut_bar_commit_arrive(); // chunk k-1 is verified to its last row: it may be committed
+                const long long tc1 = clock64();
                 if (r == rows - 1 && lane == 0) {
                     // limits the DMA warp plans chunk k+3 from (it reads them after the chunk barrier)
                     int *cl = clim + ((k + 1) & 1) * 4;
@@ -407,6 +415,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                     cl[2] = max(y - 1, 0);
                 }
                 ut_bar_rows();
+                ctl_bar += clock64() - tc1;
             }
             if (stop) break;
             nk_last = nkc + (rows - 1) * 32;
@@ -431,6 +440,10 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             }
         }
         if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
+        if (p.dbg && lane == 0) {
+            atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) ctl_bar);
+            atomicAdd((unsigned long long *) &p.dbg[13], (unsigned long long) (clock64() - ctl_t0));
+        }
     } else {
         // =============================================================================== DMA warp
         // Lane r owns row r of the chunk being handled (chunks have at most 8 rows).
@@ -563,14 +576,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 // row is verified during row 0 of chunk k.
                 const int *dp = cdesc + ((k - 1) & 3) * 4;
                 const int yp0 = dp[0], prow = dp[1];
-                int done;
-                for (int spin = 0; (done = misc[5]) < yp0 + prow && misc[0] == 0; ++spin) {
-                    if (spin > (1 << 24)) {
-                        atomicOr(p.err, 8);
-                        break;
-                    }
-                    __nanosleep(32);
-                }
+                ut_bar_commit_wait();
+                const int done = misc[5];
                 const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
                 if (lane < r_end)
                     ut_commit_row(p, yp0 + lane, tiles + ((k - 1) % 3) * UT_TILE, rtab + ((k - 1) % 3) * UT_MAXROWS * 8 + lane * 8);
