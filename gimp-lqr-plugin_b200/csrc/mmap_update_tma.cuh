@@ -1,9 +1,9 @@
 // mmap_update_tma.cuh -- K2b, the incremental m-map DP after one carve (liblqr lqr_carver_update_mmap,
 // SURVEY.md A.8): warp-specialised, verified-speculative, staged and committed with TMA bulk copies.
 //
-// One CTA of 10 warps on one SM (the algorithm is a row-serial chain):
+// One CTA of 14 warps on one SM (the algorithm is a row-serial chain):
 //
-//   * 8 COMPUTE warps walk the rows.  Per row a thread does one cell (2 or 4 for very wide bands) entirely from
+//   * 12 COMPUTE warps walk the rows.  Per row a thread does one cell (2 or 3 for very wide windows) entirely from
 //     shared memory: parents from the previous row's ring (mrow/zrow), the cell's own id / energy / old m / old
 //     parent from the chunk tile.  They do NOT wait for the exact band limits of the row: they recompute a
 //     slightly wider ACTIVE range (the limits verified two rows earlier, grown by 2*delta_x and the energy bands
@@ -24,23 +24,24 @@
 //     No per-cell staging or commit instruction exists anywhere.
 //
 // Dependent chain per row on the compute warps: LDS parents -> min/select -> FADD -> keep test -> STS -> named
-// barrier (288 threads).
+// barrier (416 threads).
 #pragma once
 #include "carver_kernels.cuh"
 #include "mmap_update_fast.cuh"
 
 namespace b200c {
 
-#define UT_NCW 8
+#define UT_NCW 12
 #define UT_CT (UT_NCW * 32)
 #define UT_THREADS (UT_CT + 64)
 #define UT_TILE 13312 // words per chunk tile (3 tiles)
 #define UT_RW 2048
 #define UT_RWM (UT_RW - 1)
 #define UT_MAXROWS 8
-#define UT_MAXCW (UT_CT * 4)
+#define UT_MAXCW 1024
+#define UT_NKS 40 // ballot words per row (36 used: 3 slots x 12 warps)
 
-#define UT_NKW (2 * UT_MAXROWS * 32) // ballot words [chunk parity][row][32]
+#define UT_NKW (2 * UT_MAXROWS * UT_NKS) // ballot words [chunk parity][row][UT_NKS]
 #define UT_RIW (2 * UT_MAXROWS * 4)  // row info     [chunk parity][row]{guard base, slots}
 #define UT_RTW (3 * UT_MAXROWS * 8)  // row tables   [tile][row]{xadd, eadd, madd, ladd, zlo, zhi, -, -}
 static constexpr size_t ut_smem_bytes()
@@ -100,39 +101,44 @@ __device__ __forceinline__ void ut_bulk_wait_read() { asm volatile("cp.async.bul
 __device__ __forceinline__ void ut_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void ut_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// One row of the compute warps.  Thread t handles the columns gr_lo + t + 256*j (j < NS) of the row's guard
-// range [gr_lo, gr_hi]: cells inside the active range are recomputed (parents from the previous row's ring),
-// the others only forward their old value / id to the ring for the next row's parents.  New value / parent are
-// left in place in the tile; `changed` bits go to nkrow.  rt = {xadd, eadd, madd, ladd}: tile word offsets.
-// The body is branch-free (out-of-range threads work on a clamped column, only the stores are predicated) so
-// that every shared-memory load of the cell is issued up front instead of one round trip after the other.
+// Per-chunk constants of a compute thread: it owns the columns clo + tid + 384*j of the chunk window for the
+// whole chunk, so every address that does not depend on the row is computed once per chunk.
+struct UtSlot {
+    int x;      // absolute column (clamped into the window for address purposes)
+    int rb;     // ring index of x
+    int rbl;    // ring index of x-1
+    int rbr;    // ring index of x+1
+    bool live;  // the column exists in this chunk's window
+};
+
+// One row of the compute warps.  Cells inside the row's guard range forward their value / id to the ring for the
+// next row's parents; those inside the active range are recomputed first (parents from the previous row's ring).
+// New value / parent are left in place in the tile; `changed` bits go to nkrow.  rt = {xadd, eadd, madd, ladd}:
+// tile word offsets.  The body is branch-free (only the stores are predicated) so that every shared-memory load
+// of the cell is issued up front instead of one round trip after the other.
 template <int NS, bool D1>
-__device__ __forceinline__ void ut_row(const DevP &p, int y, int4 rt, int *__restrict__ tile, int2 *ring, int cur,
-                                       int prev, int act_lo, int act_hi, int gr_lo, int gr_hi, unsigned *nkrow, int tid,
-                                       int lane, int warp)
+__device__ __forceinline__ void ut_row(const DevP &p, bool row0, int4 rt, int *__restrict__ tile, int2 *ring_cur,
+                                       const int2 *ring_prev, int act_lo, int act_hi, int gr_lo, int gr_hi,
+                                       const UtSlot *sl, unsigned *nkrow, int lane, int warp)
 {
     const int w = p.w;
     float *tilef = reinterpret_cast<float *>(tile);
-    const bool row0 = y == 0;
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        const int x = gr_lo + j * UT_CT + tid;
-        const bool valid = x <= gr_hi;
-        const int xc = min(x, gr_hi); // a column that is certainly staged
-        const int rb = xc & UT_RWM;
-        const int z = tile[rt.x + xc];
+        const int x = sl[j].x;
+        const int z = tile[rt.x + x];
         float best;
         int parent;
         if (D1) {
-            const int2 c0 = ring[prev + rb];
-            const int2 cl = ring[prev + ((rb - 1) & UT_RWM)];
-            const int2 cr = ring[prev + ((rb + 1) & UT_RWM)];
+            const int2 c0 = ring_prev[sl[j].rb];
+            const int2 cl = ring_prev[sl[j].rbl];
+            const int2 cr = ring_prev[sl[j].rbr];
             const float inf = __int_as_float(0x7f800000);
             // left-to-right scan with strict '<' == leftmost minimum; ties go right when leftright == 1.
             // (all m are finite: an out-of-image neighbour is replaced by +inf and can never win)
             const float m0 = __int_as_float(c0.x);
-            const float ml = xc > 0 ? __int_as_float(cl.x) : inf;
-            const float mr = xc < w - 1 ? __int_as_float(cr.x) : inf;
+            const float ml = x > 0 ? __int_as_float(cl.x) : inf;
+            const float mr = x < w - 1 ? __int_as_float(cr.x) : inf;
             best = fminf(fminf(ml, m0), mr);
             if (p.leftright)
                 parent = mr == best ? cr.y : (m0 == best ? c0.y : cl.y);
@@ -140,22 +146,23 @@ __device__ __forceinline__ void ut_row(const DevP &p, int y, int4 rt, int *__res
                 parent = ml == best ? cl.y : (m0 == best ? c0.y : cr.y);
         } else {
             const int D = p.delta_x;
-            const int dlo = max(-xc, -D), dhi = min(w - 1 - xc, D);
+            const int dlo = max(-x, -D), dhi = min(w - 1 - x, D);
             int bdx = dlo;
-            best = __int_as_float(ring[prev + ((xc + dlo) & UT_RWM)].x);
+            best = __int_as_float(ring_prev[(x + dlo) & UT_RWM].x);
             for (int dx = dlo + 1; dx <= dhi; ++dx) {
-                const float cand = __int_as_float(ring[prev + ((xc + dx) & UT_RWM)].x);
+                const float cand = __int_as_float(ring_prev[(x + dx) & UT_RWM].x);
                 if (cand < best || (cand == best && p.leftright == 1)) {
                     best = cand;
                     bdx = dx;
                 }
             }
-            parent = ring[prev + ((xc + bdx) & UT_RWM)].y;
+            parent = ring_prev[(x + bdx) & UT_RWM].y;
         }
         const float mo = tilef[rt.z + z];
         const float e = tilef[rt.y + z];
         const int lold = tile[rt.w + z];
-        const bool in_act = valid && x >= act_lo && x <= act_hi;
+        const bool in_gr = sl[j].live && x >= gr_lo && x <= gr_hi;
+        const bool in_act = in_gr && x >= act_lo && x <= act_hi;
         const float new_m = __fadd_rn(e, best);
         // (double) |d| < 1e-5  <=>  |d| <= 0x3727C5AC: that float is the largest one below the double 1e-5
         const bool keep = (lold == parent) && (fabsf(__fsub_rn(mo, new_m)) <= __int_as_float(0x3727C5AC));
@@ -163,7 +170,7 @@ __device__ __forceinline__ void ut_row(const DevP &p, int y, int4 rt, int *__res
         const float val = in_act ? (row0 ? e : (keep ? mo : new_m)) : mo; // row 0: m = en over the (exact) band
         if (changed || (in_act && row0)) tilef[rt.z + z] = val;
         if (changed) tile[rt.w + z] = parent;
-        if (valid) ring[cur + rb] = make_int2(__float_as_int(val), z);
+        if (in_gr) ring_cur[sl[j].rb] = make_int2(__float_as_int(val), z);
         const unsigned word = __ballot_sync(0xffffffffu, changed);
         if (lane == 0) nkrow[j * UT_NCW + warp] = word;
     }
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
     extern __shared__ __align__(128) unsigned char ut_smem[];
     int *tiles = reinterpret_cast<int *>(ut_smem);                    // [3][UT_TILE] chunk tiles
     int2 *ring = reinterpret_cast<int2 *>(tiles + 3 * UT_TILE);       // [2][RW] {m bits, id} of the previous / current row
-    unsigned *nk = reinterpret_cast<unsigned *>(ring + 2 * UT_RW);    // [2][8][32] "changed" ballot words
+    unsigned *nk = reinterpret_cast<unsigned *>(ring + 2 * UT_RW);    // [2][8][UT_NKS] "changed" ballot words
     int *rinfo = reinterpret_cast<int *>(nk + UT_NKW);                // [2][8][4] guard base, slots
     int *rtab = rinfo + UT_RIW;                                       // [3][8][8] row tables of the tiles
     int *pub = rtab + UT_RTW;                                         // [2][8] act_lo, act_hi, fail_row, slots, gr_lo, gr_hi
@@ -233,23 +240,29 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         __syncthreads(); // start 2: ranges of row 0 published
         int y = 0;
         bool failed = false;
-        long long dbg_work = 0, dbg_bar = 0, dbg_chunk = 0, dbg_mb = 0;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
-            const int rows = dsc[1];
+            const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
             if (tid == 0) misc[4] = k;
             int *tile = tiles + (k % 3) * UT_TILE;
             const int *rtc = rtab + (k % 3) * UT_MAXROWS * 8;
-            unsigned *nkc = nk + (k & 1) * UT_MAXROWS * 32;
-            int *ric = rinfo + (k & 1) * UT_MAXROWS * 4;
-            long long t0 = clock64();
+            unsigned *nkc = nk + (k & 1) * UT_MAXROWS * UT_NKS;
+            const int ns = cw <= UT_CT ? 1 : (cw <= 2 * UT_CT ? 2 : 3);
+            UtSlot sl[3];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int c = j * UT_CT + tid;
+                sl[j].live = c < cw;
+                sl[j].x = clo + min(c, max(cw - 1, 0));
+                sl[j].rb = sl[j].x & UT_RWM;
+                sl[j].rbl = (sl[j].x - 1) & UT_RWM;
+                sl[j].rbr = (sl[j].x + 1) & UT_RWM;
+            }
             if (!ut_mbar_wait(&mbar[k % 3], (unsigned) ((k / 3) & 1))) // the chunk's bulk loads have landed
                 atomicOr(p.err, 4);
-            dbg_mb += clock64() - t0;
             for (int r = 0; r < rows; ++r, ++y) {
                 const int par = y & 1;
-                const long long t1 = clock64();
                 // ranges of this row, already clamped to the chunk window by the control warp
                 const int4 pa = *reinterpret_cast<const int4 *>(pub + par * 8);
                 const int2 pg = *reinterpret_cast<const int2 *>(pub + par * 8 + 4);
@@ -258,36 +271,22 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                     failed = true;
                     break;
                 }
-                const int act_lo = pa.x, act_hi = pa.y, ns = pa.w, gr_lo = pg.x, gr_hi = pg.y;
-                const int cur = par * UT_RW, prev = (par ^ 1) * UT_RW;
-                unsigned *nkrow = nkc + r * 32;
-                if (tid == 0) *reinterpret_cast<int2 *>(ric + r * 4) = make_int2(gr_lo, ns);
-                if (gr_hi < gr_lo) {
-                    if (lane == 0) // nothing staged is needed by the next row: no cell, no changed bit
-                        for (int j = 0; j < ns; ++j) nkrow[j * UT_NCW + warp] = 0u;
+                int2 *ring_cur = ring + par * UT_RW;
+                const int2 *ring_prev = ring + (par ^ 1) * UT_RW;
+                unsigned *nkrow = nkc + r * UT_NKS;
+                if (cw <= 0) {
+                    if (lane == 0) nkrow[warp] = 0u;
                 } else if (ns == 1)
-                    ut_row<1, D1>(p, y, rt, tile, ring, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                    ut_row<1, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp);
                 else if (ns == 2)
-                    ut_row<2, D1>(p, y, rt, tile, ring, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
+                    ut_row<2, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp);
                 else
-                    ut_row<4, D1>(p, y, rt, tile, ring, cur, prev, act_lo, act_hi, gr_lo, gr_hi, nkrow, tid, lane, warp);
-                const long long t2 = clock64();
+                    ut_row<3, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp);
                 ut_bar_rows();
-                const long long t3 = clock64();
-                dbg_work += t2 - t1;
-                dbg_bar += t3 - t2;
             }
             ut_fence_async(); // tile writes (generic proxy) -> visible to the TMA stores (async proxy)
             if (failed) break;
-            const long long t4 = clock64();
             __syncthreads(); // chunk end
-            dbg_chunk += clock64() - t4;
-        }
-        if (p.dbg && lane == 0) {
-            atomicAdd((unsigned long long *) &p.dbg[0 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_work);
-            atomicAdd((unsigned long long *) &p.dbg[1 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_bar);
-            atomicAdd((unsigned long long *) &p.dbg[2 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_chunk);
-            atomicAdd((unsigned long long *) &p.dbg[3 + (warp == 0 ? 0 : (warp == 3 ? 4 : 8))], (unsigned long long) dbg_mb);
         }
         if (!failed) {
             // drain: the last two rows still wait for verification
@@ -298,102 +297,107 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         }
     } else if (is_control) {
         // =============================================================================== CONTROL
-        int x_min = max(p.nrg_xmin[0], 0), x_max = min(p.nrg_xmax[0], w - 1);
+        // Lane-parallel: even lanes carry the LOW side (x_min, energy-band minima), odd lanes the HIGH side with
+        // every quantity negated (-x_max, -maxima), so that one instruction stream computes both ends of every
+        // range: "lower limit" = max(floor, min(...) - growth) on either side.
+        const bool hi = lane & 1;
+        const int sgn = hi ? -1 : 1;
+        const int floor_s = hi ? -(w - 1) : 0;
+        const int *nrg = hi ? p.nrg_xmax : p.nrg_xmin;
+        int xm = hi ? -min(p.nrg_xmax[0], w - 1) : max(p.nrg_xmin[0], 0); // x_min | -x_max
         int fail_row = INT_MAX;
         unsigned long long cells = 0;
-        // guard range of a row: every column the NEXT row's active range (+- delta_x parents) can need
-        auto guard_lo = [&](int xm, int a, int b, int c) { return max(0, min(xm, min(a, min(b, c))) - 4 * D); };
-        auto guard_hi = [&](int xm, int a, int b, int c) { return min(w - 1, max(xm, max(a, max(b, c))) + 4 * D); };
-        const int n0 = p.nrg_xmin[0], n1 = p.nrg_xmin[min(1, h - 1)], n2 = p.nrg_xmin[min(2, h - 1)];
-        const int m0 = p.nrg_xmax[0], m1 = p.nrg_xmax[min(1, h - 1)], m2 = p.nrg_xmax[min(2, h - 1)];
-        // publish the ranges of row `yr` (window clo/cw of its chunk): active range from limits + two rows of
-        // growth, guard range from four; both clamped to the staged window; slots per thread from the guard width
-        auto publish = [&](int yr, int a_lo, int a_hi, int g_lo, int g_hi, int clo_r, int cw_r, int fail) {
-            const int gl = max(g_lo, clo_r), gh = min(g_hi, clo_r + cw_r - 1);
-            const int gw = gh - gl + 1;
-            int *pb = pub + (yr & 1) * 8;
-            *reinterpret_cast<int4 *>(pb) =
-                make_int4(max(a_lo, gl), min(a_hi, gh), fail, gw <= UT_CT ? 1 : (gw <= 2 * UT_CT ? 2 : 4));
-            *reinterpret_cast<int2 *>(pb + 4) = make_int2(gl, gh);
-        };
-        if (lane == 0) {
-            clim[0] = x_min;
-            clim[1] = x_max;
-            clim[2] = 0;
-        }
-        // rolling window of the energy-band limits: a*0 = row y-1, a*1 = row y, a*2 = row y+1, a*3 = row y+2
-        int an0 = 0, an1 = n0, an2 = n1, an3 = n2;
-        int ax0 = 0, ax1 = m0, ax2 = m1, ax3 = m2;
+        if (lane < 2) clim[lane] = sgn * xm;
+        if (lane == 0) clim[2] = 0;
+        // rolling window of the energy-band limits (this lane's side): a0 = row y-1, a1 = row y, ... a3 = row y+2
+        int a0 = 0, a1 = sgn * nrg[0], a2 = sgn * nrg[min(1, h - 1)], a3 = sgn * nrg[min(2, h - 1)];
         __syncthreads(); // start 1: the DMA warp described chunks 0..2
-        if (lane == 0) // row 0: the active range is the exact band (m = en there)
-            publish(0, x_min, x_max, guard_lo(x_min, n0, n0, n1), guard_hi(x_max, m0, m0, m1), cdesc[2], cdesc[3], INT_MAX);
+        {
+            // row 0: the active range is the exact band (m = en there); guard from (row 0, row 0, row 1)
+            const int wb = hi ? -(cdesc[2] + cdesc[3] - 1) : cdesc[2];
+            const int g = max(max(floor_s, min(xm, min(a1, a2)) - 4 * D), wb);
+            const int a = max(xm, g);
+            if (lane < 2) {
+                pub[lane] = sgn * a;
+                pub[4 + lane] = sgn * g;
+            }
+            if (lane == 0) pub[2] = INT_MAX;
+        }
         __syncthreads(); // start 2
         int y = 0;
         bool stop = false;
-        // nkv / riv: ballot words and row info of the row being verified (row y-1); clo_n / cw_n: window of the
-        // chunk that holds row y+1
-        auto iteration = [&](const unsigned *nkv, const int *riv, int y_lim, int clo_n, int cw_n) {
+        // nkv: ballot words of the row being verified (row y-1, window start clo_v, width cw_v);
+        // clo_n / cw_n: window of the chunk that holds row y+1
+        auto iteration = [&](const unsigned *nkv, int clo_v, int cw_v, int y_lim, int clo_n, int cw_n) {
             // runs while the compute warps process row y: verify row y-1, publish the ranges of row y+1
-            const int an4 = p.nrg_xmin[min(y + 3, h - 1)], ax4 = p.nrg_xmax[min(y + 3, h - 1)];
+            const int a4 = sgn * nrg[min(y + 3, h - 1)];
             const int yv = y - 1;
             if (yv >= 1 && yv < h && yv < y_lim && fail_row == INT_MAX) {
-                const int bmin = max(min(x_min, an0) - D, 0);
-                const int bmax = min(max(x_max, ax0) + D, w - 1);
-                const int gb = riv[0], nwords = riv[1] * UT_NCW;
+                const int b = max(min(xm, a0) - D, floor_s); // bmin | -bmax of row yv
+                const int bo = __shfl_xor_sync(0xffffffffu, b, 1);
+                const bool nonempty = b + bo <= 0;
+                const int nwords = (cw_v + 31) >> 5;
                 const unsigned wv = lane < nwords ? nkv[lane] : 0u;
                 const unsigned any = __ballot_sync(0xffffffffu, wv != 0u);
-                int F = INT_MAX, L = INT_MIN;
+                int v = 0; // first changed column seen from this side (negated on the high side)
                 if (any) {
-                    const int lf = __ffs(any) - 1, ll = 31 - __clz(any);
-                    const unsigned wf = __shfl_sync(0xffffffffu, wv, lf), wl = __shfl_sync(0xffffffffu, wv, ll);
-                    F = gb + 32 * lf + (__ffs(wf) - 1);
-                    L = gb + 32 * ll + (31 - __clz(wl));
+                    const int sel = hi ? 31 - __clz(any) : __ffs(any) - 1;
+                    const unsigned ws = __shfl_sync(0xffffffffu, wv, sel);
+                    const int pos = hi ? 31 - __clz(ws) : __ffs(ws) - 1;
+                    v = sgn * (clo_v + 32 * sel + pos);
                 }
-                const int old_min = x_min, old_max = x_max;
-                bool violation;
-                if (bmax >= bmin) {
-                    cells += (unsigned long long) (bmax - bmin + 1);
-                    violation = any && (F < bmin || L > bmax);
-                    x_min = any ? F : bmax + 1;
-                    x_max = any ? (L == bmax ? bmax : L + 1) : bmin;
+                const int old = xm;
+                bool viol;
+                if (nonempty) {
+                    if (lane == 0) cells += (unsigned long long) (1 - b - bo);
+                    viol = any && v < b;
+                    // low side: x_min = F, or bmax+1 when nothing changed; high side: x_max = (L == bmax ? bmax : L+1),
+                    // or bmin when nothing changed -- in negated coordinates
+                    if (hi)
+                        xm = any ? (v == b ? b : v - 1) : -bo;
+                    else
+                        xm = any ? v : 1 - bo;
                 } else {
-                    violation = any != 0u;
-                    x_min = bmin;
-                    x_max = bmax;
+                    viol = any != 0u;
+                    xm = b;
                 }
-                if (violation) {
+                if (__ballot_sync(0xffffffffu, viol)) {
                     fail_row = yv;
+                    if (lane < 2) misc[2 + lane] = sgn * old;
                     if (lane == 0) {
                         misc[1] = yv;
-                        misc[2] = old_min;
-                        misc[3] = old_max;
                         __threadfence_block();
                         misc[0] = 1;
                     }
                 }
             }
-            // active range of row y+1 from the limits after row y-1 (two rows of growth) and its guard range
+            // active range of row y+1 from the limits after row y-1 (two rows of growth), guard range (four rows),
+            // both clamped to the staged window of that row's chunk
+            const int wb = hi ? -(clo_n + cw_n - 1) : clo_n;
+            const int g = max(max(floor_s, min(xm, min(a1, min(a2, a3))) - 4 * D), wb);
+            const int a = max(max(floor_s, min(xm, min(a1, a2)) - 2 * D), g);
+            int *pb = pub + ((y + 1) & 1) * 8;
+            if (lane < 2) {
+                pb[lane] = sgn * a;
+                pb[4 + lane] = sgn * g;
+            }
             if (lane == 0) {
-                publish(y + 1, max(0, min(x_min, min(an1, an2)) - 2 * D), min(w - 1, max(x_max, max(ax1, ax2)) + 2 * D),
-                        guard_lo(x_min, an1, an2, an3), guard_hi(x_max, ax1, ax2, ax3), clo_n, cw_n, fail_row);
+                pb[2] = fail_row;
                 if (fail_row == INT_MAX) misc[5] = min(y, y_lim); // rows [0, y) are verified (the DMA warp commits them)
             }
-            an0 = an1, an1 = an2, an2 = an3, an3 = an4;
-            ax0 = ax1, ax1 = ax2, ax2 = ax3, ax3 = ax4;
+            a0 = a1, a1 = a2, a2 = a3, a3 = a4;
         };
         // The loop mirrors the compute warps' exactly (same stop predicate at the top of every row), so both
         // roles execute the same sequence of row and chunk barriers.
         const unsigned *nk_last = nk;
-        const int *ri_last = rinfo;
-        long long ctl_bar = 0, ctl_t0 = clock64();
+        int clo_prev = 0, cw_prev = 0;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
             const int *dn = cdesc + ((k + 1) & 3) * 4; // next chunk (described at least one chunk ago)
             const int clo_nx = dn[2], cw_nx = dn[3];
-            const unsigned *nkc = nk + (k & 1) * UT_MAXROWS * 32;
-            const int *ric = rinfo + (k & 1) * UT_MAXROWS * 4;
+            const unsigned *nkc = nk + (k & 1) * UT_MAXROWS * UT_NKS;
             for (int r = 0; r < rows; ++r, ++y) {
                 if (fail_row <= y - 2) {
                     stop = true;
@@ -402,24 +406,22 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 }
                 const bool nx = r + 1 >= rows; // row y+1 opens the next chunk
                 if (r == 0) // row y-1 is the last row of the previous chunk
-                    iteration(nk_last, ri_last, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
+                    iteration(nk_last, clo_prev, cw_prev, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
                 else
-                    iteration(nkc + (r - 1) * 32, ric + (r - 1) * 4, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
+                    iteration(nkc + (r - 1) * UT_NKS, clo, cw, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
                 if (r == 0 && k > 0) ut_bar_commit_arrive(); // chunk k-1 is verified to its last row: it may be committed
-                const long long tc1 = clock64();
-                if (r == rows - 1 && lane == 0) {
+                if (r == rows - 1) {
                     // limits the DMA warp plans chunk k+3 from (it reads them after the chunk barrier)
                     int *cl = clim + ((k + 1) & 1) * 4;
-                    cl[0] = x_min;
-                    cl[1] = x_max;
-                    cl[2] = max(y - 1, 0);
+                    if (lane < 2) cl[lane] = sgn * xm;
+                    if (lane == 0) cl[2] = max(y - 1, 0);
                 }
                 ut_bar_rows();
-                ctl_bar += clock64() - tc1;
             }
             if (stop) break;
-            nk_last = nkc + (rows - 1) * 32;
-            ri_last = ric + (rows - 1) * 4;
+            nk_last = nkc + (rows - 1) * UT_NKS;
+            clo_prev = clo;
+            cw_prev = cw;
             __syncthreads(); // chunk end
         }
         if (!stop) {
@@ -429,21 +431,16 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                     stop = true;
                     break;
                 }
-                iteration(nk_last, ri_last, y_end, 0, 0); // d == 0 verifies row y_end-1; d == 1 has nothing to verify
+                iteration(nk_last, clo_prev, cw_prev, y_end, 0, 1); // d == 0 verifies row y_end-1
                 ut_bar_rows();
             }
-            if (fail_row == INT_MAX && lane == 0 && y_end < h) {
+            if (fail_row == INT_MAX && y_end < h) {
                 // capacity stop: rows below y_end are exact; hand the exact limits to the generic loop
-                misc[1] = y_end;
-                misc[2] = x_min;
-                misc[3] = x_max;
+                if (lane < 2) misc[2 + lane] = sgn * xm;
+                if (lane == 0) misc[1] = y_end;
             }
         }
         if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
-        if (p.dbg && lane == 0) {
-            atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) ctl_bar);
-            atomicAdd((unsigned long long *) &p.dbg[13], (unsigned long long) (clock64() - ctl_t0));
-        }
     } else {
         // =============================================================================== DMA warp
         // Lane r owns row r of the chunk being handled (chunks have at most 8 rows).
