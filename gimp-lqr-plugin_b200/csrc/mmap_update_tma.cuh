@@ -34,7 +34,7 @@ namespace b200c {
 #define UT_NCW 12
 #define UT_CT (UT_NCW * 32)
 #define UT_THREADS (UT_CT + 64)
-#define UT_TILE 13312 // words per chunk tile (3 tiles)
+#define UT_TILE 12032 // words per chunk tile (4 tiles)
 #define UT_RW 2048
 #define UT_RWM (UT_RW - 1)
 #define UT_MAXROWS 8
@@ -43,10 +43,10 @@ namespace b200c {
 
 #define UT_NKW (2 * UT_MAXROWS * UT_NKS) // ballot words [chunk parity][row][UT_NKS]
 #define UT_RIW (2 * UT_MAXROWS * 4)  // row info     [chunk parity][row]{guard base, slots}
-#define UT_RTW (3 * UT_MAXROWS * 8)  // row tables   [tile][row]{xadd, eadd, madd, ladd, zlo, zhi, -, -}
+#define UT_RTW (4 * UT_MAXROWS * 8)  // row tables   [tile][row]{xadd, eadd, madd, ladd, zlo, zhi, -, -}
 static constexpr size_t ut_smem_bytes()
 {
-    return sizeof(int) * ((size_t) 3 * UT_TILE + 4 * UT_RW + UT_NKW + UT_RIW + UT_RTW + 16 + 16 + 8 + 8 + 8 + 128);
+    return sizeof(int) * ((size_t) 4 * UT_TILE + 4 * UT_RW + UT_NKW + UT_RIW + UT_RTW + 16 + 16 + 8 + 8 + 8 + 128);
 }
 
 __device__ __forceinline__ void ut_bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(UT_CT + 32) : "memory"); }
@@ -97,7 +97,7 @@ __device__ __forceinline__ void ut_bulk_store(void *dst, const void *src_smem, u
                  : "memory");
 }
 __device__ __forceinline__ void ut_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void ut_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void ut_bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void ut_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void ut_fence_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -206,17 +206,17 @@ template <bool D1>
 __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
 {
     extern __shared__ __align__(128) unsigned char ut_smem[];
-    int *tiles = reinterpret_cast<int *>(ut_smem);                    // [3][UT_TILE] chunk tiles
-    int2 *ring = reinterpret_cast<int2 *>(tiles + 3 * UT_TILE);       // [2][RW] {m bits, id} of the previous / current row
+    int *tiles = reinterpret_cast<int *>(ut_smem);                    // [4][UT_TILE] chunk tiles
+    int2 *ring = reinterpret_cast<int2 *>(tiles + 4 * UT_TILE);       // [2][RW] {m bits, id} of the previous / current row
     unsigned *nk = reinterpret_cast<unsigned *>(ring + 2 * UT_RW);    // [2][8][UT_NKS] "changed" ballot words
     int *rinfo = reinterpret_cast<int *>(nk + UT_NKW);                // [2][8][4] guard base, slots
-    int *rtab = rinfo + UT_RIW;                                       // [3][8][8] row tables of the tiles
+    int *rtab = rinfo + UT_RIW;                                       // [4][8][8] row tables of the tiles
     int *pub = rtab + UT_RTW;                                         // [2][8] act_lo, act_hi, fail_row, slots, gr_lo, gr_hi
     int *cdesc = pub + 16;                                            // [4][4] y0, rows, clo, cw
     int *clim = cdesc + 16;                                           // [2][4] x_min, x_max, y_v at chunk starts
     volatile int *misc = clim + 8;                                    // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax,
                                                                       //     4 last chunk entered, 5 rows verified, 6 last chunk issued
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(const_cast<int *>(misc) + 8); // [3] (+pad)
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(const_cast<int *>(misc) + 8); // [4]
     int *s_red = const_cast<int *>(misc) + 16;                        // [128] generic fallback scratch
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         misc[4] = -1;
         misc[5] = 0;
         misc[6] = -1;
-        for (int i = 0; i < 3; ++i) ut_mbar_init(&mbar[i], 1);
+        for (int i = 0; i < 4; ++i) ut_mbar_init(&mbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads(); // mbarriers initialised
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
             if (tid == 0) misc[4] = k;
-            int *tile = tiles + (k % 3) * UT_TILE;
-            const int *rtc = rtab + (k % 3) * UT_MAXROWS * 8;
+            int *tile = tiles + (k & 3) * UT_TILE;
+            const int *rtc = rtab + (k & 3) * UT_MAXROWS * 8;
             unsigned *nkc = nk + (k & 1) * UT_MAXROWS * UT_NKS;
             const int ns = cw <= UT_CT ? 1 : (cw <= 2 * UT_CT ? 2 : 3);
             UtSlot sl[3];
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 sl[j].rbl = (sl[j].x - 1) & UT_RWM;
                 sl[j].rbr = (sl[j].x + 1) & UT_RWM;
             }
-            if (!ut_mbar_wait(&mbar[k % 3], (unsigned) ((k / 3) & 1))) // the chunk's bulk loads have landed
+            if (!ut_mbar_wait(&mbar[k & 3], (unsigned) ((k >> 2) & 1))) // the chunk's bulk loads have landed
                 atomicOr(p.err, 4);
             for (int r = 0; r < rows; ++r, ++y) {
                 const int par = y & 1;
@@ -448,16 +448,15 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         auto plan = [&](int ya, int xv_min, int xv_max, int yv, int &rows, int &lo, int &cw) {
             rows = 0, lo = 0, cw = 0;
             if (ya >= h) return;
-            for (int want = UT_MAXROWS; want >= 2; want >>= 1) {
+            // energy-band limits of rows yv+1 .. yv+64 (two rows per lane), loaded once
+            const int j0 = yv + 1 + lane, j1 = j0 + 32;
+            const int n0 = j0 < h ? p.nrg_xmin[j0] : INT_MAX, x0 = j0 < h ? p.nrg_xmax[j0] : INT_MIN;
+            const int n1 = j1 < h ? p.nrg_xmin[j1] : INT_MAX, x1 = j1 < h ? p.nrg_xmax[j1] : INT_MIN;
+            for (int want = UT_MAXROWS; want >= 1; --want) {
                 const int yb = min(ya + want, h) - 1;
-                // energy-band extremes over rows [yv+1, yb+2] (two rows per lane: up to 64 rows)
-                const int last = min(yb + 2, h - 1);
-                const int j0 = yv + 1 + lane, j1 = j0 + 32;
-                int nlo = j0 <= last ? p.nrg_xmin[j0] : INT_MAX, nhi = j0 <= last ? p.nrg_xmax[j0] : INT_MIN;
-                if (j1 <= last) {
-                    nlo = min(nlo, p.nrg_xmin[j1]);
-                    nhi = max(nhi, p.nrg_xmax[j1]);
-                }
+                const int last = min(yb + 2, h - 1); // extremes over rows [yv+1, yb+2]
+                int nlo = min(j0 <= last ? n0 : INT_MAX, j1 <= last ? n1 : INT_MAX);
+                int nhi = max(j0 <= last ? x0 : INT_MIN, j1 <= last ? x1 : INT_MIN);
                 nlo = __reduce_min_sync(0xffffffffu, nlo);
                 nhi = __reduce_max_sync(0xffffffffu, nhi);
                 // a band grows by at most delta_x per row beyond the energy bands; the guard range of the last
@@ -485,8 +484,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         // rows that fit (the spans are only known now); the chunk is cut there.
         int issued_upto = -1; // last chunk whose bulk loads were issued
         auto issue = [&](int kk, int ya, int rows, int lo, int cw, int zlo, int zhi) -> int {
-            int *tile = tiles + (kk % 3) * UT_TILE;
-            int *rtk = rtab + (kk % 3) * UT_MAXROWS * 8;
+            int *tile = tiles + (kk & 3) * UT_TILE;
+            int *rtk = rtab + (kk & 3) * UT_MAXROWS * 8;
             const int y = ya + lane;
             const long long rawpos = (long long) y * p.raw_stride + lo;
             const int rawbase = (int) (rawpos & ~3LL), nraw = (int) ((rawpos + cw - rawbase + 3) & ~3LL);
@@ -515,14 +514,14 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             unsigned total = bytes;
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
-            if (lane == 0 && nrows > 0) ut_mbar_expect(&mbar[kk % 3], total);
+            if (lane == 0 && nrows > 0) ut_mbar_expect(&mbar[kk & 3], total);
             __syncwarp();
             if (lane < nrows) {
-                if (nraw > 0) ut_bulk_load(tile + off, p.raw + rawbase, (unsigned) nraw * 4u, &mbar[kk % 3]);
+                if (nraw > 0) ut_bulk_load(tile + off, p.raw + rawbase, (unsigned) nraw * 4u, &mbar[kk & 3]);
                 if (nsp > 0) {
-                    ut_bulk_load(tile + off + nraw, p.en + zbase, (unsigned) nsp * 4u, &mbar[kk % 3]);
-                    ut_bulk_load(tile + off + nraw + nsp, p.m + zbase, (unsigned) nsp * 4u, &mbar[kk % 3]);
-                    ut_bulk_load(tile + off + nraw + 2 * nsp, p.least + zbase, (unsigned) nsp * 4u, &mbar[kk % 3]);
+                    ut_bulk_load(tile + off + nraw, p.en + zbase, (unsigned) nsp * 4u, &mbar[kk & 3]);
+                    ut_bulk_load(tile + off + nraw + nsp, p.m + zbase, (unsigned) nsp * 4u, &mbar[kk & 3]);
+                    ut_bulk_load(tile + off + nraw + 2 * nsp, p.least + zbase, (unsigned) nsp * 4u, &mbar[kk & 3]);
                 }
             }
             if (nrows > 0) issued_upto = kk;
@@ -568,32 +567,39 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 __syncthreads(); // matches the exit barrier of the other roles
                 break;
             }
+            // chunk k+3 first: plan it from the limits published at the end of chunk k-1 (or the initial band) and
+            // fetch its span ends.  These loads are consumed in the next iteration, a whole chunk from now.
+            const int *cl = clim + (k & 1) * 4;
+            int ya3 = ya2 + rows2;
+            int rows3 = 0, lo3 = 0, cw3 = 0, zlo3, zhi3;
+            if (rows2 > 0) plan(ya3, cl[0], cl[1], cl[2], rows3, lo3, cw3);
+            span_ends(ya3, rows3, lo3, cw3, zlo3, zhi3);
             if (k > 0) {
-                // chunk k-1: its tile is recycled by chunk k+2, so its verified rows go back to HBM first.  Its last
-                // row is verified during row 0 of chunk k.
+                // chunk k-1: verified to its last row during row 0 of chunk k -> write its m / least spans back
                 const int *dp = cdesc + ((k - 1) & 3) * 4;
                 const int yp0 = dp[0], prow = dp[1];
                 ut_bar_commit_wait();
                 const int done = misc[5];
                 const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
                 if (lane < r_end)
-                    ut_commit_row(p, yp0 + lane, tiles + ((k - 1) % 3) * UT_TILE, rtab + ((k - 1) % 3) * UT_MAXROWS * 8 + lane * 8);
+                    ut_commit_row(p, yp0 + lane, tiles + ((k - 1) & 3) * UT_TILE, rtab + ((k - 1) & 3) * UT_MAXROWS * 8 + lane * 8);
                 ut_bulk_commit();
-                ut_bulk_wait_read(); // the stores have read the tile: it may be overwritten
-                __syncwarp();
             }
-            // chunk k+2: spans are known now (loaded during chunk k-1)
+            // the tile of chunk k+2 last held chunk k-2, whose stores were issued a chunk ago: wait for all but the
+            // newest store group to have read their shared-memory source
+            ut_bulk_wait_read1();
+            __syncwarp();
+            // chunk k+2: its span ends were fetched during chunk k-1
             const int nrows2 = issue(k + 2, ya2, rows2, lo2, cw2, zlo2, zhi2);
             if (nrows2 != rows2) {
-                rows2 = nrows2; // cut by the tile capacity: the next chunk starts right after the cut
+                // cut by the tile capacity (rare): the next chunk starts right after the cut, plan it again
+                rows2 = nrows2;
+                ya3 = ya2 + rows2;
+                rows3 = 0, lo3 = 0, cw3 = 0;
+                if (rows2 > 0) plan(ya3, cl[0], cl[1], cl[2], rows3, lo3, cw3);
+                span_ends(ya3, rows3, lo3, cw3, zlo3, zhi3);
             }
             put_desc((k + 2) & 3, ya2, rows2, lo2, cw2);
-            // chunk k+3: plan from the limits published at the end of chunk k-1 (or the initial band)
-            const int *cl = clim + (k & 1) * 4;
-            const int ya3 = ya2 + rows2;
-            int rows3 = 0, lo3 = 0, cw3 = 0, zlo3, zhi3;
-            if (rows2 > 0) plan(ya3, cl[0], cl[1], cl[2], rows3, lo3, cw3);
-            span_ends(ya3, rows3, lo3, cw3, zlo3, zhi3);
             __syncthreads(); // chunk k end (or the exit barrier of a failed speculation)
             if (misc[0]) break;
             rows_k = rows1;
@@ -614,12 +620,12 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int *dl = cdesc + (klast & 3) * 4;
             const int r_end = min(dl[1], max(min(fb_row, h) - dl[0], 0));
             if (lane < r_end)
-                ut_commit_row(p, dl[0] + lane, tiles + (klast % 3) * UT_TILE, rtab + (klast % 3) * UT_MAXROWS * 8 + lane * 8);
+                ut_commit_row(p, dl[0] + lane, tiles + (klast & 3) * UT_TILE, rtab + (klast & 3) * UT_MAXROWS * 8 + lane * 8);
         }
         ut_bulk_commit();
         ut_bulk_wait_all(); // results are in HBM before the kernel ends / the generic loop reads them
         for (int kk = klast + 1; kk <= (int) misc[6]; ++kk) // chunks staged ahead that nobody consumed
-            ut_mbar_wait(&mbar[kk % 3], (unsigned) ((kk / 3) & 1));
+            ut_mbar_wait(&mbar[kk & 3], (unsigned) ((kk >> 2) & 1));
     }
     if (fb_row < h) {
         __syncthreads();
