@@ -119,12 +119,19 @@ struct UtSlot {
 template <int NS, bool D1>
 __device__ __forceinline__ void ut_row(const DevP &p, bool row0, int4 rt, int *__restrict__ tile, int2 *ring_cur,
                                        const int2 *ring_prev, int act_lo, int act_hi, int gr_lo, int gr_hi,
-                                       const UtSlot *sl, unsigned *nkrow, int lane, int warp)
+                                       const UtSlot *sl, unsigned *nkrow, int lane, int warp, int clo)
 {
     const int w = p.w;
     float *tilef = reinterpret_cast<float *>(tile);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
+        // The SM sustains ~1.5 warp-instructions per cycle on this latency-bound code, so the row time is set by
+        // the TOTAL instruction count of all warps: a warp whose 32 columns miss the guard range leaves at once.
+        const int wlo = clo + j * UT_CT + warp * 32;
+        if (wlo > gr_hi || wlo + 31 < gr_lo) {
+            if (lane == 0) nkrow[j * UT_NCW + warp] = 0u;
+            continue;
+        }
         const int x = sl[j].x;
         const int z = tile[rt.x + x];
         float best;
@@ -277,11 +284,11 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 if (cw <= 0) {
                     if (lane == 0) nkrow[warp] = 0u;
                 } else if (ns == 1)
-                    ut_row<1, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp);
+                    ut_row<1, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
                 else if (ns == 2)
-                    ut_row<2, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp);
+                    ut_row<2, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
                 else
-                    ut_row<3, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp);
+                    ut_row<3, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
                 ut_bar_rows();
             }
             ut_fence_async(); // tile writes (generic proxy) -> visible to the TMA stores (async proxy)
