@@ -25,6 +25,7 @@
 #include "vpath_mmap_tiled.cuh"
 #include "mmap_update_spec.cuh"
 #include "mmap_update_tma.cuh"
+#include "vpath_tma.cuh"
 
 using namespace b200c;
 
@@ -130,6 +131,7 @@ struct B200Carver {
     bool owns_stream = true;
     int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
+    int vpath_kernel = 3;                     // B200C_VPATH=2: cp.async windowed backtrack instead of the TMA one
     int update_kernel = 4;                    // B200C_UPDATE=3: cp.async-staged speculative kernel, 2: staged exact kernel
 
     float rigidity = 0.f;
@@ -294,6 +296,7 @@ int raise_smem_limits()
         set((const void *) k_mmap_update_spec<true>, us_smem_bytes());
         set((const void *) k_mmap_update_spec<false>, us_smem_bytes());
         set((const void *) k_vpath_fast, vp_smem_bytes());
+        set((const void *) k_vpath_tma, vt_smem_bytes());
         set((const void *) k_mmap_full_tile, 200 * 1024);
     });
     if (err != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", err);
@@ -379,7 +382,9 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (fast) B_TRY(raise_smem_limits());
     {
         StageScope sc("vpath", s);
-        if (fast)
+        if (fast && c->vpath_kernel == 3)
+            k_vpath_tma<<<1, VT_THREADS, vt_smem_bytes(), s>>>(view(c));
+        else if (fast)
             k_vpath_fast<<<1, VP_THREADS, vp_smem_bytes(), s>>>(view(c));
         else
             k_vpath<<<1, 1024, 0, s>>>(view(c));
@@ -661,6 +666,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
         c->generic = g && atoi(g) != 0;
         const char *u = getenv("B200C_UPDATE");
         if (u && atoi(u) >= 2 && atoi(u) <= 4) c->update_kernel = atoi(u);
+        const char *v = getenv("B200C_VPATH");
+        if (v && atoi(v) == 2) c->vpath_kernel = 2;
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
     if (g_use_ext_stream) {

@@ -125,8 +125,7 @@ __device__ __forceinline__ void ut_row(const DevP &p, bool row0, int4 rt, int *_
     float *tilef = reinterpret_cast<float *>(tile);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        // The SM sustains ~1.5 warp-instructions per cycle on this latency-bound code, so the row time is set by
-        // the TOTAL instruction count of all warps: a warp whose 32 columns miss the guard range leaves at once.
+        // a slot whose 32 columns miss the guard range has nothing to do (uniform per warp)
         const int wlo = clo + j * UT_CT + warp * 32;
         if (wlo > gr_hi || wlo + 31 < gr_lo) {
             if (lane == 0) nkrow[j * UT_NCW + warp] = 0u;
@@ -218,7 +217,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
     unsigned *nk = reinterpret_cast<unsigned *>(ring + 2 * UT_RW);    // [2][8][UT_NKS] "changed" ballot words
     int *rinfo = reinterpret_cast<int *>(nk + UT_NKW);                // [2][8][4] guard base, slots
     int *rtab = rinfo + UT_RIW;                                       // [4][8][8] row tables of the tiles
-    int *pub = rtab + UT_RTW;                                         // [2][8] act_lo, act_hi, fail_row, slots, gr_lo, gr_hi
+    int *pub = rtab + UT_RTW;                                         // [2][8] gr_lo, gr_hi, fail_row, -, act_lo, act_hi
     int *cdesc = pub + 16;                                            // [4][4] y0, rows, clo, cw
     int *clim = cdesc + 16;                                           // [2][4] x_min, x_max, y_v at chunk starts
     volatile int *misc = clim + 8;                                    // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax,
@@ -268,27 +267,37 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             }
             if (!ut_mbar_wait(&mbar[k & 3], (unsigned) ((k >> 2) & 1))) // the chunk's bulk loads have landed
                 atomicOr(p.err, 4);
-            for (int r = 0; r < rows; ++r, ++y) {
+            // The SM sustains only ~1.5 warp-instructions per cycle on this latency-bound code, so the row time is set
+            // by the TOTAL instruction count of all warps: a warp none of whose columns touch the row's guard range
+            // reads one record, clears its ballot words and goes straight to the barrier.
+            const int wfirst = clo + warp * 32; // first column of this warp's slot 0
+            unsigned *nkrow = nkc;
+            const int *rtr = rtc;
+            for (int r = 0; r < rows; ++r, ++y, nkrow += UT_NKS, rtr += 8) {
                 const int par = y & 1;
-                // ranges of this row, already clamped to the chunk window by the control warp
-                const int4 pa = *reinterpret_cast<const int4 *>(pub + par * 8);
-                const int2 pg = *reinterpret_cast<const int2 *>(pub + par * 8 + 4);
-                const int4 rt = *reinterpret_cast<const int4 *>(rtc + r * 8);
-                if (pa.z <= y - 2) {
+                const int4 pg = *reinterpret_cast<const int4 *>(pub + par * 8); // gr_lo, gr_hi, fail_row
+                if (pg.z <= y - 2) {
                     failed = true;
                     break;
                 }
-                int2 *ring_cur = ring + par * UT_RW;
-                const int2 *ring_prev = ring + (par ^ 1) * UT_RW;
-                unsigned *nkrow = nkc + r * UT_NKS;
-                if (cw <= 0) {
-                    if (lane == 0) nkrow[warp] = 0u;
-                } else if (ns == 1)
-                    ut_row<1, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
-                else if (ns == 2)
-                    ut_row<2, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
-                else
-                    ut_row<3, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
+                bool active = false;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < ns) active |= !(wfirst + j * UT_CT > pg.y || wfirst + j * UT_CT + 31 < pg.x);
+                if (!active || cw <= 0) {
+                    if (lane < ns) nkrow[lane * UT_NCW + warp] = 0u;
+                } else {
+                    const int2 pa = *reinterpret_cast<const int2 *>(pub + par * 8 + 4); // act_lo, act_hi
+                    const int4 rt = *reinterpret_cast<const int4 *>(rtr);
+                    int2 *ring_cur = ring + par * UT_RW;
+                    const int2 *ring_prev = ring + (par ^ 1) * UT_RW;
+                    if (ns == 1)
+                        ut_row<1, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
+                    else if (ns == 2)
+                        ut_row<2, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
+                    else
+                        ut_row<3, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
+                }
                 ut_bar_rows();
             }
             ut_fence_async(); // tile writes (generic proxy) -> visible to the TMA stores (async proxy)
@@ -325,8 +334,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int g = max(max(floor_s, min(xm, min(a1, a2)) - 4 * D), wb);
             const int a = max(xm, g);
             if (lane < 2) {
-                pub[lane] = sgn * a;
-                pub[4 + lane] = sgn * g;
+                pub[lane] = sgn * g;
+                pub[4 + lane] = sgn * a;
             }
             if (lane == 0) pub[2] = INT_MAX;
         }
@@ -385,8 +394,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int a = max(max(floor_s, min(xm, min(a1, a2)) - 2 * D), g);
             int *pb = pub + ((y + 1) & 1) * 8;
             if (lane < 2) {
-                pb[lane] = sgn * a;
-                pb[4 + lane] = sgn * g;
+                pb[lane] = sgn * g;
+                pb[4 + lane] = sgn * a;
             }
             if (lane == 0) {
                 pb[2] = fail_row;

@@ -34,7 +34,8 @@ def kernel_mode(request):
     and committed with TMA bulk copies, windowed backtrack, tiled full DP), "spec" (B200C_UPDATE=3: the same
     band DP staged with cp.async gathers), "staged" (B200C_UPDATE=2: the cp.async-staged band DP that also serves rigidity),
     and "generic" (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at carver creation."""
-    old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_UPDATE")}
+    old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_UPDATE", "B200C_VPATH")}
+    os.environ["B200C_VPATH"] = "3" if request.param == "fast" else "2"
     os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
     os.environ["B200C_UPDATE"] = {"staged": "2", "spec": "3"}.get(request.param, "4")
     yield request.param
