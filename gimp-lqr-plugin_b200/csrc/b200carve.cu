@@ -296,7 +296,8 @@ int raise_smem_limits()
         set((const void *) k_mmap_update_spec<true>, us_smem_bytes());
         set((const void *) k_mmap_update_spec<false>, us_smem_bytes());
         set((const void *) k_vpath_fast, vp_smem_bytes());
-        set((const void *) k_vpath_tma, vt_smem_bytes());
+        set((const void *) k_vpath_tma<true>, vt_smem_bytes());
+        set((const void *) k_vpath_tma<false>, vt_smem_bytes());
         set((const void *) k_mmap_full_tile, 200 * 1024);
     });
     if (err != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", err);
@@ -382,8 +383,10 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (fast) B_TRY(raise_smem_limits());
     {
         StageScope sc("vpath", s);
-        if (fast && c->vpath_kernel == 3)
-            k_vpath_tma<<<1, VT_THREADS, vt_smem_bytes(), s>>>(view(c));
+        if (fast && c->vpath_kernel == 3 && c->delta_x == 1)
+            k_vpath_tma<true><<<1, VT_THREADS, vt_smem_bytes(), s>>>(view(c));
+        else if (fast && c->vpath_kernel == 3)
+            k_vpath_tma<false><<<1, VT_THREADS, vt_smem_bytes(), s>>>(view(c));
         else if (fast)
             k_vpath_fast<<<1, VP_THREADS, vp_smem_bytes(), s>>>(view(c));
         else
