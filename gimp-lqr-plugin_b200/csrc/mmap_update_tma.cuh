@@ -26,6 +26,8 @@
 // Dependent chain per row on the compute warps: LDS parents -> min/select -> FADD -> keep test -> STS -> named
 // barrier (416 threads).
 #pragma once
+#include <type_traits>
+
 #include "carver_kernels.cuh"
 #include "mmap_update_fast.cuh"
 
@@ -125,11 +127,12 @@ __device__ __forceinline__ void ut_row(const DevP &p, bool row0, int4 rt, int *_
     float *tilef = reinterpret_cast<float *>(tile);
 #pragma unroll
     for (int j = 0; j < NS; ++j) {
-        // a slot whose 32 columns miss the guard range has nothing to do (uniform per warp)
-        const int wlo = clo + j * UT_CT + warp * 32;
-        if (wlo > gr_hi || wlo + 31 < gr_lo) {
-            if (lane == 0) nkrow[j * UT_NCW + warp] = 0u;
-            continue;
+        if (NS > 1) { // a slot whose 32 columns miss the guard range has nothing to do (uniform per warp)
+            const int wlo = clo + j * UT_CT + warp * 32;
+            if (wlo > gr_hi || wlo + 31 < gr_lo) {
+                if (lane == 0) nkrow[j * UT_NCW + warp] = 0u;
+                continue;
+            }
         }
         const int x = sl[j].x;
         const int z = tile[rt.x + x];
@@ -250,6 +253,10 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
+            if (misc[0]) { // a speculation failed during the previous chunk: stop here (same test in the control warp)
+                failed = true;
+                break;
+            }
             if (tid == 0) misc[4] = k;
             int *tile = tiles + (k & 3) * UT_TILE;
             const int *rtc = rtab + (k & 3) * UT_MAXROWS * 8;
@@ -267,49 +274,48 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             }
             if (!ut_mbar_wait(&mbar[k & 3], (unsigned) ((k >> 2) & 1))) // the chunk's bulk loads have landed
                 atomicOr(p.err, 4);
-            // The SM sustains only ~1.5 warp-instructions per cycle on this latency-bound code, so the row time is set
-            // by the TOTAL instruction count of all warps: a warp none of whose columns touch the row's guard range
-            // reads one record, clears its ballot words and goes straight to the barrier.
+            // Row time = the active warps' dependent chain, so the row loop is specialised on the slot count outside
+            // the loop, carries no failure check (a failed speculation is noticed at the next chunk start; nothing
+            // past the failed row is ever committed) and idle warps -- none of whose columns touch the row's guard
+            // range -- read one record, clear their ballot words and go straight to the barrier.
             const int wfirst = clo + warp * 32; // first column of this warp's slot 0
-            unsigned *nkrow = nkc;
-            const int *rtr = rtc;
-            for (int r = 0; r < rows; ++r, ++y, nkrow += UT_NKS, rtr += 8) {
-                const int par = y & 1;
-                const int4 pg = *reinterpret_cast<const int4 *>(pub + par * 8); // gr_lo, gr_hi, fail_row
-                if (pg.z <= y - 2) {
-                    failed = true;
-                    break;
-                }
-                bool active = false;
-#pragma unroll
-                for (int j = 0; j < 3; ++j)
-                    if (j < ns) active |= !(wfirst + j * UT_CT > pg.y || wfirst + j * UT_CT + 31 < pg.x);
-                if (!active || cw <= 0) {
-                    if (lane < ns) nkrow[lane * UT_NCW + warp] = 0u;
-                } else {
+            auto rows_loop = [&](auto ns_tag) {
+                constexpr int NSC = decltype(ns_tag)::value;
+                unsigned *nkrow = nkc;
+                const int *rtr = rtc;
+                for (int r = 0; r < rows; ++r, ++y, nkrow += UT_NKS, rtr += 8) {
+                    const int par = y & 1;
+                    const int4 pg = *reinterpret_cast<const int4 *>(pub + par * 8);     // gr_lo, gr_hi
                     const int2 pa = *reinterpret_cast<const int2 *>(pub + par * 8 + 4); // act_lo, act_hi
                     const int4 rt = *reinterpret_cast<const int4 *>(rtr);
-                    int2 *ring_cur = ring + par * UT_RW;
-                    const int2 *ring_prev = ring + (par ^ 1) * UT_RW;
-                    if (ns == 1)
-                        ut_row<1, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
-                    else if (ns == 2)
-                        ut_row<2, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
-                    else
-                        ut_row<3, D1>(p, y == 0, rt, tile, ring_cur, ring_prev, pa.x, pa.y, pg.x, pg.y, sl, nkrow, lane, warp, clo);
+                    bool active = false;
+#pragma unroll
+                    for (int j = 0; j < NSC; ++j) active |= !(wfirst + j * UT_CT > pg.y || wfirst + j * UT_CT + 31 < pg.x);
+                    if (active)
+                        ut_row<NSC, D1>(p, y == 0, rt, tile, ring + par * UT_RW, ring + (par ^ 1) * UT_RW, pa.x, pa.y, pg.x,
+                                        pg.y, sl, nkrow, lane, warp, clo);
+                    else if (lane < NSC)
+                        nkrow[lane * UT_NCW + warp] = 0u;
+                    ut_bar_rows();
                 }
-                ut_bar_rows();
-            }
+            };
+            if (cw <= 0) {
+                for (int r = 0; r < rows; ++r, ++y) {
+                    if (lane == 0) nkc[r * UT_NKS + warp] = 0u;
+                    ut_bar_rows();
+                }
+            } else if (ns == 1)
+                rows_loop(std::integral_constant<int, 1>{});
+            else if (ns == 2)
+                rows_loop(std::integral_constant<int, 2>{});
+            else
+                rows_loop(std::integral_constant<int, 3>{});
             ut_fence_async(); // tile writes (generic proxy) -> visible to the TMA stores (async proxy)
-            if (failed) break;
             __syncthreads(); // chunk end
         }
         if (!failed) {
             // drain: the last two rows still wait for verification
-            for (int d = 0; d < 2; ++d, ++y) {
-                if (pub[(y & 1) * 8 + 2] <= y - 2) break;
-                ut_bar_rows();
-            }
+            for (int d = 0; d < 2; ++d, ++y) ut_bar_rows();
         }
     } else if (is_control) {
         // =============================================================================== CONTROL
@@ -390,8 +396,9 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             // active range of row y+1 from the limits after row y-1 (two rows of growth), guard range (four rows),
             // both clamped to the staged window of that row's chunk
             const int wb = hi ? -(clo_n + cw_n - 1) : clo_n;
-            const int g = max(max(floor_s, min(xm, min(a1, min(a2, a3))) - 4 * D), wb);
-            const int a = max(max(floor_s, min(xm, min(a1, a2)) - 2 * D), g);
+            int g = max(max(floor_s, min(xm, min(a1, min(a2, a3))) - 4 * D), wb);
+            int a = max(max(floor_s, min(xm, min(a1, a2)) - 2 * D), g);
+            if (fail_row != INT_MAX) g = a = 1; // failed: publish empty ranges ([1, -1]), the compute warps idle
             int *pb = pub + ((y + 1) & 1) * 8;
             if (lane < 2) {
                 pb[lane] = sgn * g;
@@ -414,12 +421,12 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             const int *dn = cdesc + ((k + 1) & 3) * 4; // next chunk (described at least one chunk ago)
             const int clo_nx = dn[2], cw_nx = dn[3];
             const unsigned *nkc = nk + (k & 1) * UT_MAXROWS * UT_NKS;
+            if (fail_row != INT_MAX) { // stop at chunk granularity (the compute warps test misc[0] at the same place)
+                stop = true;
+                if (k > 0) ut_bar_commit_arrive(); // the DMA warp waits for this chunk's hand-shake
+                break;
+            }
             for (int r = 0; r < rows; ++r, ++y) {
-                if (fail_row <= y - 2) {
-                    stop = true;
-                    if (r == 0 && k > 0) ut_bar_commit_arrive(); // the DMA warp waits for this chunk's hand-shake
-                    break;
-                }
                 const bool nx = r + 1 >= rows; // row y+1 opens the next chunk
                 if (r == 0) // row y-1 is the last row of the previous chunk
                     iteration(nk_last, clo_prev, cw_prev, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
@@ -443,10 +450,6 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         if (!stop) {
             const int y_end = y;
             for (int d = 0; d < 2; ++d, ++y) {
-                if (fail_row <= y - 2) {
-                    stop = true;
-                    break;
-                }
                 iteration(nk_last, clo_prev, cw_prev, y_end, 0, 1); // d == 0 verifies row y_end-1
                 ut_bar_rows();
             }
