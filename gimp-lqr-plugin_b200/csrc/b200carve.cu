@@ -129,6 +129,7 @@ struct B200Carver {
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
     long long *dbg_d = nullptr;               // role cycle counters (B200C_DBG=1)
     bool owns_stream = true;
+    int4 *ctab_d = nullptr;                   // per-row energy-band combos for the control warp
     int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
     int vpath_kernel = 3;                     // B200C_VPATH=2: cp.async windowed backtrack instead of the TMA one
@@ -213,6 +214,7 @@ DevP view(const B200Carver *c)
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
+    p.ctab = c->ctab_d;
     return p;
 }
 
@@ -406,7 +408,7 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
         {
             StageScope sc("energy_band", s);
             if (fast)
-                k_energy_band_pre<<<(c->h + 7) / 8, 256, 0, s>>>(view(c), 2 * kUpdatePrefetchRows, c->pre_lo, c->pre_hi);
+                k_energy_band_pre<<<(c->h + 7) / 8, 256, 0, s>>>(view(c), 2 * kUpdatePrefetchRows, c->pre_lo, c->pre_hi, c->ctab_d);
             else
                 k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
             B_TRY(check_launch("k_energy_band"));
@@ -610,6 +612,8 @@ int transpose(B200Carver *c)
         dfree(c, c->nrg_xmax);
         dfree(c, c->pre_lo);
         dfree(c, c->pre_hi);
+        dfree(c, c->ctab_d);
+        B_TRY(dalloc(c, &c->ctab_d, (size_t) 2 * c->h, true));
         B_TRY(dalloc(c, &c->pre_lo, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->vpath, (size_t) c->h, true));
@@ -791,6 +795,7 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->pre_lo);
     dfree(c, c->pre_hi);
     dfree(c, c->err_d);
+    dfree(c, c->ctab_d);
     if (c->cells_d) {
         unsigned long long n = 0;
         if (cudaMemcpyAsync(&n, c->cells_d, sizeof n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
@@ -833,6 +838,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->pre_lo, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
+    B_TRY(dalloc(c, &c->ctab_d, (size_t) 2 * c->h, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));
     c->delta_x = delta_x;

@@ -36,6 +36,7 @@ struct DevP {
     const float *rigmap; // centred: rigmap[dx], dx in [-delta_x, delta_x]
     int *vpath, *vpath_x, *nrg_xmin, *nrg_xmax;
     unsigned long long *cells; // running count of band cells visited by the incremental DP
+    const int4 *ctab;  // per-row energy-band combos for the control warp (see k_energy_band_pre)
     long long *dbg;    // optional cycle counters of the band-DP roles (B200C_DBG=1), 16 slots
     int *err;          // device error word: bit 0 staged window did not cover the band, bit 1 backtrack left its window
 };

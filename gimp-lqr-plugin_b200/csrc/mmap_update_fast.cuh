@@ -296,18 +296,21 @@ k_mmap_update_fast(DevP p, const int *__restrict__ pre_lo, const int *__restrict
     }
 }
 
-// K1b + window prediction inputs: like k_energy_band, and additionally writes for every row y the extremes
-// of the energy bands of rows [y - span, y + 1] (span = 2*KP of the fast update kernel).
-__global__ void __launch_bounds__(256) k_energy_band_pre(DevP p, int span, int *pre_lo, int *pre_hi)
+// K1b + prediction inputs: like k_energy_band, and additionally writes for every row y
+//   * pre_lo / pre_hi: the extremes of the energy bands of rows [y - span, y + 1] (staged kernel, span = 2*KP);
+//   * ctab[2*y + side]: {n[y-1], ext(n[y], n[y+1]), ext(n[y..y+2]), 0} of the energy-band limits n, side 0 = minima,
+//     side 1 = maxima NEGATED -- the three values the control warp of the speculative kernel needs for row y
+//     (rows clamped to the image).
+__global__ void __launch_bounds__(256) k_energy_band_pre(DevP p, int span, int *pre_lo, int *pre_hi, int4 *ctab)
 {
     const int lane = threadIdx.x & 31;
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (y >= p.h) return;
     const int r = p.nrg_radius;
-    // lane l looks at row y - span + l (l <= span + 1 <= 31): its energy band
-    const int yy = y - span + lane;
-    int bmin = INT_MAX, bmax = INT_MIN;
-    if (lane <= span + 1 && yy >= 0 && yy < p.h) {
+    // lane l looks at row y - span + l (l <= span + 2 <= 31), clamped to the image: its energy band
+    const int yy = min(max(y - span + lane, 0), p.h - 1);
+    int bmin, bmax;
+    {
         const int own = p.vpath_x[yy];
         int xmin = own, xmax = own - 1;
         for (int y1 = max(yy - r, 0); y1 <= min(yy + r, p.h - 1); ++y1) {
@@ -321,13 +324,21 @@ __global__ void __launch_bounds__(256) k_energy_band_pre(DevP p, int span, int *
     // lane `span` holds row y itself
     const int xmin = __shfl_sync(0xffffffffu, bmin, span);
     const int xmax = __shfl_sync(0xffffffffu, bmax, span);
-    const int lo = __reduce_min_sync(0xffffffffu, bmin);
-    const int hi = __reduce_max_sync(0xffffffffu, bmax);
+    const bool in_pre = lane <= span + 1 && y - span + lane >= 0 && y - span + lane < p.h;
+    const int lo = __reduce_min_sync(0xffffffffu, in_pre ? bmin : INT_MAX);
+    const int hi = __reduce_max_sync(0xffffffffu, in_pre ? bmax : INT_MIN);
+    const int nm1 = __shfl_sync(0xffffffffu, bmin, span - 1), xm1 = __shfl_sync(0xffffffffu, bmax, span - 1);
+    const int np1 = __shfl_sync(0xffffffffu, bmin, span + 1), xp1 = __shfl_sync(0xffffffffu, bmax, span + 1);
+    const int np2 = __shfl_sync(0xffffffffu, bmin, span + 2), xp2 = __shfl_sync(0xffffffffu, bmax, span + 2);
     if (lane == 0) {
         p.nrg_xmin[y] = xmin;
         p.nrg_xmax[y] = xmax;
         pre_lo[y] = lo;
         pre_hi[y] = hi;
+        if (ctab) {
+            ctab[2 * y + 0] = make_int4(nm1, min(xmin, np1), min(xmin, min(np1, np2)), 0);
+            ctab[2 * y + 1] = make_int4(-xm1, -max(xmax, xp1), -max(xmax, max(xp1, xp2)), 0);
+        }
     }
     for (int x = xmin + lane; x <= xmax; x += 32) {
         const int z = p.raw[(size_t) y * p.raw_stride + x];

@@ -249,6 +249,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         __syncthreads(); // start 2: ranges of row 0 published
         int y = 0;
         bool failed = false;
+        long long dbg_busy = 0, dbg_rel = clock64();
+        int dbg_probe = 0;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
@@ -296,7 +298,12 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                                         pg.y, sl, nkrow, lane, warp, clo);
                     else if (lane < NSC)
                         nkrow[lane * UT_NCW + warp] = 0u;
+                    if (p.dbg) dbg_busy += clock64() - dbg_rel;
                     ut_bar_rows();
+                    if (p.dbg) {
+                        dbg_probe += *reinterpret_cast<volatile int *>(pub); // the deferred barrier wait lands here
+                        dbg_rel = clock64();
+                    }
                 }
             };
             if (cw <= 0) {
@@ -317,6 +324,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             // drain: the last two rows still wait for verification
             for (int d = 0; d < 2; ++d, ++y) ut_bar_rows();
         }
+        if (p.dbg && lane == 0) atomicAdd((unsigned long long *) &p.dbg[warp], (unsigned long long) dbg_busy + (dbg_probe == 0x7fffffff));
     } else if (is_control) {
         // =============================================================================== CONTROL
         // Lane-parallel: even lanes carry the LOW side (x_min, energy-band minima), odd lanes the HIGH side with
@@ -325,19 +333,18 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         const bool hi = lane & 1;
         const int sgn = hi ? -1 : 1;
         const int floor_s = hi ? -(w - 1) : 0;
-        const int *nrg = hi ? p.nrg_xmax : p.nrg_xmin;
+        const int4 *ctab = p.ctab + (hi ? 1 : 0); // this lane's side: {n[y-1], ext(n[y..y+1]), ext(n[y..y+2])} at [2*y]
         int xm = hi ? -min(p.nrg_xmax[0], w - 1) : max(p.nrg_xmin[0], 0); // x_min | -x_max
         int fail_row = INT_MAX;
         unsigned long long cells = 0;
         if (lane < 2) clim[lane] = sgn * xm;
         if (lane == 0) clim[2] = 0;
-        // rolling window of the energy-band limits (this lane's side): a0 = row y-1, a1 = row y, ... a3 = row y+2
-        int a0 = 0, a1 = sgn * nrg[0], a2 = sgn * nrg[min(1, h - 1)], a3 = sgn * nrg[min(2, h - 1)];
+        int4 cn = ctab[0]; // record of row y, fetched one row ahead
         __syncthreads(); // start 1: the DMA warp described chunks 0..2
         {
-            // row 0: the active range is the exact band (m = en there); guard from (row 0, row 0, row 1)
+            // row 0: the active range is the exact band (m = en there); guard from rows (0, 0, 1)
             const int wb = hi ? -(cdesc[2] + cdesc[3] - 1) : cdesc[2];
-            const int g = max(max(floor_s, min(xm, min(a1, a2)) - 4 * D), wb);
+            const int g = max(max(floor_s, min(xm, cn.y) - 4 * D), wb);
             const int a = max(xm, g);
             if (lane < 2) {
                 pub[lane] = sgn * g;
@@ -348,41 +355,31 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         __syncthreads(); // start 2
         int y = 0;
         bool stop = false;
-        // nkv: ballot words of the row being verified (row y-1, window start clo_v, width cw_v);
-        // clo_n / cw_n: window of the chunk that holds row y+1
-        auto iteration = [&](const unsigned *nkv, int clo_v, int cw_v, int y_lim, int clo_n, int cw_n) {
-            // runs while the compute warps process row y: verify row y-1, publish the ranges of row y+1
-            const int a4 = sgn * nrg[min(y + 3, h - 1)];
+        // Runs while the compute warps process row y: verify row y-1 (ballot words nkv, window start clo_v, nwords_v
+        // words), publish the ranges of row y+1 (wb: this side's window bound of the chunk holding row y+1).
+        auto iteration = [&](const unsigned *nkv, int clo_v, int nwords_v, int y_lim, int wb) {
+            const int4 c = cn;
+            cn = ctab[2 * min(y + 1, h - 1)];
+            const int a0 = y < h ? c.x : c.y; // energy-band limit of row y-1 (past the last row the record is clamped)
             const int yv = y - 1;
-            if (yv >= 1 && yv < h && yv < y_lim && fail_row == INT_MAX) {
+            if (yv >= 1 && yv < y_lim && fail_row == INT_MAX) {
+                const unsigned wv = lane < nwords_v ? nkv[lane] : 0u;
                 const int b = max(min(xm, a0) - D, floor_s); // bmin | -bmax of row yv
                 const int bo = __shfl_xor_sync(0xffffffffu, b, 1);
-                const bool nonempty = b + bo <= 0;
-                const int nwords = (cw_v + 31) >> 5;
-                const unsigned wv = lane < nwords ? nkv[lane] : 0u;
                 const unsigned any = __ballot_sync(0xffffffffu, wv != 0u);
-                int v = 0; // first changed column seen from this side (negated on the high side)
-                if (any) {
-                    const int sel = hi ? 31 - __clz(any) : __ffs(any) - 1;
-                    const unsigned ws = __shfl_sync(0xffffffffu, wv, sel);
-                    const int pos = hi ? 31 - __clz(ws) : __ffs(ws) - 1;
-                    v = sgn * (clo_v + 32 * sel + pos);
-                }
+                const int sel = hi ? 31 - __clz(any) : __ffs(any) - 1;
+                const unsigned ws = __shfl_sync(0xffffffffu, wv, sel & 31);
+                const int pos = hi ? 31 - __clz(ws) : __ffs(ws) - 1;
+                const int v = sgn * (clo_v + 32 * sel + pos); // first changed column seen from this side (valid if any)
+                const bool nonempty = b + bo <= 0;
+                if (lane == 0 && nonempty) cells += (unsigned long long) (1 - b - bo);
+                // low side: x_min = F, or bmax+1 when nothing changed; high side: x_max = (L == bmax ? bmax : L+1), or
+                // bmin when nothing changed -- in negated coordinates; an empty band keeps its limits
+                const int xm_any = hi ? (v == b ? b : v - 1) : v;
+                const int xm_none = hi ? -bo : 1 - bo;
+                const bool viol = any && (!nonempty || v < b);
                 const int old = xm;
-                bool viol;
-                if (nonempty) {
-                    if (lane == 0) cells += (unsigned long long) (1 - b - bo);
-                    viol = any && v < b;
-                    // low side: x_min = F, or bmax+1 when nothing changed; high side: x_max = (L == bmax ? bmax : L+1),
-                    // or bmin when nothing changed -- in negated coordinates
-                    if (hi)
-                        xm = any ? (v == b ? b : v - 1) : -bo;
-                    else
-                        xm = any ? v : 1 - bo;
-                } else {
-                    viol = any != 0u;
-                    xm = b;
-                }
+                xm = nonempty ? (any ? xm_any : xm_none) : b;
                 if (__ballot_sync(0xffffffffu, viol)) {
                     fail_row = yv;
                     if (lane < 2) misc[2 + lane] = sgn * old;
@@ -394,32 +391,29 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 }
             }
             // active range of row y+1 from the limits after row y-1 (two rows of growth), guard range (four rows),
-            // both clamped to the staged window of that row's chunk
-            const int wb = hi ? -(clo_n + cw_n - 1) : clo_n;
-            int g = max(max(floor_s, min(xm, min(a1, min(a2, a3))) - 4 * D), wb);
-            int a = max(max(floor_s, min(xm, min(a1, a2)) - 2 * D), g);
-            if (fail_row != INT_MAX) g = a = 1; // failed: publish empty ranges ([1, -1]), the compute warps idle
+            // both clamped to the staged window of that row's chunk; empty ([1, -1]) once a speculation has failed
+            int g = max(max(floor_s, min(xm, c.z) - 4 * D), wb);
+            int a = max(max(floor_s, min(xm, c.y) - 2 * D), g);
+            if (fail_row != INT_MAX) g = a = 1;
             int *pb = pub + ((y + 1) & 1) * 8;
             if (lane < 2) {
                 pb[lane] = sgn * g;
                 pb[4 + lane] = sgn * a;
             }
-            if (lane == 0) {
-                pb[2] = fail_row;
-                if (fail_row == INT_MAX) misc[5] = min(y, y_lim); // rows [0, y) are verified (the DMA warp commits them)
-            }
-            a0 = a1, a1 = a2, a2 = a3, a3 = a4;
         };
         // The loop mirrors the compute warps' exactly (same stop predicate at the top of every row), so both
         // roles execute the same sequence of row and chunk barriers.
         const unsigned *nk_last = nk;
-        int clo_prev = 0, cw_prev = 0;
+        int clo_prev = 0, nw_prev = 0;
+        long long cdbg_busy = 0, cdbg_rel = clock64(), cdbg_t0 = clock64();
+        int cdbg_probe = 0;
         for (int k = 0;; ++k) {
             const int *dsc = cdesc + (k & 3) * 4;
             const int rows = dsc[1], clo = dsc[2], cw = dsc[3];
             if (rows == 0) break;
             const int *dn = cdesc + ((k + 1) & 3) * 4; // next chunk (described at least one chunk ago)
-            const int clo_nx = dn[2], cw_nx = dn[3];
+            const int wb_cur = hi ? -(clo + cw - 1) : clo, wb_nxt = hi ? -(dn[2] + dn[3] - 1) : dn[2];
+            const int nw = (cw + 31) >> 5;
             const unsigned *nkc = nk + (k & 1) * UT_MAXROWS * UT_NKS;
             if (fail_row != INT_MAX) { // stop at chunk granularity (the compute warps test misc[0] at the same place)
                 stop = true;
@@ -427,30 +421,35 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 break;
             }
             for (int r = 0; r < rows; ++r, ++y) {
-                const bool nx = r + 1 >= rows; // row y+1 opens the next chunk
-                if (r == 0) // row y-1 is the last row of the previous chunk
-                    iteration(nk_last, clo_prev, cw_prev, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
-                else
-                    iteration(nkc + (r - 1) * UT_NKS, clo, cw, INT_MAX, nx ? clo_nx : clo, nx ? cw_nx : cw);
-                if (r == 0 && k > 0) ut_bar_commit_arrive(); // chunk k-1 is verified to its last row: it may be committed
+                const int wb = r + 1 >= rows ? wb_nxt : wb_cur; // row y+1 may open the next chunk
+                if (r == 0) { // row y-1 is the last row of the previous chunk
+                    iteration(nk_last, clo_prev, nw_prev, INT_MAX, wb);
+                    if (k > 0) ut_bar_commit_arrive(); // chunk k-1 is verified to its last row: the DMA warp may commit it
+                } else {
+                    iteration(nkc + (r - 1) * UT_NKS, clo, nw, INT_MAX, wb);
+                }
                 if (r == rows - 1) {
                     // limits the DMA warp plans chunk k+3 from (it reads them after the chunk barrier)
                     int *cl = clim + ((k + 1) & 1) * 4;
                     if (lane < 2) cl[lane] = sgn * xm;
                     if (lane == 0) cl[2] = max(y - 1, 0);
                 }
+                if (p.dbg) cdbg_busy += clock64() - cdbg_rel;
                 ut_bar_rows();
+                if (p.dbg) {
+                    cdbg_probe += *reinterpret_cast<volatile int *>(pub);
+                    cdbg_rel = clock64();
+                }
             }
-            if (stop) break;
             nk_last = nkc + (rows - 1) * UT_NKS;
             clo_prev = clo;
-            cw_prev = cw;
+            nw_prev = nw;
             __syncthreads(); // chunk end
         }
         if (!stop) {
             const int y_end = y;
             for (int d = 0; d < 2; ++d, ++y) {
-                iteration(nk_last, clo_prev, cw_prev, y_end, 0, 1); // d == 0 verifies row y_end-1
+                iteration(nk_last, clo_prev, nw_prev, y_end, 0); // d == 0 verifies row y_end-1
                 ut_bar_rows();
             }
             if (fail_row == INT_MAX && y_end < h) {
@@ -460,6 +459,10 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             }
         }
         if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
+        if (p.dbg && lane == 0) {
+            atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) cdbg_busy + (cdbg_probe == 0x7fffffff));
+            atomicAdd((unsigned long long *) &p.dbg[15], (unsigned long long) (clock64() - cdbg_t0));
+        }
     } else {
         // =============================================================================== DMA warp
         // Lane r owns row r of the chunk being handled (chunks have at most 8 rows).
@@ -598,8 +601,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 const int *dp = cdesc + ((k - 1) & 3) * 4;
                 const int yp0 = dp[0], prow = dp[1];
                 ut_bar_commit_wait();
-                const int done = misc[5];
-                const int r_end = min(prow, max(misc[0] ? min(done, (int) misc[1]) - yp0 : prow, 0));
+                // rows are verified in order: on a failure everything below the failed row is good
+                const int r_end = min(prow, max(misc[0] ? (int) misc[1] - yp0 : prow, 0));
                 if (lane < r_end)
                     ut_commit_row(p, yp0 + lane, tiles + ((k - 1) & 3) * UT_TILE, rtab + ((k - 1) & 3) * UT_MAXROWS * 8 + lane * 8);
                 ut_bulk_commit();
