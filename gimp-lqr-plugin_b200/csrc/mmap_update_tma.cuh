@@ -36,7 +36,7 @@ namespace b200c {
 #define UT_NCW 12
 #define UT_CT (UT_NCW * 32)
 #define UT_THREADS (UT_CT + 64)
-#define UT_TILE 12032 // words per chunk tile (4 tiles)
+#define UT_TILE 11904 // words per chunk tile (4 tiles)
 #define UT_RW 2048
 #define UT_RWM (UT_RW - 1)
 #define UT_MAXROWS 8
@@ -46,9 +46,10 @@ namespace b200c {
 #define UT_NKW (2 * UT_MAXROWS * UT_NKS) // ballot words [chunk parity][row][UT_NKS]
 #define UT_RIW (2 * UT_MAXROWS * 4)  // row info     [chunk parity][row]{guard base, slots}
 #define UT_RTW (4 * UT_MAXROWS * 8)  // row tables   [tile][row]{xadd, eadd, madd, ladd, zlo, zhi, -, -}
+#define UT_CTW (4 * (UT_MAXROWS + 1) * 8) // control-table slices [tile][row][side]{n[y-1], ext2, ext3, -}
 static constexpr size_t ut_smem_bytes()
 {
-    return sizeof(int) * ((size_t) 4 * UT_TILE + 4 * UT_RW + UT_NKW + UT_RIW + UT_RTW + 16 + 16 + 8 + 8 + 8 + 128);
+    return sizeof(int) * ((size_t) 4 * UT_TILE + 4 * UT_RW + UT_NKW + UT_RIW + UT_RTW + UT_CTW + 16 + 16 + 8 + 8 + 8 + 128);
 }
 
 __device__ __forceinline__ void ut_bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(UT_CT + 32) : "memory"); }
@@ -220,7 +221,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
     unsigned *nk = reinterpret_cast<unsigned *>(ring + 2 * UT_RW);    // [2][8][UT_NKS] "changed" ballot words
     int *rinfo = reinterpret_cast<int *>(nk + UT_NKW);                // [2][8][4] guard base, slots
     int *rtab = rinfo + UT_RIW;                                       // [4][8][8] row tables of the tiles
-    int *pub = rtab + UT_RTW;                                         // [2][8] gr_lo, gr_hi, fail_row, -, act_lo, act_hi
+    int4 *ctile = reinterpret_cast<int4 *>(rtab + UT_RTW);           // [4][9][2] control-table slices of the tiles
+    int *pub = rtab + UT_RTW + UT_CTW;                                         // [2][8] gr_lo, gr_hi, fail_row, -, act_lo, act_hi
     int *cdesc = pub + 16;                                            // [4][4] y0, rows, clo, cw
     int *clim = cdesc + 16;                                           // [2][4] x_min, x_max, y_v at chunk starts
     volatile int *misc = clim + 8;                                    // [8] 0 stop, 1 fb_row, 2 fb_xmin, 3 fb_xmax,
@@ -333,15 +335,16 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         const bool hi = lane & 1;
         const int sgn = hi ? -1 : 1;
         const int floor_s = hi ? -(w - 1) : 0;
-        const int4 *ctab = p.ctab + (hi ? 1 : 0); // this lane's side: {n[y-1], ext(n[y..y+1]), ext(n[y..y+2])} at [2*y]
         int xm = hi ? -min(p.nrg_xmax[0], w - 1) : max(p.nrg_xmin[0], 0); // x_min | -x_max
         int fail_row = INT_MAX;
         unsigned long long cells = 0;
         if (lane < 2) clim[lane] = sgn * xm;
         if (lane == 0) clim[2] = 0;
-        int4 cn = ctab[0]; // record of row y, fetched one row ahead
         __syncthreads(); // start 1: the DMA warp described chunks 0..2
+        if (!ut_mbar_wait(&mbar[0], 0u)) atomicOr(p.err, 4);
+        int4 clast = ctile[hi ? 1 : 0]; // this lane's side: {n[y-1], ext(n[y..y+1]), ext(n[y..y+2])} of row 0
         {
+            const int4 cn = clast;
             // row 0: the active range is the exact band (m = en there); guard from rows (0, 0, 1)
             const int wb = hi ? -(cdesc[2] + cdesc[3] - 1) : cdesc[2];
             const int g = max(max(floor_s, min(xm, cn.y) - 4 * D), wb);
@@ -357,10 +360,8 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         bool stop = false;
         // Runs while the compute warps process row y: verify row y-1 (ballot words nkv, window start clo_v, nwords_v
         // words), publish the ranges of row y+1 (wb: this side's window bound of the chunk holding row y+1).
-        auto iteration = [&](const unsigned *nkv, int clo_v, int nwords_v, int y_lim, int wb) {
-            const int4 c = cn;
-            cn = ctab[2 * min(y + 1, h - 1)];
-            const int a0 = y < h ? c.x : c.y; // energy-band limit of row y-1 (past the last row the record is clamped)
+        auto iteration = [&](const unsigned *nkv, int clo_v, int nwords_v, int y_lim, int wb, int4 c) {
+            const int a0 = y < h ? c.x : c.y; // energy-band limit of row y-1 (past the last row: the last record's n[h-1])
             const int yv = y - 1;
             if (yv >= 1 && yv < y_lim && fail_row == INT_MAX) {
                 const unsigned wv = lane < nwords_v ? nkv[lane] : 0u;
@@ -404,7 +405,7 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
         // The loop mirrors the compute warps' exactly (same stop predicate at the top of every row), so both
         // roles execute the same sequence of row and chunk barriers.
         const unsigned *nk_last = nk;
-        int clo_prev = 0, nw_prev = 0;
+        int clo_prev = 0, nw_prev = 0, klast_c = 0, rows_last = 0;
         long long cdbg_busy = 0, cdbg_rel = clock64(), cdbg_t0 = clock64();
         int cdbg_probe = 0;
         for (int k = 0;; ++k) {
@@ -420,13 +421,17 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
                 if (k > 0) ut_bar_commit_arrive(); // the DMA warp waits for this chunk's hand-shake
                 break;
             }
+            if (!ut_mbar_wait(&mbar[k & 3], (unsigned) ((k >> 2) & 1))) atomicOr(p.err, 4); // table slice landed
+            const int4 *ct = ctile + (k & 3) * (UT_MAXROWS + 1) * 2 + (hi ? 1 : 0);
             for (int r = 0; r < rows; ++r, ++y) {
                 const int wb = r + 1 >= rows ? wb_nxt : wb_cur; // row y+1 may open the next chunk
+                const int4 c = ct[2 * r];
+                clast = c;
                 if (r == 0) { // row y-1 is the last row of the previous chunk
-                    iteration(nk_last, clo_prev, nw_prev, INT_MAX, wb);
+                    iteration(nk_last, clo_prev, nw_prev, INT_MAX, wb, c);
                     if (k > 0) ut_bar_commit_arrive(); // chunk k-1 is verified to its last row: the DMA warp may commit it
                 } else {
-                    iteration(nkc + (r - 1) * UT_NKS, clo, nw, INT_MAX, wb);
+                    iteration(nkc + (r - 1) * UT_NKS, clo, nw, INT_MAX, wb, c);
                 }
                 if (r == rows - 1) {
                     // limits the DMA warp plans chunk k+3 from (it reads them after the chunk barrier)
@@ -444,12 +449,15 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             nk_last = nkc + (rows - 1) * UT_NKS;
             clo_prev = clo;
             nw_prev = nw;
+            klast_c = k;
+            rows_last = rows;
             __syncthreads(); // chunk end
         }
         if (!stop) {
             const int y_end = y;
             for (int d = 0; d < 2; ++d, ++y) {
-                iteration(nk_last, clo_prev, nw_prev, y_end, 0); // d == 0 verifies row y_end-1
+                // d == 0 verifies row y_end-1: its n[] is the record of row y_end's .x, or the last record's .y at the image end
+                iteration(nk_last, clo_prev, nw_prev, y_end, 0, y < h ? ctile[((klast_c & 3) * (UT_MAXROWS + 1) + rows_last) * 2 + (hi ? 1 : 0)] : clast);
                 ut_bar_rows();
             }
             if (fail_row == INT_MAX && y_end < h) {
@@ -536,7 +544,12 @@ __global__ void __launch_bounds__(UT_THREADS, 1) k_mmap_update_tma(DevP p)
             unsigned total = bytes;
 #pragma unroll
             for (int s = 16; s > 0; s >>= 1) total += __shfl_xor_sync(0xffffffffu, total, s);
-            if (lane == 0 && nrows > 0) ut_mbar_expect(&mbar[kk & 3], total);
+            // the control warp's table: records of rows ya .. ya+nrows (one extra: the row after the chunk)
+            const int nrec = min(nrows + 1, h - ya);
+            if (lane == 0 && nrows > 0) {
+                ut_mbar_expect(&mbar[kk & 3], total + (unsigned) nrec * 32u);
+                ut_bulk_load(ctile + (kk & 3) * (UT_MAXROWS + 1) * 2, p.ctab + 2 * ya, (unsigned) nrec * 32u, &mbar[kk & 3]);
+            }
             __syncwarp();
             if (lane < nrows) {
                 if (nraw > 0) ut_bulk_load(tile + off, p.raw + rawbase, (unsigned) nraw * 4u, &mbar[kk & 3]);
