@@ -132,35 +132,25 @@ def device_step(eng, d_in_ptr, d_out_ptr):
         eng.b200c_carver_destroy(c)
 
 
-def abi_step(lib, img):
-    """render_init_carver + render_noninteractive call order (render.c:222-238,318,366,376) on host buffers."""
-    vals = pkg.render.PlugInVals(new_width=W - SEAMS, new_height=H)
-    c = pkg.render.render_init_carver(lib, img, vals)
-    try:
-        c.resize(W - SEAMS, H)
-        out = c.scan_image()
-    finally:
-        c.destroy()
-    return out
+def abi_step(lib_path, img, seams=SEAMS):
+    """The plug-in's own call sequence in C (tests/harness/plugin_sequence.c: render_init_carver + render_noninteractive +
+    write_carver_to_layer, render.c:220-248,318,366,376; io_functions.c:155-164) on host buffers."""
+    harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+    vals = pkg.render.PlugInVals(new_width=W - seams, new_height=H)
+    out, _, res = harness.render(lib_path, img, vals)
+    return out, res
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    oracle = pkg.load_oracle()
     img = pkg.synth.smooth_noise(W, H, CH)
-    est_step = 4.5  # s, one full config-2 pass on one core
+    est_step = 2.5  # s, one full config-2 pass on one core
     seams = SEAMS
     if (args.steps + args.warmup) * est_step > 170:
         seams = max(20, int(SEAMS * 170 / ((args.steps + args.warmup) * est_step)))
-    vals = pkg.render.PlugInVals(new_width=W - seams, new_height=H)
-
     def step():
-        c = pkg.render.render_init_carver(oracle, img, vals)
-        c.resize(W - seams, H)
-        out = c.scan_image()
-        c.destroy()
-        return out
+        return abi_step(pkg.ORACLE_PATH, img, seams)[0]
 
     for _ in range(args.warmup):
         step()
@@ -182,16 +172,11 @@ def run_reference(args, rank):
 
 
 def cpu_baseline():
-    oracle = pkg.load_oracle()
     img = pkg.synth.smooth_noise(W, H, CH)
-    vals = pkg.render.PlugInVals(new_width=W - SEAMS, new_height=H)
     times = []
     for _ in range(3):
         t0 = time.perf_counter()
-        c = pkg.render.render_init_carver(oracle, img, vals)
-        c.resize(W - SEAMS, H)
-        c.scan_image()
-        c.destroy()
+        abi_step(pkg.ORACLE_PATH, img)
         times.append(time.perf_counter() - t0)
     t = statistics.median(times)
     return {"value": SEAMS / t, "unit": UNIT, "cores": 1, "kind": "port",
@@ -229,7 +214,7 @@ def main():
     warmup = max(args.warmup, 3)
 
     eng = bind_engine()
-    lib = pkg.load_product()
+    pkg.load_product()  # fails loudly when the CUDA engine is not built
     eng.b200c_set_device(local_rank)
 
     img = pkg.synth.smooth_noise(W, H, CH, seed=pkg.synth.SEED + rank)
@@ -291,11 +276,14 @@ def main():
 
     # ---------------- e2e: host buffers through the C ABI -------------------------------------------
     for _ in range(2):
-        out_abi = abi_step(lib, img)
+        out_abi, _ = abi_step(pkg.SHIM_PATH, img)
     barrier()
     t0 = time.perf_counter()
+    phases = {"ms_new": 0.0, "ms_setup": 0.0, "ms_resize": 0.0, "ms_scan": 0.0}
     for _ in range(args.steps):
-        out_abi = abi_step(lib, img)
+        out_abi, hres = abi_step(pkg.SHIM_PATH, img)
+        for k in phases:
+            phases[k] += getattr(hres, k) / args.steps
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(out_abi, out_dev), "device-resident and C-ABI paths disagree"
@@ -344,8 +332,9 @@ def main():
                        "mpixel_per_s_carved": value * (W - SEAMS / 2) * H / 1e6},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * H * CH,
                     "d2h_bytes_per_step": (W - SEAMS) * H * CH, "ms_per_step": e2e_ms_max / args.steps,
-                    "path": "liblqr-1.so C ABI: lqr_carver_new..resize..scan_line, pageable host buffers as the "
-                            "plug-in passes them"},
+                    "phases_ms": {k: round(v, 3) for k, v in phases.items()},
+                    "path": "tests/harness/plugin_sequence.c -> liblqr-1.so C ABI: lqr_carver_new .. resize .. scan_line "
+                            "loop, pageable host buffers as the plug-in passes them (rank 0 phases)"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

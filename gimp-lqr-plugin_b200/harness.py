@@ -1,0 +1,62 @@
+"""ctypes binding of tests/harness/plugin_sequence.c: the plug-in's render path (render.c:220-248,318-376;
+io_functions.c:155-164) replayed in C against a library exporting the LqrCarver API."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import REPO_DIR
+from .render import PlugInVals
+
+HARNESS_PATH = os.path.join(REPO_DIR, "tests", "harness", "libplugin_sequence.so")
+
+
+class HarnessVals(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "height", "bpp", "new_width", "new_height", "pres_coeff", "disc_coeff")] + \
+        [("rigidity", C.c_float), ("delta_x", C.c_int), ("enl_step", C.c_float)] + \
+        [(n, C.c_int) for n in ("nrg_func", "res_order", "output_seams", "scaleback", "no_disc_on_enlarge", "mask_bpp",
+                                "resize_aux_layers")]
+
+
+class HarnessResult(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("out_width", "out_height", "n_vmaps", "vmap_width", "vmap_height", "vmap_depth",
+                                       "n_progress_updates")] + \
+        [(n, C.c_double) for n in ("ms_new", "ms_setup", "ms_resize", "ms_scan", "ms_total")]
+
+
+_lib = None
+
+
+def _load():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(HARNESS_PATH)
+        _lib.harness_render.restype = C.c_int
+        _lib.harness_render.argtypes = [C.c_char_p, C.c_void_p, C.POINTER(HarnessVals), C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.POINTER(HarnessResult)]
+    return _lib
+
+
+def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=None, rigmask=None):
+    """Returns (image, first_vmap_or_None, HarnessResult).  Masks must have the layer's size."""
+    layer = np.ascontiguousarray(layer, dtype=np.uint8)
+    h, w, bpp = layer.shape
+    masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint8) for m in (pres, disc, rigmask)]
+    mbpp = next((m.shape[2] for m in masks if m is not None), 0)
+    hv = HarnessVals(w, h, bpp, vals.new_width, vals.new_height, vals.pres_coeff, vals.disc_coeff, vals.rigidity,
+                     vals.delta_x, vals.enl_step, vals.nrg_func, vals.res_order, int(vals.output_seams),
+                     int(vals.scaleback), int(vals.no_disc_on_enlarge), mbpp, int(vals.resize_aux_layers))
+    out = np.zeros((max(h, vals.new_height), max(w, vals.new_width), bpp), dtype=np.uint8)
+    vmap = np.zeros((h, w), dtype=np.int32)
+    res = HarnessResult()
+    ptr = [None if m is None else m.ctypes.data for m in masks]
+    ok = _load().harness_render(lib_path.encode(), layer.ctypes.data, C.byref(hv), ptr[0], ptr[1], ptr[2], out.ctypes.data,
+                                vmap.ctypes.data, C.byref(res))
+    if not ok:
+        raise RuntimeError("harness_render failed")
+    img = out.reshape(-1)[: res.out_width * res.out_height * bpp].reshape(res.out_height, res.out_width, bpp).copy()
+    vm = vmap.reshape(-1)[: res.vmap_width * res.vmap_height].reshape(res.vmap_height, res.vmap_width).copy() \
+        if res.n_vmaps else None
+    return img, vm, res
