@@ -21,11 +21,9 @@
 
 #include "b200carve.h"
 #include "carver_kernels.cuh"
-#include "mmap_update_fast.cuh"
-#include "vpath_mmap_tiled.cuh"
-#include "mmap_update_spec.cuh"
-#include "mmap_update_tma.cuh"
-#include "vpath_tma.cuh"
+#include "band_dp.cuh"
+#include "seam_path.cuh"
+#include "mmap_full_cluster.cuh"
 
 using namespace b200c;
 
@@ -122,18 +120,17 @@ struct B200Carver {
 
     uint8_t *rgb = nullptr;
     int *vs = nullptr; // owned by the root; attached carvers alias it
-    float *en = nullptr, *m = nullptr, *bias = nullptr, *rigmask = nullptr;
-    int *least = nullptr, *raw = nullptr;
-    int *vpath = nullptr, *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
+    float *bias = nullptr, *rigmask = nullptr;   // physical (pixel id)
+    int *raw = nullptr;                          // index table: x-th visible pixel of row y
+    float *en = nullptr, *m = nullptr, *rig = nullptr; // compact maps [h_start][pitch] (DevP)
+    int8_t *pdx = nullptr;                       // compact parent offsets
+    int pitch = 0;
+    int *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
     long long *dbg_d = nullptr;               // role cycle counters (B200C_DBG=1)
     bool owns_stream = true;
-    int4 *ctab_d = nullptr;                   // per-row energy-band combos for the control warp
-    int *pre_lo = nullptr, *pre_hi = nullptr; // sliding extremes of the energy bands (window prediction)
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
-    int vpath_kernel = 3;                     // B200C_VPATH=2: cp.async windowed backtrack instead of the TMA one
-    int update_kernel = 4;                    // B200C_UPDATE=3: cp.async-staged speculative kernel, 2: staged exact kernel
 
     float rigidity = 0.f;
     int delta_x = 1;
@@ -154,7 +151,6 @@ template <class T>
 int dalloc(B200Carver *c, T **p, size_t n, bool zero)
 {
     *p = nullptr;
-    n += 8; // slack: the TMA staging reads 16-byte aligned spans that may end a few elements past the map
     CU_TRY(cudaMallocAsync((void **) p, n * sizeof(T), c->stream));
     if (zero) CU_TRY(cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream));
     return B200C_OK;
@@ -189,6 +185,7 @@ DevP view(const B200Carver *c)
     p.h0 = c->h0;
     p.w_start = c->w_start;
     p.raw_stride = c->w_start;
+    p.pitch = c->pitch;
     p.channels = c->channels;
     p.alpha = c->alpha;
     p.level = c->level;
@@ -203,18 +200,17 @@ DevP view(const B200Carver *c)
     p.raw = c->raw;
     p.en = c->en;
     p.m = c->m;
-    p.least = c->least;
+    p.pdx = c->pdx;
+    p.rig = c->rig;
     p.bias = c->bias;
     p.rigmask = c->rigmask;
     p.rigmap = c->rigmap_d ? c->rigmap_d + c->delta_x : nullptr;
-    p.vpath = c->vpath;
     p.vpath_x = c->vpath_x;
     p.nrg_xmin = c->nrg_xmin;
     p.nrg_xmax = c->nrg_xmax;
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
-    p.ctab = c->ctab_d;
     return p;
 }
 
@@ -255,15 +251,37 @@ int init_raw(B200Carver *c)
     return check_launch("k_init_raw");
 }
 
+// The compact maps (DevP): en for every carver that computes energy, m / pdx for an initialised one; sized by
+// the reference size, which only flatten and transpose change.  rig is made on demand by build_maps.
+void free_maps(B200Carver *c)
+{
+    dfree(c, c->en);
+    dfree(c, c->m);
+    dfree(c, c->pdx);
+    dfree(c, c->rig);
+    c->nrg_uptodate = false;
+}
+
+int alloc_maps(B200Carver *c)
+{
+    free_maps(c);
+    c->pitch = (c->w_start + 15) / 16 * 16;
+    const size_t n = (size_t) c->pitch * c->h_start + 64; // slack: aligned windows may end past the last row
+    if (c->nrg_active) B_TRY(dalloc(c, &c->en, n, true));
+    if (c->active) {
+        B_TRY(dalloc(c, &c->m, n, true));
+        B_TRY(dalloc(c, &c->pdx, n, true));
+    }
+    return B200C_OK;
+}
+
 int init_energy_related(B200Carver *c)
 {
     if (c->active || c->nrg_active) return fail(B200C_ERROR, "init_energy_related: already initialised");
-    const size_t n = (size_t) c->w * c->h;
-    B_TRY(dalloc(c, &c->en, n, true));
     B_TRY(dalloc(c, &c->raw, (size_t) c->w_start * c->h_start, false));
     B_TRY(init_raw(c));
     c->nrg_active = true;
-    return B200C_OK;
+    return alloc_maps(c);
 }
 
 // ---- A.3 / A.5 full passes ---------------------------------------------------------------------------
@@ -278,9 +296,7 @@ int build_emap(B200Carver *c)
     return B200C_OK;
 }
 
-constexpr int kUpdatePrefetchRows = 6; // KP of k_mmap_update_fast
-
-bool fast_path(const B200Carver *c) { return !c->generic && c->delta_x <= UF_MAX_DELTA; }
+bool fast_path(const B200Carver *c) { return !c->generic; }
 
 int raise_smem_limits()
 {
@@ -291,16 +307,7 @@ int raise_smem_limits()
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
             if (e != cudaSuccess && err == cudaSuccess) err = e;
         };
-        set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, false>, UfLayout<kUpdatePrefetchRows, false>::bytes);
-        set((const void *) k_mmap_update_fast<kUpdatePrefetchRows, true>, UfLayout<kUpdatePrefetchRows, true>::bytes);
-        set((const void *) k_mmap_update_tma<true>, ut_smem_bytes());
-        set((const void *) k_mmap_update_tma<false>, ut_smem_bytes());
-        set((const void *) k_mmap_update_spec<true>, us_smem_bytes());
-        set((const void *) k_mmap_update_spec<false>, us_smem_bytes());
-        set((const void *) k_vpath_fast, vp_smem_bytes());
-        set((const void *) k_vpath_tma<true>, vt_smem_bytes());
-        set((const void *) k_vpath_tma<false>, vt_smem_bytes());
-        set((const void *) k_mmap_full_tile, 200 * 1024);
+        (void) set;
     });
     if (err != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", err);
     return B200C_OK;
@@ -308,19 +315,6 @@ int raise_smem_limits()
 
 int build_mmap(B200Carver *c)
 {
-    if (fast_path(c)) {
-        const MfGeom g = mf_geometry(c->delta_x, c->w, c->rigidity != 0.f && c->rigmask != nullptr);
-        if (g.T <= 1024 && g.smem <= 200 * 1024) {
-            B_TRY(raise_smem_limits());
-            const int grid = (c->w + g.S - 1) / g.S;
-            const int launches = (c->h + g.K - 1) / g.K;
-            StageScope sc("mmap_full", c->stream, launches);
-            const DevP p = view(c);
-            for (int y0 = 0; y0 < c->h; y0 += g.K)
-                k_mmap_full_tile<<<grid, g.T, g.smem, c->stream>>>(p, y0, g.K, g.S);
-            return check_launch("k_mmap_full_tile");
-        }
-    }
     StageScope sc("mmap_full", c->stream);
     k_mmap_full<<<1, 1024, 0, c->stream>>>(view(c));
     return check_launch("k_mmap_full");
@@ -351,24 +345,18 @@ int inflate(B200Carver *c, int l)
         B_TRY(check_launch("k_inflate_rows"));
     }
     dfree(c, c->rgb);
-    dfree(c, c->en);
-    dfree(c, c->m);
-    dfree(c, c->least);
     dfree(c, c->bias);
     dfree(c, c->rigmask);
-    c->nrg_uptodate = false;
+    c->nrg_uptodate = false; // the compact maps keep their size (w_start x h); the next build_maps refills them
     c->rgb = new_rgb;
     if (!c->root) {
         dfree(c, c->vs);
         c->vs = new_vs;
         propagate_vs(c);
     }
-    if (c->nrg_active) B_TRY(dalloc(c, &c->en, n1, true));
     if (c->active) {
         c->bias = new_bias;
         c->rigmask = new_rigmask;
-        B_TRY(dalloc(c, &c->m, n1, true));
-        B_TRY(dalloc(c, &c->least, n1, true));
     }
     c->w0 = w1;
     c->w = c->w_start;
@@ -385,14 +373,7 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (fast) B_TRY(raise_smem_limits());
     {
         StageScope sc("vpath", s);
-        if (fast && c->vpath_kernel == 3 && c->delta_x == 1)
-            k_vpath_tma<true><<<1, VT_THREADS, vt_smem_bytes(), s>>>(view(c));
-        else if (fast && c->vpath_kernel == 3)
-            k_vpath_tma<false><<<1, VT_THREADS, vt_smem_bytes(), s>>>(view(c));
-        else if (fast)
-            k_vpath_fast<<<1, VP_THREADS, vp_smem_bytes(), s>>>(view(c));
-        else
-            k_vpath<<<1, 1024, 0, s>>>(view(c));
+        k_vpath<<<1, 1024, 0, s>>>(view(c));
         B_TRY(check_launch("k_vpath"));
     }
     const int vs_value = l + c->max_level - 1;
@@ -407,10 +388,7 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (c->w > 1) {
         {
             StageScope sc("energy_band", s);
-            if (fast)
-                k_energy_band_pre<<<(c->h + 7) / 8, 256, 0, s>>>(view(c), 2 * kUpdatePrefetchRows, c->pre_lo, c->pre_hi, c->ctab_d);
-            else
-                k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
+            k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
             B_TRY(check_launch("k_energy_band"));
         }
         c->nrg_uptodate = true;
@@ -419,22 +397,7 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             B_TRY(build_mmap(c));
         } else {
             StageScope sc("mmap_update", s);
-            if (fast && c->rigidity == 0.f && c->update_kernel == 4 && c->delta_x == 1)
-                k_mmap_update_tma<true><<<1, UT_THREADS, ut_smem_bytes(), s>>>(view(c));
-            else if (fast && c->rigidity == 0.f && c->update_kernel == 4)
-                k_mmap_update_tma<false><<<1, UT_THREADS, ut_smem_bytes(), s>>>(view(c));
-            else if (fast && c->rigidity == 0.f && c->update_kernel == 3 && c->delta_x == 1)
-                k_mmap_update_spec<true><<<1, US_THREADS, us_smem_bytes(), s>>>(view(c));
-            else if (fast && c->rigidity == 0.f && c->update_kernel == 3)
-                k_mmap_update_spec<false><<<1, US_THREADS, us_smem_bytes(), s>>>(view(c));
-            else if (fast && c->rigidity != 0.f)
-                k_mmap_update_fast<kUpdatePrefetchRows, true>
-                    <<<1, UF_THREADS, UfLayout<kUpdatePrefetchRows, true>::bytes, s>>>(view(c), c->pre_lo, c->pre_hi);
-            else if (fast)
-                k_mmap_update_fast<kUpdatePrefetchRows, false>
-                    <<<1, UF_THREADS, UfLayout<kUpdatePrefetchRows, false>::bytes, s>>>(view(c), c->pre_lo, c->pre_hi);
-            else
-                k_mmap_update<<<1, 512, 0, s>>>(view(c));
+            k_mmap_update<<<1, 512, 0, s>>>(view(c));
             B_TRY(check_launch("k_mmap_update"));
         }
     } else {
@@ -443,6 +406,18 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
         B_TRY(check_launch("k_finish_vsmap"));
     }
     return B200C_OK;
+}
+
+// the rigidity mask in current coordinates, for the DP kernels (start of a build_maps session)
+int gather_rig(B200Carver *c)
+{
+    dfree(c, c->rig);
+    if (c->rigidity == 0.f || !c->rigmask) return B200C_OK;
+    B_TRY(dalloc(c, &c->rig, (size_t) c->pitch * c->h_start + 64, true));
+    dim3 grid((c->w + 255) / 256, c->h);
+    StageScope sc("gather_rig", c->stream);
+    k_gather_rig<<<grid, 256, 0, c->stream>>>(view(c));
+    return check_launch("k_gather_rig");
 }
 
 int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user, bool do_inflate)
@@ -481,10 +456,7 @@ int flatten(B200Carver *c)
 {
     for (B200Carver *a : c->attached) B_TRY(flatten(a));
 
-    dfree(c, c->en);
-    dfree(c, c->m);
-    dfree(c, c->least);
-    c->nrg_uptodate = false;
+    free_maps(c);
 
     const size_t n = (size_t) c->w * c->h;
     uint8_t *new_rgb = nullptr;
@@ -523,12 +495,8 @@ int flatten(B200Carver *c)
         dfree(c, c->raw);
         B_TRY(dalloc(c, &c->raw, n, false));
         B_TRY(init_raw(c));
-        B_TRY(dalloc(c, &c->en, n, true));
     }
-    if (c->active) {
-        B_TRY(dalloc(c, &c->m, n, true));
-        B_TRY(dalloc(c, &c->least, n, true));
-    }
+    B_TRY(alloc_maps(c));
     return B200C_OK;
 }
 
@@ -554,10 +522,7 @@ int transpose(B200Carver *c)
     for (B200Carver *a : c->attached) B_TRY(transpose(a));
 
     const size_t n = (size_t) c->w0 * c->h0;
-    dfree(c, c->en);
-    dfree(c, c->m);
-    dfree(c, c->least);
-    c->nrg_uptodate = false;
+    free_maps(c);
 
     uint8_t *new_rgb = nullptr;
     float *new_bias = nullptr, *new_rigmask = nullptr;
@@ -601,22 +566,12 @@ int transpose(B200Carver *c)
         dfree(c, c->raw);
         B_TRY(dalloc(c, &c->raw, n, false));
         B_TRY(init_raw(c));
-        B_TRY(dalloc(c, &c->en, n, true));
     }
+    B_TRY(alloc_maps(c));
     if (c->active) {
-        B_TRY(dalloc(c, &c->m, n, true));
-        B_TRY(dalloc(c, &c->least, n, true));
-        dfree(c, c->vpath);
         dfree(c, c->vpath_x);
         dfree(c, c->nrg_xmin);
         dfree(c, c->nrg_xmax);
-        dfree(c, c->pre_lo);
-        dfree(c, c->pre_hi);
-        dfree(c, c->ctab_d);
-        B_TRY(dalloc(c, &c->ctab_d, (size_t) 2 * c->h, true));
-        B_TRY(dalloc(c, &c->pre_lo, (size_t) c->h, true));
-        B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
-        B_TRY(dalloc(c, &c->vpath, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
@@ -671,10 +626,6 @@ B200Carver *carver_new_common(int width, int height, int channels)
     {
         const char *g = getenv("B200C_GENERIC");
         c->generic = g && atoi(g) != 0;
-        const char *u = getenv("B200C_UPDATE");
-        if (u && atoi(u) >= 2 && atoi(u) <= 4) c->update_kernel = atoi(u);
-        const char *v = getenv("B200C_VPATH");
-        if (v && atoi(v) == 2) c->vpath_kernel = 2;
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
     if (g_use_ext_stream) {
@@ -782,20 +733,14 @@ void b200c_carver_destroy(B200Carver *c)
     const bool owns_stream = c->root == nullptr && c->owns_stream; // attached carvers run on their root's queue
     dfree(c, c->rgb);
     if (!c->root) dfree(c, c->vs);
-    dfree(c, c->en);
-    dfree(c, c->m);
-    dfree(c, c->least);
+    free_maps(c);
     dfree(c, c->raw);
     dfree(c, c->bias);
     dfree(c, c->rigmask);
-    dfree(c, c->vpath);
     dfree(c, c->vpath_x);
     dfree(c, c->nrg_xmin);
     dfree(c, c->nrg_xmax);
-    dfree(c, c->pre_lo);
-    dfree(c, c->pre_hi);
     dfree(c, c->err_d);
-    dfree(c, c->ctab_d);
     if (c->cells_d) {
         unsigned long long n = 0;
         if (cudaMemcpyAsync(&n, c->cells_d, sizeof n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
@@ -827,18 +772,14 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     if (!c || delta_x < 0) return fail(B200C_ERROR, "carver_init: bad arguments");
     if (c->active) return fail(B200C_ERROR, "carver_init: already active");
     B_TRY(use_device(c));
+    if (delta_x > B200C_MAX_DELTA) return fail(B200C_ERROR, "carver_init: delta_x above the engine's limit (120)");
     if (!c->nrg_active) B_TRY(init_energy_related(c));
-    const size_t n = (size_t) c->w * c->h;
-    B_TRY(dalloc(c, &c->m, n, true));
-    B_TRY(dalloc(c, &c->least, n, true));
-    B_TRY(dalloc(c, &c->vpath, (size_t) c->h, true));
+    c->active = true;
+    B_TRY(alloc_maps(c));
     B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
-    B_TRY(dalloc(c, &c->pre_lo, (size_t) c->h, true));
-    B_TRY(dalloc(c, &c->pre_hi, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
-    B_TRY(dalloc(c, &c->ctab_d, (size_t) 2 * c->h, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));
     c->delta_x = delta_x;
@@ -848,7 +789,6 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
         c->rigmap_h[x + delta_x] = c->rigidity * powf(fabsf((float) x), 1.5f) / c->h; // A.1 / A.4
     B_TRY(dalloc(c, &c->rigmap_d, c->rigmap_h.size(), false));
     B_TRY(upload_rigmap(c));
-    c->active = true;
     return B200C_OK;
 }
 
@@ -964,6 +904,7 @@ int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_pro
     B_TRY(use_device(c));
     set_width_one(c, c->w_start - c->max_level + 1);
     B_TRY(build_emap(c));
+    B_TRY(gather_rig(c));
     B_TRY(build_mmap(c));
     B_TRY(build_vsmap(c, depth, update_step, progress, user, true));
     return B200C_OK;
@@ -1109,6 +1050,7 @@ int b200c_debug_build(B200Carver *c, int n_seams)
     B_TRY(use_device(c));
     set_width_one(c, c->w_start - c->max_level + 1);
     B_TRY(build_emap(c));
+    B_TRY(gather_rig(c));
     B_TRY(build_mmap(c));
     if (n_seams > 0) B_TRY(build_vsmap(c, c->max_level + n_seams, 1, nullptr, nullptr, false));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -1122,9 +1064,21 @@ long b200c_debug_fetch(B200Carver *c, int what, void *out, long cap)
     const void *src = nullptr;
     long n = (long) c->w0 * c->h0;
     switch (what) {
-        case B200C_DBG_EN: src = c->en; break;
-        case B200C_DBG_M: src = c->m; break;
-        case B200C_DBG_LEAST: src = c->least; break;
+        case B200C_DBG_EN:
+        case B200C_DBG_M:
+        case B200C_DBG_LEAST: {
+            // the compact maps, scattered back to the physical (pixel id) layout liblqr keeps them in
+            if (!c->raw || !c->en || (what != B200C_DBG_EN && !c->m)) return 0;
+            int *tmp = nullptr;
+            if (dalloc(c, &tmp, (size_t) n, true) != B200C_OK) return -1;
+            dim3 grid((c->w + 255) / 256, c->h);
+            k_export_physical<<<grid, 256, 0, c->stream>>>(view(c), what - B200C_DBG_EN, tmp);
+            if (n > cap) n = cap;
+            const bool ok = cudaMemcpyAsync(out, tmp, (size_t) n * 4, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+                            cudaStreamSynchronize(c->stream) == cudaSuccess;
+            dfree(c, tmp);
+            return ok ? n : -1;
+        }
         case B200C_DBG_RAW: src = c->raw; n = (long) c->w_start * c->h_start; break;
         case B200C_DBG_VS: src = c->vs; break;
         case B200C_DBG_VPATH_X: src = c->vpath_x; n = c->h; break;

@@ -13,12 +13,27 @@ namespace b200c {
 enum { READ_BRIGHTNESS = 0, READ_LUMA = 1 };
 enum { GRAD_NORM = 0, GRAD_SUMABS = 1, GRAD_XABS = 2, GRAD_NULL = 3 };
 
+// Parent offsets are stored as one signed byte per cell; PDX_NONE marks "the parent pixel is gone".
+#define B200C_PDX_NONE (-128)
+#define B200C_MAX_DELTA 120 // |parent offset| <= delta_x + 1 must fit the byte
+
 // Device view of one carver, passed by value to every kernel.
+//
+// HBM layout.  Pixels, the visibility map, bias and rigidity mask are PHYSICAL
+// (w0 x h0, never moved).  The seam-search state is COMPACT: row y of en / m / pdx / rig holds the values
+// of the row's visible pixels in their CURRENT order, x in [0, w), at pitch `pitch` (a multiple of 16
+// cells, so every row and every 16-cell window is 64-byte aligned for vector and TMA bulk access).  The
+// carve kernel closes the gap in all of them, so DP rows are contiguous and need no indirection; `raw`
+// (x-th visible pixel of row y -> physical id) is only used to reach pixels, bias and the visibility map.
+// pdx[y][x] = x_parent - x in CURRENT coordinates: the carve kernel re-expresses it after every seam so it
+// keeps naming the same parent PIXEL (liblqr stores the parent's pixel id in `least`), or PDX_NONE once
+// that pixel has been carved away.
 struct DevP {
     int w, h;          // current size (internal orientation)
     int w0, h0;        // allocated map size
     int w_start;       // reference width
     int raw_stride;    // pitch of the raw index table (== w_start)
+    int pitch;         // pitch of the compact maps, in cells
     int channels, alpha;
     int level;
     int delta_x;
@@ -28,17 +43,17 @@ struct DevP {
     const uint8_t *rgb;
     int *vs;
     int *raw;
-    float *en;
-    float *m;
-    int *least;
+    float *en;         // compact
+    float *m;          // compact
+    int8_t *pdx;       // compact
+    float *rig;        // compact copy of the rigidity mask (NULL without a mask)
     const float *bias;
     const float *rigmask;
     const float *rigmap; // centred: rigmap[dx], dx in [-delta_x, delta_x]
-    int *vpath, *vpath_x, *nrg_xmin, *nrg_xmax;
-    unsigned long long *cells; // running count of band cells visited by the incremental DP
-    const int4 *ctab;  // per-row energy-band combos for the control warp (see k_energy_band_pre)
-    long long *dbg;    // optional cycle counters of the band-DP roles (B200C_DBG=1), 16 slots
-    int *err;          // device error word: bit 0 staged window did not cover the band, bit 1 backtrack left its window
+    int *vpath_x, *nrg_xmin, *nrg_xmax;
+    unsigned long long *cells; // running count of band cells evaluated by the incremental DP
+    long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
+    int *err;          // device error word: bit 0 band left its staged window, bit 1 backtrack met a dead parent, bit 2 bulk copy timed out
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -95,40 +110,44 @@ __device__ __forceinline__ float energy_at(const DevP &p, int x, int y)
     return __fadd_rn(e, b_add);
 }
 
-// A.5 best parent of cell (x, y): scan x+[-delta_x, delta_x] (clipped) left to right, strict '<' keeps the
-// leftmost minimum, leftright==1 turns ties to the right.  Returns the candidate value, parent pixel id.
-__device__ __forceinline__ float best_parent(const DevP &p, int x, int y, int z, int &parent)
+// A.5 best parent of cell x of a row whose predecessor row holds the cumulative values `up` (compact, current
+// coordinates): scan x+[-delta_x, delta_x] (clipped) left to right, strict '<' keeps the leftmost minimum,
+// leftright==1 turns ties to the right.  Returns the candidate value; bdx = x_parent - x.  rf = the cell's
+// rigidity-mask factor (1 without a mask).
+__device__ __forceinline__ float best_parent(const DevP &p, const float *up, int x, float rf, int &bdx)
 {
     const int x1_min = max(-x, -p.delta_x);
     const int x1_max = min(p.w - 1 - x, p.delta_x);
-    const int *up = p.raw + (size_t) (y - 1) * p.raw_stride;
-    int zd = up[x + x1_min];
-    int least = zd;
+    int least = x1_min;
     float best;
     if (p.use_rig) {
-        const float rf = p.rigmask ? p.rigmask[z] : 1.f;
-        best = __fadd_rn(p.m[zd], __fmul_rn(rf, p.rigmap[x1_min]));
+        best = __fadd_rn(up[x + x1_min], __fmul_rn(rf, p.rigmap[x1_min]));
         for (int x1 = x1_min + 1; x1 <= x1_max; ++x1) {
-            zd = up[x + x1];
-            const float cand = __fadd_rn(p.m[zd], __fmul_rn(rf, p.rigmap[x1]));
+            const float cand = __fadd_rn(up[x + x1], __fmul_rn(rf, p.rigmap[x1]));
             if (cand < best || (cand == best && p.leftright == 1)) {
                 best = cand;
-                least = zd;
+                least = x1;
             }
         }
     } else {
-        best = p.m[zd];
+        best = up[x + x1_min];
         for (int x1 = x1_min + 1; x1 <= x1_max; ++x1) {
-            zd = up[x + x1];
-            const float cand = p.m[zd];
+            const float cand = up[x + x1];
             if (cand < best || (cand == best && p.leftright == 1)) {
                 best = cand;
-                least = zd;
+                least = x1;
             }
         }
     }
-    parent = least;
+    bdx = least;
     return best;
+}
+
+// liblqr's keep-old test of the incremental DP (A.8): same parent and (double) |m_old - m_new| < 1e-5.
+// For floats that is |d| <= 0x3727C5AC, the largest float below the double 1e-5.
+__device__ __forceinline__ bool keep_old(int pdx_old, int pdx_new, float m_old, float m_new)
+{
+    return pdx_old == pdx_new && fabsf(__fsub_rn(m_old, m_new)) <= __int_as_float(0x3727C5AC);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -139,14 +158,22 @@ __global__ void k_init_raw(int *raw, int w, int h)
     if (x < w && y < h) raw[(size_t) y * w + x] = y * w + x;
 }
 
+// compact copy of the rigidity mask in current coordinates (start of a build_maps session)
+__global__ void __launch_bounds__(256) k_gather_rig(DevP p)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= p.w || y >= p.h) return;
+    p.rig[(size_t) y * p.pitch + x] = p.rigmask[p.raw[(size_t) y * p.raw_stride + x]];
+}
+
 // K1 -- A.3 full energy map (lqr_carver_build_emap): one thread per visible pixel.
 __global__ void __launch_bounds__(256) k_energy_full(DevP p)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= p.w || y >= p.h) return;
-    const int z = p.raw[(size_t) y * p.raw_stride + x];
-    p.en[z] = energy_at(p, x, y);
+    p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
 }
 
 // K1b -- A.8 energy band after a carve (lqr_carver_update_emap): one warp per row derives the row's
@@ -171,92 +198,85 @@ __global__ void __launch_bounds__(256) k_energy_band(DevP p)
         p.nrg_xmin[y] = xmin;
         p.nrg_xmax[y] = xmax;
     }
-    for (int x = xmin + lane; x <= xmax; x += 32) {
-        const int z = p.raw[(size_t) y * p.raw_stride + x];
-        p.en[z] = energy_at(p, x, y);
-    }
+    for (int x = xmin + lane; x <= xmax; x += 32) p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
 }
 
 // K2 (generic) -- A.5 full m-map DP (lqr_carver_build_mmap): one CTA walks the rows, the row is spread
 // over the threads, a block barrier separates dependent rows.  Correct for any width / delta_x; the
-// tiled multi-CTA version lives in mmap_tiled.cuh.
+// cluster kernel of mmap_full_cluster.cuh is the fast path.
 __global__ void __launch_bounds__(1024) k_mmap_full(DevP p)
 {
-    for (int x = threadIdx.x; x < p.w; x += blockDim.x) {
-        const int z = p.raw[x];
-        p.m[z] = p.en[z];
-    }
+    for (int x = threadIdx.x; x < p.w; x += blockDim.x) p.m[x] = p.en[x];
     __syncthreads();
     for (int y = 1; y < p.h; ++y) {
-        const int *row = p.raw + (size_t) y * p.raw_stride;
+        const size_t o = (size_t) y * p.pitch;
+        const float *up = p.m + o - p.pitch;
         for (int x = threadIdx.x; x < p.w; x += blockDim.x) {
-            const int z = row[x];
-            int parent;
-            const float best = best_parent(p, x, y, z, parent);
-            p.least[z] = parent;
-            p.m[z] = __fadd_rn(p.en[z], best);
+            int bdx;
+            const float best = best_parent(p, up, x, p.rig ? p.rig[o + x] : 1.f, bdx);
+            p.pdx[o + x] = (int8_t) bdx;
+            p.m[o + x] = __fadd_rn(p.en[o + x], best);
         }
         __syncthreads();
     }
 }
 
-// K2b (generic) -- A.8 incremental DP (lqr_carver_update_mmap) with the keep-old rule (same parent and
-// |m_old - m_new| < 1e-5 keeps m_old) and the self-trimming band: the leading run of kept cells advances
-// x_min, a trailing run pulls x_max back to its first cell.  One CTA, rows serial, band parallel.
-__global__ void __launch_bounds__(512) k_mmap_update(DevP p)
+// K2b (generic) -- A.8 incremental DP (lqr_carver_update_mmap) with the keep-old rule.  Rows [y_from, h) are
+// processed by one CTA; (lo, hi) is the hull of the cells of row y_from-1 whose value or parent changed
+// (lo > hi: none).  Row y evaluates [min(lo, nrg_xmin[y]) - delta_x, max(hi, nrg_xmax[y]) + delta_x]: every
+// cell with a changed parent, a changed energy or a changed set of parent candidates lies in that range, and a
+// cell outside it re-evaluates to "keep" (DESIGN.md section 5), so the stored maps are the ones liblqr's
+// self-trimming band produces.  s_red: 64 ints of shared scratch.
+__device__ void update_rows_generic(const DevP &p, int y_from, int lo, int hi, int *s_red)
 {
-    __shared__ int s_first[2][16];
-    __shared__ int s_last[2][16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    int x_min = max(p.nrg_xmin[0], 0);
-    int x_max = min(p.nrg_xmax[0], p.w - 1);
-    for (int x = x_min + tid; x <= x_max; x += blockDim.x) {
-        const int z = p.raw[x];
-        p.m[z] = p.en[z];
-    }
-    __syncthreads();
-    for (int y = 1; y < p.h; ++y) {
-        x_min = min(x_min, p.nrg_xmin[y]);
-        x_max = max(x_max, p.nrg_xmax[y]);
-        x_min = max(x_min - p.delta_x, 0);
-        x_max = min(x_max + p.delta_x, p.w - 1);
-        const int *row = p.raw + (size_t) y * p.raw_stride;
-        int first = INT_MAX, last = INT_MIN; // extremes of the cells whose m changed (not kept)
-        for (int x = x_min + tid; x <= x_max; x += blockDim.x) {
-            const int z = row[x];
-            int parent;
-            const float new_m = __fadd_rn(p.en[z], best_parent(p, x, y, z, parent));
-            const bool keep = (p.least[z] == parent) && ((double) fabsf(__fsub_rn(p.m[z], new_m)) < 1e-5);
-            if (!keep) {
-                p.m[z] = new_m;
+    unsigned long long cells = 0;
+    for (int y = y_from; y < p.h; ++y) {
+        const size_t o = (size_t) y * p.pitch;
+        const int elo = max(min(lo, p.nrg_xmin[y]) - (y ? p.delta_x : 0), 0);
+        const int ehi = min(max(hi, p.nrg_xmax[y]) + (y ? p.delta_x : 0), p.w - 1);
+        int first = INT_MAX, last = INT_MIN;
+        for (int x = elo + tid; x <= ehi; x += blockDim.x) {
+            if (y == 0) { // row 0: m = en over the energy band; the band carries over to row 1 (A.8)
+                p.m[x] = p.en[x];
+                first = min(first, x);
+                last = max(last, x);
+                continue;
+            }
+            int bdx;
+            const float new_m = __fadd_rn(p.en[o + x], best_parent(p, p.m + o - p.pitch, x, p.rig ? p.rig[o + x] : 1.f, bdx));
+            if (!keep_old(p.pdx[o + x], bdx, p.m[o + x], new_m)) {
+                p.m[o + x] = new_m;
+                p.pdx[o + x] = (int8_t) bdx;
                 first = min(first, x);
                 last = max(last, x);
             }
-            p.least[z] = parent;
         }
+        if (tid == 0 && ehi >= elo) cells += (unsigned long long) (ehi - elo + 1);
         first = __reduce_min_sync(0xffffffffu, first);
         last = __reduce_max_sync(0xffffffffu, last);
-        const int buf = y & 1;
+        const int buf = (y & 1) * 32;
         if (lane == 0) {
-            s_first[buf][warp] = first;
-            s_last[buf][warp] = last;
+            s_red[buf + warp] = first;
+            s_red[buf + 16 + warp] = last;
         }
-        __syncthreads(); // publishes this row's m/least and the per-warp extremes
-        int F = INT_MAX, L = INT_MIN;
+        __syncthreads(); // publishes this row's m / pdx and the per-warp extremes
+        lo = INT_MAX, hi = INT_MIN;
         for (int i = 0; i < nwarp; ++i) {
-            F = min(F, s_first[buf][i]);
-            L = max(L, s_last[buf][i]);
-        }
-        if (x_max >= x_min) {
-            const int nx_min = (F != INT_MAX) ? F : x_max + 1;
-            const int nx_max = (L != INT_MIN) ? (L == x_max ? x_max : L + 1) : x_min;
-            x_min = nx_min;
-            x_max = nx_max;
+            lo = min(lo, s_red[buf + i]);
+            hi = max(hi, s_red[buf + 16 + i]);
         }
     }
+    if (tid == 0 && p.cells) atomicAdd(p.cells, cells);
 }
 
-// K3 (generic) -- A.6 seam: arg-min over the last row of m with the tie rule, then follow `least` upwards.
+__global__ void __launch_bounds__(512) k_mmap_update(DevP p)
+{
+    __shared__ int s_red[64];
+    update_rows_generic(p, 0, INT_MAX, INT_MIN, s_red);
+}
+
+// K3 (generic) -- A.6 seam: arg-min over the last row of m with the tie rule, then follow the parents upwards.
 __device__ __forceinline__ bool seam_better(float ov, int ox, float v, int x, int leftright)
 {
     if (ox < 0) return false;
@@ -266,16 +286,15 @@ __device__ __forceinline__ bool seam_better(float ov, int ox, float v, int x, in
     return false;
 }
 
-__global__ void __launch_bounds__(1024) k_vpath(DevP p)
+// block-wide arg-min over the last row (all threads must call); result valid in thread 0. s_v/s_x: 32 entries.
+__device__ __forceinline__ int last_row_argmin(const DevP &p, float *s_v, int *s_x)
 {
-    __shared__ float s_v[32];
-    __shared__ int s_x[32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    const int *row = p.raw + (size_t) (p.h - 1) * p.raw_stride;
+    const float *row = p.m + (size_t) (p.h - 1) * p.pitch;
     float best = 536870912.f; // (float)(1 << 29)
     int bx = -1;
     for (int x = tid; x < p.w; x += blockDim.x) {
-        const float v = p.m[row[x]];
+        const float v = row[x];
         if (v < best || (v == best && p.leftright == 1)) {
             best = v;
             bx = x;
@@ -294,54 +313,89 @@ __global__ void __launch_bounds__(1024) k_vpath(DevP p)
         s_x[warp] = bx;
     }
     __syncthreads();
-    if (tid != 0) return;
-    for (int i = 1; i < nwarp; ++i)
-        if (seam_better(s_v[i], s_x[i], best, bx, p.leftright)) {
-            best = s_v[i];
-            bx = s_x[i];
-        }
-    int last_x = bx < 0 ? 0 : bx;
-    int last = row[last_x];
+    if (tid == 0) {
+        for (int i = 1; i < nwarp; ++i)
+            if (seam_better(s_v[i], s_x[i], best, bx, p.leftright)) {
+                best = s_v[i];
+                bx = s_x[i];
+            }
+    }
+    return bx < 0 ? 0 : bx;
+}
+
+__global__ void __launch_bounds__(1024) k_vpath(DevP p)
+{
+    __shared__ float s_v[32];
+    __shared__ int s_x[32];
+    int x = last_row_argmin(p, s_v, s_x);
+    if (threadIdx.x != 0) return;
     for (int y = p.h - 1; y >= 0; --y) {
-        p.vpath[y] = last;
-        p.vpath_x[y] = last_x;
+        p.vpath_x[y] = x;
         if (y > 0) {
-            const int *cur = p.raw + (size_t) y * p.raw_stride;
-            const int *up = cur - p.raw_stride;
-            last = p.least[cur[last_x]];
-            const int x_lo = max(last_x - p.delta_x, 0), x_hi = min(last_x + p.delta_x, p.w - 1);
-            for (int x = x_lo; x <= x_hi; ++x)
-                if (up[x] == last) {
-                    last_x = x;
-                    break;
-                }
+            const int d = p.pdx[(size_t) y * p.pitch + x];
+            if (d == B200C_PDX_NONE) {
+                atomicOr(p.err, 2);
+            } else {
+                x = min(max(x + d, 0), p.w - 1);
+            }
         }
     }
 }
 
-// K4 -- A.7 carve: mark the seam in the visibility map and shift the row's index table left by one past
-// the seam.  One CTA per row; p.w is the width AFTER the carve.  Loads of a chunk are parked in registers
-// before the barrier, so the in-place shift never reads a slot another thread already overwrote.
+// K4 -- A.7 carve (lqr_carver_update_vsmap + lqr_carver_carve): mark the seam pixel in the visibility map and
+// close the gap at x = s in the row's index table AND in the compact maps (en, m, rig shift left by one; pdx
+// shifts and is re-expressed so that it still names the same parent pixel: a parent right of the upper row's
+// seam moved one column left, a parent ON that seam is gone).  One CTA per row; p.w is the width AFTER the
+// carve.  Loads of a chunk are parked in registers before the barrier, so the in-place shift never reads a
+// slot another thread already overwrote.
 #define B200C_CARVE_THREADS 256
-#define B200C_CARVE_ITEMS 8
+#define B200C_CARVE_ITEMS 4
 __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP p, int vs_value)
 {
     const int y = blockIdx.x;
-    int *row = p.raw + (size_t) y * p.raw_stride;
-    const int vx = p.vpath_x[y];
-    if (threadIdx.x == 0) p.vs[p.vpath[y]] = vs_value;
-    for (int base = vx; base < p.w; base += B200C_CARVE_THREADS * B200C_CARVE_ITEMS) {
-        int v[B200C_CARVE_ITEMS];
+    const size_t o = (size_t) y * p.pitch;
+    int *raw = p.raw + (size_t) y * p.raw_stride;
+    float *en = p.en + o, *m = p.m + o, *rig = p.rig ? p.rig + o : nullptr;
+    int8_t *pdx = p.pdx + o;
+    const int s = p.vpath_x[y];
+    const int sp = y > 0 ? p.vpath_x[y - 1] : INT_MIN;
+    if (threadIdx.x == 0) p.vs[raw[s]] = vs_value; // read before the first barrier, i.e. before any store
+    const int start = max(s - p.delta_x - 1, 0);   // cells left of the seam stay put but may see their parent move
+    for (int base = start; base < p.w; base += B200C_CARVE_THREADS * B200C_CARVE_ITEMS) {
+        int vr[B200C_CARVE_ITEMS], vd[B200C_CARVE_ITEMS];
+        float ve[B200C_CARVE_ITEMS], vm[B200C_CARVE_ITEMS], vg[B200C_CARVE_ITEMS];
 #pragma unroll
         for (int i = 0; i < B200C_CARVE_ITEMS; ++i) {
-            const int x = base + i * B200C_CARVE_THREADS + threadIdx.x;
-            v[i] = (x < p.w) ? row[x + 1] : 0;
+            const int xn = base + i * B200C_CARVE_THREADS + threadIdx.x; // new column
+            const int xo = xn + (xn >= s);                               // the column it had before
+            vd[i] = B200C_PDX_NONE;
+            if (xn < p.w) {
+                if (xn >= s) {
+                    vr[i] = raw[xo];
+                    ve[i] = en[xo];
+                    vm[i] = m[xo];
+                    if (rig) vg[i] = rig[xo];
+                }
+                if (y > 0) {
+                    const int d = pdx[xo];
+                    const int xp = xo + d; // old column of the parent in the upper row
+                    if (d != B200C_PDX_NONE && xp != sp) vd[i] = (xp - (xp > sp)) - xn;
+                }
+            }
         }
         __syncthreads();
 #pragma unroll
         for (int i = 0; i < B200C_CARVE_ITEMS; ++i) {
-            const int x = base + i * B200C_CARVE_THREADS + threadIdx.x;
-            if (x < p.w) row[x] = v[i];
+            const int xn = base + i * B200C_CARVE_THREADS + threadIdx.x;
+            if (xn < p.w) {
+                if (xn >= s) {
+                    raw[xn] = vr[i];
+                    en[xn] = ve[i];
+                    m[xn] = vm[i];
+                    if (rig) rig[xn] = vg[i];
+                }
+                if (y > 0) pdx[xn] = (int8_t) vd[i];
+            }
         }
     }
 }
@@ -351,6 +405,25 @@ __global__ void k_finish_vsmap(DevP p)
 {
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y < p.h) p.vs[p.raw[(size_t) y * p.raw_stride]] = p.w0;
+}
+
+// test hook: the compact maps scattered back to liblqr's physical layout (index = pixel id); what: 0 en, 1 m,
+// 2 least (pixel id of the parent, -1 when it has none / it is gone)
+__global__ void __launch_bounds__(256) k_export_physical(DevP p, int what, int *out)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= p.w || y >= p.h) return;
+    const int z = p.raw[(size_t) y * p.raw_stride + x];
+    const size_t o = (size_t) y * p.pitch + x;
+    if (what == 0) {
+        out[z] = __float_as_int(p.en[o]);
+    } else if (what == 1) {
+        out[z] = __float_as_int(p.m[o]);
+    } else {
+        const int d = p.pdx[o];
+        out[z] = (y > 0 && d != B200C_PDX_NONE) ? p.raw[(size_t) (y - 1) * p.raw_stride + x + d] : -1;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -551,7 +624,7 @@ __global__ void k_energy_export(DevP p, int transposed, float *out)
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int i = blockIdx.y;
     if (j >= p.w || i >= p.h) return;
-    const float v = p.en[p.raw[(size_t) i * p.raw_stride + j]];
+    const float v = p.en[(size_t) i * p.pitch + j];
     out[transposed ? (size_t) j * p.h + i : (size_t) i * p.w + j] = v;
 }
 

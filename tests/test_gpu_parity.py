@@ -28,22 +28,18 @@ def engine(pkg, product):
     return eng
 
 
-@pytest.fixture(params=["fast", "spec", "staged", "generic"])
+@pytest.fixture(params=["fast", "generic"])
 def kernel_mode(request):
-    """Every kernel set must match the oracle: "fast" (default: warp-specialised speculative band DP staged
-    and committed with TMA bulk copies, windowed backtrack, tiled full DP), "spec" (B200C_UPDATE=3: the same
-    band DP staged with cp.async gathers), "staged" (B200C_UPDATE=2: the cp.async-staged band DP that also serves rigidity),
-    and "generic" (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at carver creation."""
-    old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_UPDATE", "B200C_VPATH")}
-    os.environ["B200C_VPATH"] = "3" if request.param == "fast" else "2"
+    """Every kernel set must match the oracle: "fast" (default: trapezoid-tiled band DP staged with TMA bulk
+    copies, staged backtrack, cluster full DP) and "generic" (B200C_GENERIC=1: the single-CTA kernels everything
+    falls back to).  Read at carver creation."""
+    old = os.environ.get("B200C_GENERIC")
     os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
-    os.environ["B200C_UPDATE"] = {"staged": "2", "spec": "3"}.get(request.param, "4")
     yield request.param
-    for k, v in old.items():
-        if v is None:
-            os.environ.pop(k, None)
-        else:
-            os.environ[k] = v
+    if old is None:
+        os.environ.pop("B200C_GENERIC", None)
+    else:
+        os.environ["B200C_GENERIC"] = old
 
 
 def test_device_is_blackwell(engine):
