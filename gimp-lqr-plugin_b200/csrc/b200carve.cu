@@ -126,6 +126,8 @@ struct B200Carver {
     int8_t *pdx = nullptr;                       // compact parent offsets
     int pitch = 0;
     int *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
+    unsigned *nrg_pack = nullptr;
+    alignas(64) BdMaps maps;                  // TMA tensor maps over the compact arrays (band DP)
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
     long long *dbg_d = nullptr;               // role cycle counters (B200C_DBG=1)
@@ -208,6 +210,7 @@ DevP view(const B200Carver *c)
     p.vpath_x = c->vpath_x;
     p.nrg_xmin = c->nrg_xmin;
     p.nrg_xmax = c->nrg_xmax;
+    p.nrg_pack = c->nrg_pack;
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
@@ -251,6 +254,39 @@ int init_raw(B200Carver *c)
     return check_launch("k_init_raw");
 }
 
+// ---- TMA tensor maps over the compact arrays (band_dp.cuh): 2-D, tiled, boxes of BD_BW columns x box_rows rows
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(CUtensorMap *tm, void *base, bool bytes, int pitch, int rows, int box_rows)
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *f = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn) f;
+    });
+    if (!fn) return fail(B200C_ERROR, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t esz = bytes ? 1 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t) pitch, (cuuint64_t) rows};
+    cuuint64_t strides[1] = {(cuuint64_t) pitch * esz};
+    cuuint32_t box[2] = {BD_BW, (cuuint32_t) box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(tm, bytes ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides,
+                          box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char msg[96];
+        snprintf(msg, sizeof msg, "cuTensorMapEncodeTiled failed (CUresult %d)", (int) r);
+        return fail(B200C_ERROR, msg);
+    }
+    return B200C_OK;
+}
+
 // The compact maps (DevP): en for every carver that computes energy, m / pdx for an initialised one; sized by
 // the reference size, which only flatten and transpose change.  rig is made on demand by build_maps.
 void free_maps(B200Carver *c)
@@ -265,12 +301,16 @@ void free_maps(B200Carver *c)
 int alloc_maps(B200Carver *c)
 {
     free_maps(c);
-    c->pitch = (c->w_start + 15) / 16 * 16;
+    c->pitch = (c->w_start + 4 + 15) / 16 * 16; // >= 4 columns right of the image: +inf sentinels of en / m
     const size_t n = (size_t) c->pitch * c->h_start + 64; // slack: aligned windows may end past the last row
     if (c->nrg_active) B_TRY(dalloc(c, &c->en, n, true));
     if (c->active) {
         B_TRY(dalloc(c, &c->m, n, true));
         B_TRY(dalloc(c, &c->pdx, n, true));
+        B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, BD_K + 1));
+        B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, BD_K));
+        B_TRY(encode_map(&c->maps.pdx, c->pdx, true, c->pitch, c->h_start, BD_K));
+        c->maps.rig = c->maps.en;
     }
     return B200C_OK;
 }
@@ -288,7 +328,7 @@ int init_energy_related(B200Carver *c)
 int build_emap(B200Carver *c)
 {
     if (c->nrg_uptodate) return B200C_OK;
-    dim3 grid((c->w + 255) / 256, c->h);
+    dim3 grid((c->pitch + 255) / 256, c->h);
     StageScope sc("energy_full", c->stream);
     k_energy_full<<<grid, 256, 0, c->stream>>>(view(c));
     B_TRY(check_launch("k_energy_full"));
@@ -307,14 +347,107 @@ int raise_smem_limits()
             cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
             if (e != cudaSuccess && err == cudaSuccess) err = e;
         };
-        (void) set;
+        set((const void *) k_seam_path, sp_smem_bytes());
+        set((const void *) k_band_dp<0, false, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<0, false, false>, mf_smem_bytes(0, false));
+        set((const void *) k_band_dp<0, false, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<0, false, true>, mf_smem_bytes(0, false));
+        set((const void *) k_band_dp<0, true, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<0, true, false>, mf_smem_bytes(0, true));
+        set((const void *) k_band_dp<0, true, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<0, true, true>, mf_smem_bytes(0, true));
+        set((const void *) k_band_dp<1, false, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<1, false, false>, mf_smem_bytes(1, false));
+        set((const void *) k_band_dp<1, false, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<1, false, true>, mf_smem_bytes(1, false));
+        set((const void *) k_band_dp<1, true, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<1, true, false>, mf_smem_bytes(1, true));
+        set((const void *) k_band_dp<1, true, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<1, true, true>, mf_smem_bytes(1, true));
+        set((const void *) k_band_dp<2, false, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<2, false, false>, mf_smem_bytes(2, false));
+        set((const void *) k_band_dp<2, false, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<2, false, true>, mf_smem_bytes(2, false));
+        set((const void *) k_band_dp<2, true, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<2, true, false>, mf_smem_bytes(2, true));
+        set((const void *) k_band_dp<2, true, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<2, true, true>, mf_smem_bytes(2, true));
+        set((const void *) k_band_dp<3, false, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<3, false, false>, mf_smem_bytes(3, false));
+        set((const void *) k_band_dp<3, false, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<3, false, true>, mf_smem_bytes(3, false));
+        set((const void *) k_band_dp<3, true, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<3, true, false>, mf_smem_bytes(3, true));
+        set((const void *) k_band_dp<3, true, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<3, true, true>, mf_smem_bytes(3, true));
+        set((const void *) k_band_dp<4, false, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<4, false, false>, mf_smem_bytes(4, false));
+        set((const void *) k_band_dp<4, false, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<4, false, true>, mf_smem_bytes(4, false));
+        set((const void *) k_band_dp<4, true, false>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<4, true, false>, mf_smem_bytes(4, true));
+        set((const void *) k_band_dp<4, true, true>, bd_smem_bytes());
+        set((const void *) k_mmap_full_strips<4, true, true>, mf_smem_bytes(4, true));
     });
     if (err != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", err);
     return B200C_OK;
 }
 
+template <int D>
+void launch_band_dp_d(B200Carver *c)
+{
+    const DevP p = view(c);
+    const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
+    const size_t sm = bd_smem_bytes();
+    if (rig && lr) k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    else if (rig) k_band_dp<D, true, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    else if (lr) k_band_dp<D, false, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    else k_band_dp<D, false, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+}
+
+void launch_band_dp(B200Carver *c)
+{
+    switch (c->delta_x) {
+        case 0: launch_band_dp_d<0>(c); break;
+        case 1: launch_band_dp_d<1>(c); break;
+        case 2: launch_band_dp_d<2>(c); break;
+        case 3: launch_band_dp_d<3>(c); break;
+        default: launch_band_dp_d<4>(c); break;
+    }
+}
+
+template <int D>
+void launch_mmap_full_d(B200Carver *c, int grid, int y0, int rows)
+{
+    const DevP p = view(c);
+    const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
+    const size_t sm = mf_smem_bytes(D, rig);
+    if (rig && lr) k_mmap_full_strips<D, true, true><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
+    else if (rig) k_mmap_full_strips<D, true, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
+    else if (lr) k_mmap_full_strips<D, false, true><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
+    else k_mmap_full_strips<D, false, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
+}
+
 int build_mmap(B200Carver *c)
 {
+    if (fast_path(c) && c->delta_x <= 4) {
+        B_TRY(raise_smem_limits());
+        const int R = mf_rows(c->delta_x), S = 128 - 2 * mf_hk(c->delta_x);
+        const int nstrips = (c->w + 4 + S - 1) / S;
+        const int grid = (nstrips + MF_WARPS - 1) / MF_WARPS;
+        StageScope sc("mmap_full", c->stream, (c->h + R - 1) / R);
+        for (int y0 = 0; y0 < c->h; y0 += R) {
+            const int rows = c->h - y0 < R ? c->h - y0 : R;
+            switch (c->delta_x) {
+                case 0: launch_mmap_full_d<0>(c, grid, y0, rows); break;
+                case 1: launch_mmap_full_d<1>(c, grid, y0, rows); break;
+                case 2: launch_mmap_full_d<2>(c, grid, y0, rows); break;
+                case 3: launch_mmap_full_d<3>(c, grid, y0, rows); break;
+                default: launch_mmap_full_d<4>(c, grid, y0, rows); break;
+            }
+        }
+        return check_launch("k_mmap_full_strips");
+    }
     StageScope sc("mmap_full", c->stream);
     k_mmap_full<<<1, 1024, 0, c->stream>>>(view(c));
     return check_launch("k_mmap_full");
@@ -373,7 +506,10 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (fast) B_TRY(raise_smem_limits());
     {
         StageScope sc("vpath", s);
-        k_vpath<<<1, 1024, 0, s>>>(view(c));
+        if (fast)
+            k_seam_path<<<1, SP_THREADS, sp_smem_bytes(), s>>>(view(c));
+        else
+            k_vpath<<<1, 1024, 0, s>>>(view(c));
         B_TRY(check_launch("k_vpath"));
     }
     const int vs_value = l + c->max_level - 1;
@@ -397,7 +533,10 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             B_TRY(build_mmap(c));
         } else {
             StageScope sc("mmap_update", s);
-            k_mmap_update<<<1, 512, 0, s>>>(view(c));
+            if (fast && c->delta_x <= 4 && c->h <= BD_HMAX)
+                launch_band_dp(c);
+            else
+                k_mmap_update<<<1, 512, 0, s>>>(view(c));
             B_TRY(check_launch("k_mmap_update"));
         }
     } else {
@@ -412,8 +551,9 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
 int gather_rig(B200Carver *c)
 {
     dfree(c, c->rig);
-    if (c->rigidity == 0.f || !c->rigmask) return B200C_OK;
+    if (c->rigidity == 0.f) return B200C_OK; // without a mask the factor is 1 everywhere
     B_TRY(dalloc(c, &c->rig, (size_t) c->pitch * c->h_start + 64, true));
+    B_TRY(encode_map(&c->maps.rig, c->rig, false, c->pitch, c->h_start, BD_K));
     dim3 grid((c->w + 255) / 256, c->h);
     StageScope sc("gather_rig", c->stream);
     k_gather_rig<<<grid, 256, 0, c->stream>>>(view(c));
@@ -572,9 +712,13 @@ int transpose(B200Carver *c)
         dfree(c, c->vpath_x);
         dfree(c, c->nrg_xmin);
         dfree(c, c->nrg_xmax);
+    dfree(c, c->nrg_pack);
+        dfree(c, c->nrg_pack);
         B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
+        B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
         for (int x = -c->delta_x; x <= c->delta_x; ++x) {
             float &v = c->rigmap_h[x + c->delta_x];
             v = v * c->w0 / c->h0;
@@ -626,6 +770,7 @@ B200Carver *carver_new_common(int width, int height, int channels)
     {
         const char *g = getenv("B200C_GENERIC");
         c->generic = g && atoi(g) != 0;
+
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
     if (g_use_ext_stream) {
@@ -740,6 +885,7 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->vpath_x);
     dfree(c, c->nrg_xmin);
     dfree(c, c->nrg_xmax);
+    dfree(c, c->nrg_pack);
     dfree(c, c->err_d);
     if (c->cells_d) {
         unsigned long long n = 0;
@@ -779,6 +925,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));

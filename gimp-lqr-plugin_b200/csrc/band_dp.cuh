@@ -1,1 +1,470 @@
+// band_dp.cuh -- K2b, the incremental m-map DP after one carve (liblqr lqr_carver_update_mmap)
+// on the compact maps: one CTA, trapezoid-tiled over warps, rows staged as 2-D TMA tiles.
+//
+// The update is a row-serial chain (row y needs row y-1), so the design minimises the latency of one row:
+//
+//   * The rows are cut into CHUNKS of 8 rows.  A chunk works on one column WINDOW starting at llo (16-cell aligned)
+//     that contains every cell liblqr's self-trimming band could touch in those rows: the hull of the cells that
+//     changed in the last finished row, grown by delta_x per row, merged with the energy bands of the rows in
+//     between.  Every cell of the window's evaluation range [elo, ehi] is evaluated on every row of the chunk with
+//     liblqr's keep-old rule.  Evaluating MORE cells than liblqr's band is exact: a cell whose parents, energy
+//     and parent candidates did not change re-evaluates to "keep" (DESIGN.md section 5).
+//   * COMPUTE warps own 128-column segments of the window, 4 consecutive cells per lane, all state in registers.
+//     Inside a chunk a warp never talks to another warp: a row step is two shuffles (the neighbours' edge cells)
+//     plus 4 cells of 3-input min / add / keep-test per lane.  Neighbouring segments overlap by 2*8*delta_x
+//     columns; the cells a warp computes in that overlap go stale by delta_x columns per row (their parents belong
+//     to the neighbour) and are simply not stored -- each column of the window is stored by exactly one warp, the
+//     one in whose interior it lies.  Only at a chunk boundary do the warps meet: the last row is handed over
+//     through shared memory and one named barrier.  The first three segments run on three different SM
+//     sub-partitions (warps 1,2,3); sub-partition 0 belongs to the producer.
+//   * One PRODUCER warp plans the windows of up to 3 chunks ahead (the band cannot outrun delta_x per row, so the
+//     hull known now bounds it) and fetches them with the TMA as 2-D tiles of 128 columns x 8 rows (9 for m: the
+//     row above the chunk) -- cp.async.bulk.tensor.2d from tensor maps over the compact m / en / pdx [/ rig]
+//     arrays, completion on one mbarrier per chunk -- into a ring of box slots in shared memory.  Results go
+//     straight back to HBM with vector stores (fire and forget; nothing waits for them).
+//
+// If a window ever outgrows 12 segments the kernel finishes the remaining rows with the exact generic row loop.
 #pragma once
+#include <cuda.h>
+
+#include "carver_kernels.cuh"
+
+namespace b200c {
+
+#define BD_NCW 12                 // compute warps = max segments of a window
+#define BD_NWARPS 16              // warp 0 producer, warps 4/8/12 idle: sub-partition 0 is the producer's alone
+#define BD_THREADS (BD_NWARPS * 32)
+#define BD_SYNC_THREADS ((BD_NCW + 1) * 32)
+#define BD_K 8                    // rows per chunk = height of a TMA box
+#define BD_BW 128                 // columns per TMA box
+#define BD_LA 3                   // chunks planned ahead, at most
+#define BD_NRING 8                // descriptor / mbarrier ring
+#define BD_HMAX 8192              // rows whose energy bands fit the shared-memory table
+#define BD_HANDW (BD_NCW * 128)
+#define BD_BOX_M ((BD_K + 1) * BD_BW * 4)
+#define BD_BOX_E (BD_K * BD_BW * 4)
+#define BD_BOX_P (BD_K * BD_BW)
+#define BD_RING_BYTES 175104      // 18 slots without, 12 slots with the rigidity-mask box
+
+template <bool RIG>
+struct BdSlot {
+    static constexpr int off_e = BD_BOX_M;
+    static constexpr int off_g = BD_BOX_M + BD_BOX_E;
+    static constexpr int off_p = BD_BOX_M + BD_BOX_E + (RIG ? BD_BOX_E : 0);
+    static constexpr int bytes = off_p + BD_BOX_P;
+    static constexpr int nslot = BD_RING_BYTES / bytes;
+};
+
+struct BdDesc {
+    int y0, rows, llo, nb, elo, ehi, nseg, slot0;
+};
+
+static constexpr size_t bd_smem_bytes()
+{
+    return (size_t) BD_RING_BYTES + (size_t) BD_HMAX * 4 + 2 * BD_HANDW * 4 + BD_NRING * sizeof(BdDesc) + 256 + 64 + 64 +
+           64 * 4 + 128;
+}
+
+__device__ __forceinline__ unsigned bd_saddr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bd_mbar_init(void *mbar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bd_saddr(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bd_mbar_expect(void *mbar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bd_saddr(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bd_mbar_arrive(void *mbar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bd_saddr(mbar)) : "memory");
+}
+// bounded wait: a copy that never completes is a bug, not a reason to hang the GPU
+__device__ __forceinline__ bool bd_mbar_wait(void *mbar, unsigned parity)
+{
+    const unsigned a = bd_saddr(mbar);
+    for (int tries = 0; tries < (1 << 22); ++tries) {
+        unsigned ok;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+// global -> shared 2-D tile copy (TMA), completion counted in bytes on `mbar`; out-of-range elements arrive as 0
+__device__ __forceinline__ void bd_tma_load_2d(void *dst_smem, const CUtensorMap *tm, int c0, int c1, void *mbar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            bd_saddr(dst_smem)),
+        "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(bd_saddr(mbar))
+        : "memory");
+}
+__device__ __forceinline__ void bd_bar_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory"); }
+
+// ------------------------------------------------------------------------------------------- compute warps
+// One row of one lane: 4 cells.  v[] = row y-1 at columns x0-D .. x0+3+D.  Everything a single warp issues per row
+// is on the critical path of the whole update (one warp-instruction costs the ALU pipe 2 cycles), so the body is
+// kept to: one 3-input min (FMNMX3 for D == 1), the add, the keep test and the selects.
+// evm / tolv fold the lane's "evaluate" flag into the keep test: a lane outside the evaluation range gets evm = 0
+// (every parent byte compares equal) and tolv = +inf (every value is close), so it keeps all four cells.
+template <int D, bool RIG, bool LR>
+__device__ __forceinline__ void bd_cells(const float (&v)[4 + 2 * D], const float4 e4, const float4 o4, const float4 g4,
+                                         const float (&rmap)[2 * D + 1], unsigned pwo, unsigned evm, float tolv,
+                                         float (&val)[4], unsigned &pk)
+{
+    const float en[4] = {e4.x, e4.y, e4.z, e4.w};
+    const float mo[4] = {o4.x, o4.y, o4.z, o4.w};
+    const float rf[4] = {g4.x, g4.y, g4.z, g4.w};
+    float nm[4];
+    bool far[4];
+    pk = 0; // the four new parent offsets, one byte each
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float cand[2 * D + 1];
+#pragma unroll
+        for (int j = 0; j <= 2 * D; ++j) cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
+        float best = cand[0];
+#pragma unroll
+        for (int j = 1; j <= 2 * D; ++j) best = fminf(best, cand[j]);
+        // the scan "cand < best || (cand == best && leftright)" keeps the FIRST minimum, or the LAST when leftright;
+        // the offset goes straight into byte i of the packed word
+        unsigned b = ((unsigned) ((LR ? -D : D) & 0xff)) << (8 * i);
+#pragma unroll
+        for (int j = 1; j <= 2 * D; ++j) {
+            const int jj = LR ? j : 2 * D - j;
+            if (cand[jj] == best) b = ((unsigned) ((jj - D) & 0xff)) << (8 * i);
+        }
+        pk |= b;
+        nm[i] = __fadd_rn(en[i], best);
+        // liblqr: (double) |m_old - m_new| < 1e-5 keeps; tolv is the largest float below 1e-5.  (An unordered
+        // compare only happens on the +inf sentinel columns, where either outcome stores +inf.)
+        far[i] = fabsf(__fsub_rn(mo[i], nm[i])) > tolv;
+    }
+    const unsigned diff = (pk ^ pwo) & evm; // byte i == 0  <=>  cell i keeps its parent
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool take = ((diff >> (8 * i)) & 0xffu) != 0u || far[i];
+        val[i] = take ? nm[i] : mo[i];
+    }
+}
+
+template <int D, bool RIG, bool LR>
+__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand, const BdDesc *desc, int *hull,
+                                           unsigned long long *mbar, int seg, int lane)
+{
+    using SL = BdSlot<RIG>;
+    constexpr int HK = (BD_K * D + 3) & ~3; // columns a segment edge goes stale over one chunk
+    constexpr int S = 128 - 2 * HK;         // stride of the segments = width of an interior
+    const float inf = __int_as_float(0x7f800000);
+    const unsigned full = 0xffffffffu;
+    float rmap[2 * D + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
+    float mp[4] = {0.f, 0.f, 0.f, 0.f}; // row y-1 at this lane's cells
+    int hl_llo = 0, hl_end = 0;         // hand-over range of the previous chunk
+    long long t_wait = 0, t_bar = 0, t_rows = 0, t_all = p.dbg ? clock64() : 0;
+    int n_rows = 0;
+
+    for (int k = 0;; ++k) {
+        long long t0 = 0;
+        if (p.dbg) t0 = clock64();
+        if (!bd_mbar_wait(&mbar[k % BD_NRING], (unsigned) ((k / BD_NRING) & 1))) atomicOr(p.err, 4);
+        if (p.dbg) t_wait += clock64() - t0;
+        const BdDesc d = desc[k % BD_NRING];
+        if (d.rows == 0) break;
+        int *hull_k = hull + (k & 1) * (2 * BD_NCW);
+        const int lw = d.nb * BD_BW;
+        const int own_end = d.llo + min(lw, d.nseg * S + 2 * HK); // columns [llo, own_end) lie in some interior
+        if (seg < d.nseg) {
+            const int rows = d.rows;
+            const int x0 = d.llo + seg * S + 4 * lane;
+            const int c = min(x0 - d.llo, lw - 4);
+            const bool ev = x0 >= d.elo && x0 <= d.ehi; // the evaluation range is a whole number of lanes
+            const int ilo = seg == 0 ? 0 : HK, ihi = seg == d.nseg - 1 ? 128 : 128 - HK;
+            const bool interior = 4 * lane >= ilo && 4 * lane < ihi && x0 < own_end;
+            const bool st = interior && ev;
+            const bool leftb = x0 == 0; // columns < 0 do not exist; columns >= w hold +inf in the maps (sentinels)
+            const unsigned evm = ev ? 0xffffffffu : 0u;
+            const float tolv = ev ? __int_as_float(0x3727C5AC) : inf;
+
+            int slot = d.slot0 + (c >> 7);
+            if (slot >= SL::nslot) slot -= SL::nslot;
+            const unsigned char *sb = ring + (size_t) slot * SL::bytes;
+            const int cc = c & (BD_BW - 1);
+            const float *op = reinterpret_cast<const float *>(sb) + cc;               // m rows -1 .. 7
+            const float *ep = reinterpret_cast<const float *>(sb + SL::off_e) + cc;   // en rows 0 .. 7
+            const float *gq = reinterpret_cast<const float *>(sb + SL::off_g) + cc;   // rigidity mask rows (RIG)
+            const unsigned char *pp = sb + SL::off_p + cc;                            // pdx rows 0 .. 7
+
+            if (d.y0 > 0) {
+                const float4 v = (x0 >= hl_llo && x0 < hl_end)
+                                     ? *reinterpret_cast<const float4 *>(hand + ((k - 1) & 1) * BD_HANDW + (x0 - hl_llo))
+                                     : *reinterpret_cast<const float4 *>(op);
+                mp[0] = v.x, mp[1] = v.y, mp[2] = v.z, mp[3] = v.w;
+            }
+            // operands of the row about to be computed; the next row's are fetched before the chain of this one
+            // (the fetch past the last row reads the neighbouring box of the slot and is never used)
+            op += BD_BW;
+            float4 e4 = *reinterpret_cast<const float4 *>(ep);
+            float4 o4 = *reinterpret_cast<const float4 *>(op);
+            unsigned pw = *reinterpret_cast<const unsigned *>(pp);
+            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
+            unsigned chg = 0;
+            float val[4];
+            long long tr0 = 0;
+            if (p.dbg) tr0 = clock64();
+            unsigned go = (unsigned) d.y0 * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
+            int r = 0;
+            if (d.y0 == 0) { // row 0 of the image: m = en over the band (A.8)
+                val[0] = ev ? e4.x : o4.x, val[1] = ev ? e4.y : o4.y, val[2] = ev ? e4.z : o4.z, val[3] = ev ? e4.w : o4.w;
+                chg = ev ? ((e4.x != o4.x ? 1u : 0u) | (e4.y != o4.y ? 2u : 0u) | (e4.z != o4.z ? 4u : 0u) | (e4.w != o4.w ? 8u : 0u)) : 0u;
+                if (st && chg) *reinterpret_cast<float4 *>(p.m + go) = make_float4(val[0], val[1], val[2], val[3]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mp[i] = val[i];
+                ep += BD_BW, op += BD_BW, pp += BD_BW, gq += BD_BW, go += p.pitch;
+                e4 = *reinterpret_cast<const float4 *>(ep);
+                o4 = *reinterpret_cast<const float4 *>(op);
+                pw = *reinterpret_cast<const unsigned *>(pp);
+                if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
+                r = 1;
+            }
+            float4 co = o4;       // old values / parents of the row just computed (for the hull of its changes)
+            unsigned pwo = pw, pwn = pw;
+            for (; r < rows; ++r) {
+                const float4 ce = e4, cg = g4;
+                co = o4;
+                pwo = pw;
+                ep += BD_BW, op += BD_BW, pp += BD_BW, gq += BD_BW;
+                e4 = *reinterpret_cast<const float4 *>(ep);
+                o4 = *reinterpret_cast<const float4 *>(op);
+                pw = *reinterpret_cast<const unsigned *>(pp);
+                if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
+                float v[4 + 2 * D];
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    const float l = __shfl_up_sync(full, mp[4 - D + j], 1);
+                    v[j] = leftb ? inf : l;
+                    v[4 + D + j] = __shfl_down_sync(full, mp[j], 1);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[D + i] = mp[i];
+                bd_cells<D, RIG, LR>(v, ce, co, cg, rmap, pwo, evm, tolv, val, pwn);
+                if (st) { // a kept cell has bdx == its old parent, so the packed offsets are right for every cell
+                    *reinterpret_cast<float4 *>(p.m + go) = make_float4(val[0], val[1], val[2], val[3]);
+                    *reinterpret_cast<unsigned *>(p.pdx + go) = pwn;
+                }
+                go += p.pitch;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mp[i] = val[i];
+            }
+            if (rows > 1 || d.y0 > 0) { // cells of the last row whose value or parent changed
+                chg = (val[0] != co.x ? 1u : 0u) | (val[1] != co.y ? 2u : 0u) | (val[2] != co.z ? 4u : 0u) | (val[3] != co.w ? 8u : 0u);
+                const unsigned df = pwn ^ pwo;
+                chg |= ((df & 0xffu) ? 1u : 0u) | ((df & 0xff00u) ? 2u : 0u) | ((df & 0xff0000u) ? 4u : 0u) | ((df & 0xff000000u) ? 8u : 0u);
+            }
+            if (p.dbg) {
+                t_rows += clock64() - tr0;
+                n_rows += rows;
+            }
+            // hand the last row over and publish the hull of its changed cells
+            if (interior) *reinterpret_cast<float4 *>(hand + (k & 1) * BD_HANDW + (x0 - d.llo)) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+            int lo = INT_MAX, hi = INT_MIN;
+            if (st && chg) {
+                lo = x0 + __ffs(chg) - 1;
+                hi = x0 + 31 - __clz(chg);
+            }
+            lo = __reduce_min_sync(full, lo);
+            hi = __reduce_max_sync(full, hi);
+            if (lane == 0) {
+                hull_k[2 * seg] = lo;
+                hull_k[2 * seg + 1] = hi;
+            }
+        } else if (lane == 0) {
+            hull_k[2 * seg] = INT_MAX;
+            hull_k[2 * seg + 1] = INT_MIN;
+        }
+        long long t1 = 0;
+        if (p.dbg) t1 = clock64();
+        bd_bar_chunk();
+        if (p.dbg) t_bar += clock64() - t1;
+        hl_llo = d.llo;
+        hl_end = own_end;
+    }
+    if (p.dbg && lane == 0) {
+        atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 0 : 2], (unsigned long long) t_wait);
+        atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 1 : 3], (unsigned long long) t_bar);
+        if (seg == 0) {
+            atomicAdd((unsigned long long *) &p.dbg[5], (unsigned long long) t_rows);
+            atomicAdd((unsigned long long *) &p.dbg[6], (unsigned long long) (clock64() - t_all));
+            atomicAdd((unsigned long long *) &p.dbg[7], (unsigned long long) n_rows);
+        } else {
+            atomicAdd((unsigned long long *) &p.dbg[8], (unsigned long long) n_rows);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- producer warp
+struct BdMaps {
+    CUtensorMap m, en, pdx, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x 9 (m) / 128 x 8
+};
+
+template <int D, bool RIG>
+__device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, unsigned char *ring, const unsigned *nrg,
+                                            BdDesc *desc, const int *hull, unsigned long long *mbar, volatile int *misc,
+                                            int lane)
+{
+    using SL = BdSlot<RIG>;
+    constexpr int HK = (BD_K * D + 3) & ~3;
+    constexpr int S = 128 - 2 * HK;
+    const unsigned full = 0xffffffffu;
+    int ya = 0;                                  // first row of the next chunk to plan
+    int hlo = INT_MAX, hhi = INT_MIN, yl = -1;   // hull of the changed cells of row yl
+    bool ended = false;
+    int kp = 0;                                  // next chunk to plan
+    int slot_next = 0, slots_free = SL::nslot;
+    unsigned long long cells = 0;
+    long long t_plan = 0;
+
+    // plans chunk kp and issues its tiles; false when it has to wait for ring space
+    auto plan_issue = [&]() -> bool {
+        const long long tp0 = p.dbg ? clock64() : 0;
+        BdDesc *dd = desc + (kp % BD_NRING);
+        void *mb = &mbar[kp % BD_NRING];
+        int end_y = -1;
+        int elo = 0, ehi = -1, llo = 0, nb = 0, nseg = 0, rows = 0;
+        if (ya >= p.h) {
+            end_y = p.h;
+        } else {
+            rows = min(BD_K, p.h - ya);
+            const int yb = ya + rows - 1;
+            int nlo = INT_MAX, nhi = INT_MIN; // extremes of the energy bands of rows (yl, yb]
+            for (int j = yl + 1 + lane; j <= yb; j += 32) {
+                const unsigned pk = nrg[j];
+                const int a = (int) (pk & 0xffffffu);
+                nlo = min(nlo, a);
+                nhi = max(nhi, a + (int) (pk >> 24) - 1);
+            }
+            nlo = __reduce_min_sync(full, nlo);
+            nhi = __reduce_max_sync(full, nhi);
+            const int g = (yb - yl) * D; // the band grows by at most delta_x per row past the hull / energy bands
+            elo = max(min(hlo, nlo) - g, 0) & ~3;       // whole lanes: evaluating more cells is exact, and
+            ehi = min(max(hhi, nhi) + g, p.w - 1) | 3;  // cells right of w-1 are +inf sentinels nobody reads
+            llo = max(min(elo, p.w - 1) - D, 0) & ~15;
+            const int need = max(max(ehi, elo) + D + 1 - llo, 16);
+            nseg = need <= 128 ? 1 : (need - 2 * HK + S - 1) / S;
+            nb = (need + BD_BW - 1) / BD_BW;
+            if (nseg > BD_NCW || nb > SL::nslot) end_y = ya; // too wide: the exact generic loop takes over at row ya
+        }
+        if (end_y < 0 && nb > slots_free) return false;
+        if (end_y >= 0) {
+            if (lane == 0) {
+                dd->rows = 0;
+                dd->y0 = end_y;
+                bd_mbar_arrive(mb);
+            }
+            ended = true;
+        } else {
+            if (lane == 0) {
+                dd->y0 = ya;
+                dd->rows = rows;
+                dd->llo = llo;
+                dd->nb = nb;
+                dd->elo = elo;
+                dd->ehi = ehi;
+                dd->nseg = nseg;
+                dd->slot0 = slot_next;
+                bd_mbar_expect(mb, (unsigned) nb * (unsigned) (BD_BOX_M + BD_BOX_E + BD_BOX_P + (RIG ? BD_BOX_E : 0)));
+            }
+            __syncwarp();
+            if (lane < nb) {
+                int slot = slot_next + lane;
+                if (slot >= SL::nslot) slot -= SL::nslot;
+                unsigned char *sb = ring + (size_t) slot * SL::bytes;
+                const int cx = llo + lane * BD_BW;
+                bd_tma_load_2d(sb, &tm.m, cx, ya - 1, mb);
+                bd_tma_load_2d(sb + SL::off_e, &tm.en, cx, ya, mb);
+                if (RIG) bd_tma_load_2d(sb + SL::off_g, &tm.rig, cx, ya, mb);
+                bd_tma_load_2d(sb + SL::off_p, &tm.pdx, cx, ya, mb);
+            }
+            slot_next += nb;
+            if (slot_next >= SL::nslot) slot_next -= SL::nslot;
+            slots_free -= nb;
+            if (ehi >= elo) cells += (unsigned long long) (ehi - elo + 1) * rows;
+            ya += rows;
+        }
+        ++kp;
+        if (p.dbg) t_plan += clock64() - tp0;
+        return true;
+    };
+
+    for (int k = 0;; ++k) {
+        // chunk k must be planned by now, and up to BD_LA more while the ring has room
+        while (!ended && kp <= k + BD_LA)
+            if (!plan_issue()) break;
+        const BdDesc *dk = desc + (k % BD_NRING);
+        const int rows_k = dk->rows, y0_k = dk->y0, nb_k = dk->nb;
+        if (rows_k == 0) {
+            if (lane == 0) {
+                misc[0] = y0_k; // first row left to the generic loop (h: none)
+                misc[1] = hlo;
+                misc[2] = hhi;
+            }
+            break;
+        }
+        bd_bar_chunk(); // end of chunk k: its slots are free, the hull of its last row is known
+        slots_free += nb_k;
+        const int *hull_k = hull + (k & 1) * (2 * BD_NCW);
+        int lo = lane < BD_NCW ? hull_k[2 * lane] : INT_MAX;
+        int hi = lane < BD_NCW ? hull_k[2 * lane + 1] : INT_MIN;
+        hlo = __reduce_min_sync(full, lo);
+        hhi = __reduce_max_sync(full, hi);
+        yl = y0_k + rows_k - 1;
+    }
+    if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
+    if (p.dbg && lane == 0) {
+        atomicAdd((unsigned long long *) &p.dbg[4], (unsigned long long) kp);
+        atomicAdd((unsigned long long *) &p.dbg[9], (unsigned long long) t_plan);
+    }
+}
+
+template <int D, bool RIG, bool LR>
+__global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const __grid_constant__ BdMaps tm)
+{
+    extern __shared__ __align__(128) unsigned char bd_smem[];
+    unsigned char *ring = bd_smem;
+    unsigned *nrg = reinterpret_cast<unsigned *>(ring + BD_RING_BYTES);
+    float *hand = reinterpret_cast<float *>(nrg + BD_HMAX);
+    BdDesc *desc = reinterpret_cast<BdDesc *>(hand + 2 * BD_HANDW);
+    int *hull = reinterpret_cast<int *>(desc + BD_NRING);                         // [2][BD_NCW][2], 256 bytes reserved
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(hull + 64); // [BD_NRING]
+    volatile int *misc = reinterpret_cast<volatile int *>(mbar + BD_NRING);
+    int *s_red = const_cast<int *>(misc) + 16;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int y = tid; y < p.h; y += BD_THREADS) nrg[y] = p.nrg_pack[y];
+    if (tid == 0) {
+        for (int i = 0; i < BD_NRING; ++i) bd_mbar_init(&mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        misc[0] = p.h;
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane);
+    } else if (warp & 3) {
+        bd_compute<D, RIG, LR>(p, ring, hand, desc, hull, mbar, (warp >> 2) * 3 + (warp & 3) - 1, lane);
+    }
+    __syncthreads();
+    const int y_from = misc[0];
+    if (y_from < p.h) update_rows_generic(p, y_from, misc[1], misc[2], s_red);
+}
+
+} // namespace b200c

@@ -51,6 +51,7 @@ struct DevP {
     const float *rigmask;
     const float *rigmap; // centred: rigmap[dx], dx in [-delta_x, delta_x]
     int *vpath_x, *nrg_xmin, *nrg_xmax;
+    unsigned *nrg_pack; // per row: nrg_xmin | (nrg_xmax - nrg_xmin + 1) << 24, for the band DP's window planner
     unsigned long long *cells; // running count of band cells evaluated by the incremental DP
     long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
     int *err;          // device error word: bit 0 band left its staged window, bit 1 backtrack met a dead parent, bit 2 bulk copy timed out
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(256) k_gather_rig(DevP p)
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= p.w || y >= p.h) return;
-    p.rig[(size_t) y * p.pitch + x] = p.rigmask[p.raw[(size_t) y * p.raw_stride + x]];
+    p.rig[(size_t) y * p.pitch + x] = p.rigmask ? p.rigmask[p.raw[(size_t) y * p.raw_stride + x]] : 1.f;
 }
 
 // K1 -- A.3 full energy map (lqr_carver_build_emap): one thread per visible pixel.
@@ -172,8 +173,10 @@ __global__ void __launch_bounds__(256) k_energy_full(DevP p)
 {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= p.w || y >= p.h) return;
-    p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
+    if (x >= p.pitch || y >= p.h) return;
+    // columns right of the image hold +inf in en and m: a sentinel that never wins a minimum, so the DP kernels
+    // need no right-border case
+    p.en[(size_t) y * p.pitch + x] = x < p.w ? energy_at(p, x, y) : __int_as_float(0x7f800000);
 }
 
 // K1b -- A.8 energy band after a carve (lqr_carver_update_emap): one warp per row derives the row's
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(256) k_energy_band(DevP p)
     if (lane == 0) {
         p.nrg_xmin[y] = xmin;
         p.nrg_xmax[y] = xmax;
+        p.nrg_pack[y] = ((unsigned) xmin & 0xffffffu) | ((unsigned) max(xmax - xmin + 1, 0) << 24);
     }
     for (int x = xmin + lane; x <= xmax; x += 32) p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
 }
@@ -206,7 +210,7 @@ __global__ void __launch_bounds__(256) k_energy_band(DevP p)
 // cluster kernel of mmap_full_cluster.cuh is the fast path.
 __global__ void __launch_bounds__(1024) k_mmap_full(DevP p)
 {
-    for (int x = threadIdx.x; x < p.w; x += blockDim.x) p.m[x] = p.en[x];
+    for (int x = threadIdx.x; x < p.pitch; x += blockDim.x) p.m[x] = p.en[x]; // incl. the +inf sentinels
     __syncthreads();
     for (int y = 1; y < p.h; ++y) {
         const size_t o = (size_t) y * p.pitch;
@@ -217,6 +221,7 @@ __global__ void __launch_bounds__(1024) k_mmap_full(DevP p)
             p.pdx[o + x] = (int8_t) bdx;
             p.m[o + x] = __fadd_rn(p.en[o + x], best);
         }
+        for (int x = p.w + threadIdx.x; x < p.pitch; x += blockDim.x) p.m[o + x] = __int_as_float(0x7f800000);
         __syncthreads();
     }
 }
@@ -398,6 +403,8 @@ __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP p, int vs_va
             }
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0) en[p.w] = m[p.w] = __int_as_float(0x7f800000); // the vacated column joins the sentinels
 }
 
 // A.7 finish_vsmap: the image is one pixel wide; the survivors get the largest level.
