@@ -127,6 +127,8 @@ struct B200Carver {
     int pitch = 0;
     int *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
     unsigned *nrg_pack = nullptr;
+    int4 *fix_d = nullptr;                    // band-DP chunk table for k_fix_parents (+ its count)
+    int *fixn_d = nullptr;
     alignas(64) BdMaps maps;                  // TMA tensor maps over the compact arrays (band DP)
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
@@ -211,6 +213,8 @@ DevP view(const B200Carver *c)
     p.nrg_xmin = c->nrg_xmin;
     p.nrg_xmax = c->nrg_xmax;
     p.nrg_pack = c->nrg_pack;
+    p.fix = c->fix_d;
+    p.fixn = c->fixn_d;
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
@@ -399,10 +403,20 @@ void launch_band_dp_d(B200Carver *c)
     const DevP p = view(c);
     const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
     const size_t sm = bd_smem_bytes();
-    if (rig && lr) k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-    else if (rig) k_band_dp<D, true, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-    else if (lr) k_band_dp<D, false, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-    else k_band_dp<D, false, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    const int nfix = (c->h + BD_K - 1) / BD_K;
+    if (rig && lr) {
+        k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+        k_fix_parents<D, true, true><<<nfix, 256, 0, c->stream>>>(p);
+    } else if (rig) {
+        k_band_dp<D, true, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+        k_fix_parents<D, true, false><<<nfix, 256, 0, c->stream>>>(p);
+    } else if (lr) {
+        k_band_dp<D, false, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+        k_fix_parents<D, false, true><<<nfix, 256, 0, c->stream>>>(p);
+    } else {
+        k_band_dp<D, false, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+        k_fix_parents<D, false, false><<<nfix, 256, 0, c->stream>>>(p);
+    }
 }
 
 void launch_band_dp(B200Carver *c)
@@ -712,13 +726,13 @@ int transpose(B200Carver *c)
         dfree(c, c->vpath_x);
         dfree(c, c->nrg_xmin);
         dfree(c, c->nrg_xmax);
-    dfree(c, c->nrg_pack);
         dfree(c, c->nrg_pack);
+        dfree(c, c->fix_d);
         B_TRY(dalloc(c, &c->vpath_x, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
-    B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
+        B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / BD_K + 4, true));
         for (int x = -c->delta_x; x <= c->delta_x; ++x) {
             float &v = c->rigmap_h[x + c->delta_x];
             v = v * c->w0 / c->h0;
@@ -886,6 +900,8 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->nrg_xmin);
     dfree(c, c->nrg_xmax);
     dfree(c, c->nrg_pack);
+    dfree(c, c->fix_d);
+    dfree(c, c->fixn_d);
     dfree(c, c->err_d);
     if (c->cells_d) {
         unsigned long long n = 0;
@@ -926,6 +942,8 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
+    B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / BD_K + 4, true));
+    B_TRY(dalloc(c, &c->fixn_d, 1, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));

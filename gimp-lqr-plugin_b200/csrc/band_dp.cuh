@@ -32,7 +32,7 @@
 namespace b200c {
 
 #define BD_NCW 12                 // compute warps = max segments of a window
-#define BD_NWARPS 16              // warp 0 producer, warps 4/8/12 idle: sub-partition 0 is the producer's alone
+#define BD_NWARPS 13              // warp 0 producer, warp s+1 = segment s: the first four segments sit on four different sub-partitions
 #define BD_THREADS (BD_NWARPS * 32)
 #define BD_SYNC_THREADS ((BD_NCW + 1) * 32)
 #define BD_K 8                    // rows per chunk = height of a TMA box
@@ -57,6 +57,9 @@ struct BdSlot {
 
 struct BdDesc {
     int y0, rows, llo, nb, elo, ehi, nseg, slot0;
+    int ropen;    // the fetched columns reach the +inf sentinels right of the image: the right edge does not go stale
+    int hlo, hhi; // columns [hlo, hhi) are handed over to the next chunk (the union of the interiors)
+    int pad;
 };
 
 static constexpr size_t bd_smem_bytes()
@@ -109,50 +112,28 @@ __device__ __forceinline__ void bd_tma_load_2d(void *dst_smem, const CUtensorMap
 __device__ __forceinline__ void bd_bar_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory"); }
 
 // ------------------------------------------------------------------------------------------- compute warps
-// One row of one lane: 4 cells.  v[] = row y-1 at columns x0-D .. x0+3+D.  Everything a single warp issues per row
-// is on the critical path of the whole update (one warp-instruction costs the ALU pipe 2 cycles), so the body is
-// kept to: one 3-input min (FMNMX3 for D == 1), the add, the keep test and the selects.
-// evm / tolv fold the lane's "evaluate" flag into the keep test: a lane outside the evaluation range gets evm = 0
-// (every parent byte compares equal) and tolv = +inf (every value is close), so it keeps all four cells.
-template <int D, bool RIG, bool LR>
-__device__ __forceinline__ void bd_cells(const float (&v)[4 + 2 * D], const float4 e4, const float4 o4, const float4 g4,
-                                         const float (&rmap)[2 * D + 1], unsigned pwo, unsigned evm, float tolv,
-                                         float (&val)[4], unsigned &pk)
+// Everything a single warp issues per row is on the critical path of the whole update (one warp-instruction costs
+// the ALU pipe 2 cycles), so the row body carries only what the NEXT row needs: the new cumulative values.
+//
+//   nm = en + min(parents);  d = m_old - nm
+//   d == 0            -> nothing to decide (nm is m_old)
+//   |d| > tol         -> liblqr stores nm
+//   0 < |d| <= tol    -> "near": liblqr keeps m_old if the parent is unchanged, else stores nm.  Only this case needs
+//                        the arg-min and the stored parent; it is rare (an ulp-sized drift of a kept cell), so it
+//                        is a warp-uniform slow path.
+// The new parent offsets are not needed by the chain at all (the next row reads values, not parents): they are
+// recomputed from the final values by k_fix_parents, in parallel, after this kernel.
+template <int D, bool LR>
+__device__ __forceinline__ int bd_argmin(const float (&cand)[2 * D + 1], float best)
 {
-    const float en[4] = {e4.x, e4.y, e4.z, e4.w};
-    const float mo[4] = {o4.x, o4.y, o4.z, o4.w};
-    const float rf[4] = {g4.x, g4.y, g4.z, g4.w};
-    float nm[4];
-    bool far[4];
-    pk = 0; // the four new parent offsets, one byte each
+    // the scan "cand < best || (cand == best && leftright)" keeps the FIRST minimum, or the LAST when leftright
+    int bdx = LR ? -D : D;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float cand[2 * D + 1];
-#pragma unroll
-        for (int j = 0; j <= 2 * D; ++j) cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
-        float best = cand[0];
-#pragma unroll
-        for (int j = 1; j <= 2 * D; ++j) best = fminf(best, cand[j]);
-        // the scan "cand < best || (cand == best && leftright)" keeps the FIRST minimum, or the LAST when leftright;
-        // the offset goes straight into byte i of the packed word
-        unsigned b = ((unsigned) ((LR ? -D : D) & 0xff)) << (8 * i);
-#pragma unroll
-        for (int j = 1; j <= 2 * D; ++j) {
-            const int jj = LR ? j : 2 * D - j;
-            if (cand[jj] == best) b = ((unsigned) ((jj - D) & 0xff)) << (8 * i);
-        }
-        pk |= b;
-        nm[i] = __fadd_rn(en[i], best);
-        // liblqr: (double) |m_old - m_new| < 1e-5 keeps; tolv is the largest float below 1e-5.  (An unordered
-        // compare only happens on the +inf sentinel columns, where either outcome stores +inf.)
-        far[i] = fabsf(__fsub_rn(mo[i], nm[i])) > tolv;
+    for (int j = 1; j <= 2 * D; ++j) {
+        const int jj = LR ? j : 2 * D - j;
+        if (cand[jj] == best) bdx = jj - D;
     }
-    const unsigned diff = (pk ^ pwo) & evm; // byte i == 0  <=>  cell i keeps its parent
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const bool take = ((diff >> (8 * i)) & 0xffu) != 0u || far[i];
-        val[i] = take ? nm[i] : mo[i];
-    }
+    return bdx;
 }
 
 template <int D, bool RIG, bool LR>
@@ -163,14 +144,15 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     constexpr int HK = (BD_K * D + 3) & ~3; // columns a segment edge goes stale over one chunk
     constexpr int S = 128 - 2 * HK;         // stride of the segments = width of an interior
     const float inf = __int_as_float(0x7f800000);
+    const float tol = __int_as_float(0x3727C5AC); // (double) |d| < 1e-5  <=>  |d| <= this float
     const unsigned full = 0xffffffffu;
     float rmap[2 * D + 1];
 #pragma unroll
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
     float mp[4] = {0.f, 0.f, 0.f, 0.f}; // row y-1 at this lane's cells
-    int hl_llo = 0, hl_end = 0;         // hand-over range of the previous chunk
+    int hl_lo = 0, hl_hi = 0;           // hand-over range of the previous chunk
     long long t_wait = 0, t_bar = 0, t_rows = 0, t_all = p.dbg ? clock64() : 0;
-    int n_rows = 0;
+    int n_rows = 0, n_slow = 0;
 
     for (int k = 0;; ++k) {
         long long t0 = 0;
@@ -181,18 +163,21 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
         if (d.rows == 0) break;
         int *hull_k = hull + (k & 1) * (2 * BD_NCW);
         const int lw = d.nb * BD_BW;
-        const int own_end = d.llo + min(lw, d.nseg * S + 2 * HK); // columns [llo, own_end) lie in some interior
         if (seg < d.nseg) {
             const int rows = d.rows;
             const int x0 = d.llo + seg * S + 4 * lane;
             const int c = min(x0 - d.llo, lw - 4);
-            const bool ev = x0 >= d.elo && x0 <= d.ehi; // the evaluation range is a whole number of lanes
-            const int ilo = seg == 0 ? 0 : HK, ihi = seg == d.nseg - 1 ? 128 : 128 - HK;
-            const bool interior = 4 * lane >= ilo && 4 * lane < ihi && x0 < own_end;
-            const bool st = interior && ev;
+            // a segment edge next to another segment -- or to columns that were not fetched -- goes stale; an edge
+            // at the image border (or inside the +inf sentinel columns) does not
+            const int ilo = (seg == 0 && d.llo == 0) ? 0 : HK;
+            const int ihi = (seg == d.nseg - 1 && d.ropen) ? 128 : 128 - HK;
+            const bool interior = 4 * lane >= ilo && 4 * lane < ihi && x0 < d.hhi; // hhi: see the producer
+#ifdef BD_DEBUG_STORE_ALL
+            const bool st = interior && x0 < p.pitch;
+#else
+            const bool st = interior && x0 >= d.elo && x0 <= d.ehi;
+#endif
             const bool leftb = x0 == 0; // columns < 0 do not exist; columns >= w hold +inf in the maps (sentinels)
-            const unsigned evm = ev ? 0xffffffffu : 0u;
-            const float tolv = ev ? __int_as_float(0x3727C5AC) : inf;
 
             int slot = d.slot0 + (c >> 7);
             if (slot >= SL::nslot) slot -= SL::nslot;
@@ -204,8 +189,8 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             const unsigned char *pp = sb + SL::off_p + cc;                            // pdx rows 0 .. 7
 
             if (d.y0 > 0) {
-                const float4 v = (x0 >= hl_llo && x0 < hl_end)
-                                     ? *reinterpret_cast<const float4 *>(hand + ((k - 1) & 1) * BD_HANDW + (x0 - hl_llo))
+                const float4 v = (x0 >= hl_lo && x0 < hl_hi)
+                                     ? *reinterpret_cast<const float4 *>(hand + ((k - 1) & 1) * BD_HANDW + (x0 - hl_lo))
                                      : *reinterpret_cast<const float4 *>(op);
                 mp[0] = v.x, mp[1] = v.y, mp[2] = v.z, mp[3] = v.w;
             }
@@ -214,38 +199,29 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             op += BD_BW;
             float4 e4 = *reinterpret_cast<const float4 *>(ep);
             float4 o4 = *reinterpret_cast<const float4 *>(op);
-            unsigned pw = *reinterpret_cast<const unsigned *>(pp);
             float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
-            unsigned chg = 0;
-            float val[4];
+            float4 co = o4;
             long long tr0 = 0;
             if (p.dbg) tr0 = clock64();
             unsigned go = (unsigned) d.y0 * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
             int r = 0;
-            if (d.y0 == 0) { // row 0 of the image: m = en over the band (A.8)
-                val[0] = ev ? e4.x : o4.x, val[1] = ev ? e4.y : o4.y, val[2] = ev ? e4.z : o4.z, val[3] = ev ? e4.w : o4.w;
-                chg = ev ? ((e4.x != o4.x ? 1u : 0u) | (e4.y != o4.y ? 2u : 0u) | (e4.z != o4.z ? 4u : 0u) | (e4.w != o4.w ? 8u : 0u)) : 0u;
-                if (st && chg) *reinterpret_cast<float4 *>(p.m + go) = make_float4(val[0], val[1], val[2], val[3]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i) mp[i] = val[i];
+            if (d.y0 == 0) { // row 0 of the image: m = en (A.8; true of every cell of the row, evaluated or not)
+                mp[0] = e4.x, mp[1] = e4.y, mp[2] = e4.z, mp[3] = e4.w;
+                if (st) *reinterpret_cast<float4 *>(p.m + go) = e4;
                 ep += BD_BW, op += BD_BW, pp += BD_BW, gq += BD_BW, go += p.pitch;
                 e4 = *reinterpret_cast<const float4 *>(ep);
                 o4 = *reinterpret_cast<const float4 *>(op);
-                pw = *reinterpret_cast<const unsigned *>(pp);
                 if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
                 r = 1;
             }
-            float4 co = o4;       // old values / parents of the row just computed (for the hull of its changes)
-            unsigned pwo = pw, pwn = pw;
             for (; r < rows; ++r) {
                 const float4 ce = e4, cg = g4;
                 co = o4;
-                pwo = pw;
+                const unsigned char *ppc = pp;
                 ep += BD_BW, op += BD_BW, pp += BD_BW, gq += BD_BW;
                 e4 = *reinterpret_cast<const float4 *>(ep);
                 o4 = *reinterpret_cast<const float4 *>(op);
-                pw = *reinterpret_cast<const unsigned *>(pp);
                 if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
                 float v[4 + 2 * D];
 #pragma unroll
@@ -256,28 +232,58 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[D + i] = mp[i];
-                bd_cells<D, RIG, LR>(v, ce, co, cg, rmap, pwo, evm, tolv, val, pwn);
-                if (st) { // a kept cell has bdx == its old parent, so the packed offsets are right for every cell
-                    *reinterpret_cast<float4 *>(p.m + go) = make_float4(val[0], val[1], val[2], val[3]);
-                    *reinterpret_cast<unsigned *>(p.pdx + go) = pwn;
-                }
-                go += p.pitch;
+                const float en[4] = {ce.x, ce.y, ce.z, ce.w};
+                const float mo[4] = {co.x, co.y, co.z, co.w};
+                const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
+                bool near = false;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mp[i] = val[i];
-            }
-            if (rows > 1 || d.y0 > 0) { // cells of the last row whose value or parent changed
-                chg = (val[0] != co.x ? 1u : 0u) | (val[1] != co.y ? 2u : 0u) | (val[2] != co.z ? 4u : 0u) | (val[3] != co.w ? 8u : 0u);
-                const unsigned df = pwn ^ pwo;
-                chg |= ((df & 0xffu) ? 1u : 0u) | ((df & 0xff00u) ? 2u : 0u) | ((df & 0xff0000u) ? 4u : 0u) | ((df & 0xff000000u) ? 8u : 0u);
+                for (int i = 0; i < 4; ++i) {
+                    float best = RIG ? __fadd_rn(v[i], __fmul_rn(rf[i], rmap[0])) : v[i];
+#pragma unroll
+                    for (int j = 1; j <= 2 * D; ++j)
+                        best = fminf(best, RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j]);
+                    mp[i] = __fadd_rn(en[i], best);
+                    const float df = __fsub_rn(mo[i], mp[i]);
+                    near |= df != 0.f && fabsf(df) <= tol;
+                }
+#ifdef BD_DEBUG_ALWAYS_SLOW
+                near = true;
+#endif
+                if (__any_sync(full, near)) { // rare: a kept cell's ulp-sized drift; needs the arg-min and the stored parent
+                    const unsigned pwo = *reinterpret_cast<const unsigned *>(ppc);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float df = __fsub_rn(mo[i], mp[i]);
+                        if (df != 0.f && fabsf(df) <= tol) {
+                            float cand[2 * D + 1];
+                            float best = inf;
+#pragma unroll
+                            for (int j = 0; j <= 2 * D; ++j) {
+                                cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
+                                best = fminf(best, cand[j]);
+                            }
+                            if ((int) (signed char) (pwo >> (8 * i)) == bd_argmin<D, LR>(cand, best)) mp[i] = mo[i];
+                        }
+                    }
+                    ++n_slow;
+                }
+                if (st) *reinterpret_cast<float4 *>(p.m + go) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+                go += p.pitch;
             }
             if (p.dbg) {
                 t_rows += clock64() - tr0;
                 n_rows += rows;
             }
-            // hand the last row over and publish the hull of its changed cells
-            if (interior) *reinterpret_cast<float4 *>(hand + (k & 1) * BD_HANDW + (x0 - d.llo)) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+            // hand the last row over and publish the hull of the cells whose VALUE changed in it (a changed parent
+            // alone does not matter to the next row)
+            if (interior) *reinterpret_cast<float4 *>(hand + (k & 1) * BD_HANDW + (x0 - d.hlo)) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+            unsigned chg = 0;
+            if (st && (rows > 1 || d.y0 > 0))
+                chg = (mp[0] != co.x ? 1u : 0u) | (mp[1] != co.y ? 2u : 0u) | (mp[2] != co.z ? 4u : 0u) | (mp[3] != co.w ? 8u : 0u);
+            else if (st) // the chunk was row 0 alone: compare with the old row 0
+                chg = 0xfu;
             int lo = INT_MAX, hi = INT_MIN;
-            if (st && chg) {
+            if (chg) {
                 lo = x0 + __ffs(chg) - 1;
                 hi = x0 + 31 - __clz(chg);
             }
@@ -295,8 +301,8 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
         if (p.dbg) t1 = clock64();
         bd_bar_chunk();
         if (p.dbg) t_bar += clock64() - t1;
-        hl_llo = d.llo;
-        hl_end = own_end;
+        hl_lo = d.hlo;
+        hl_hi = d.hhi;
     }
     if (p.dbg && lane == 0) {
         atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 0 : 2], (unsigned long long) t_wait);
@@ -305,6 +311,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             atomicAdd((unsigned long long *) &p.dbg[5], (unsigned long long) t_rows);
             atomicAdd((unsigned long long *) &p.dbg[6], (unsigned long long) (clock64() - t_all));
             atomicAdd((unsigned long long *) &p.dbg[7], (unsigned long long) n_rows);
+            atomicAdd((unsigned long long *) &p.dbg[10], (unsigned long long) n_slow);
         } else {
             atomicAdd((unsigned long long *) &p.dbg[8], (unsigned long long) n_rows);
         }
@@ -339,7 +346,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         BdDesc *dd = desc + (kp % BD_NRING);
         void *mb = &mbar[kp % BD_NRING];
         int end_y = -1;
-        int elo = 0, ehi = -1, llo = 0, nb = 0, nseg = 0, rows = 0;
+        int elo = 0, ehi = -1, llo = 0, nb = 0, nseg = 0, rows = 0, ropen = 0, lw = 0;
         if (ya >= p.h) {
             end_y = p.h;
         } else {
@@ -357,10 +364,15 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             const int g = (yb - yl) * D; // the band grows by at most delta_x per row past the hull / energy bands
             elo = max(min(hlo, nlo) - g, 0) & ~3;       // whole lanes: evaluating more cells is exact, and
             ehi = min(max(hhi, nhi) + g, p.w - 1) | 3;  // cells right of w-1 are +inf sentinels nobody reads
-            llo = max(min(elo, p.w - 1) - D, 0) & ~15;
-            const int need = max(max(ehi, elo) + D + 1 - llo, 16);
+            // the window reaches HK columns past the evaluation range on either side: its outer edges go stale like
+            // the edges between segments, unless they are the image border / the sentinel columns
+            const int wlim = min((p.w + 4 + 3) & ~3, p.pitch);
+            llo = max(min(elo, p.w - 1) - HK, 0) & ~15;
+            const int need = max(min(max(ehi, elo) + HK + 1, wlim) - llo, 16);
             nseg = need <= 128 ? 1 : (need - 2 * HK + S - 1) / S;
             nb = (need + BD_BW - 1) / BD_BW;
+            lw = nb * BD_BW;
+            ropen = llo + min(lw, (nseg - 1) * S + 128) >= wlim; // fetched AND covered by the last segment
             if (nseg > BD_NCW || nb > SL::nslot) end_y = ya; // too wide: the exact generic loop takes over at row ya
         }
         if (end_y < 0 && nb > slots_free) return false;
@@ -381,6 +393,11 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
                 dd->ehi = ehi;
                 dd->nseg = nseg;
                 dd->slot0 = slot_next;
+                dd->ropen = ropen;
+                dd->hlo = llo + (llo == 0 ? 0 : HK);
+                // the fetched columns end at llo + lw: unless that is past the image, the last HK of them go stale too
+                dd->hhi = llo + (ropen ? min(lw, (nseg - 1) * S + 128) : min(lw - HK, nseg * S + HK));
+                if (p.fix) p.fix[kp] = make_int4(ya, rows, elo, ehi);
                 bd_mbar_expect(mb, (unsigned) nb * (unsigned) (BD_BOX_M + BD_BOX_E + BD_BOX_P + (RIG ? BD_BOX_E : 0)));
             }
             __syncwarp();
@@ -429,9 +446,52 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         yl = y0_k + rows_k - 1;
     }
     if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
+    if (lane == 0 && p.fixn) *p.fixn = kp - 1; // chunks whose parents k_fix_parents has to recompute (the last is the end marker)
     if (p.dbg && lane == 0) {
         atomicAdd((unsigned long long *) &p.dbg[4], (unsigned long long) kp);
         atomicAdd((unsigned long long *) &p.dbg[9], (unsigned long long) t_plan);
+    }
+}
+
+// Parents of the cells the band DP evaluated, recomputed from the final values: one CTA per chunk of the table the
+// producer left in p.fix ({y0, rows, elo, ehi}); 4 cells per thread, packed store.  liblqr writes least[] for every
+// cell of its band (A.8); for a kept cell the arg-min equals the stored parent, so writing the arg-min everywhere
+// in the (larger) evaluated range is the same map.
+template <int D, bool RIG, bool LR>
+__global__ void __launch_bounds__(256) k_fix_parents(const DevP p)
+{
+    if ((int) blockIdx.x >= *p.fixn) return;
+    const int4 f = p.fix[blockIdx.x];
+    const int y0 = f.x, rows = f.y, elo = f.z, ehi = f.w;
+    const int nq = (ehi - elo + 1) >> 2; // groups of 4 cells per row
+    const float inf = __int_as_float(0x7f800000);
+    float rmap[2 * D + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
+    for (int t = threadIdx.x; t < rows * nq; t += blockDim.x) {
+        const int r = t / nq, x0 = elo + 4 * (t - r * nq), y = y0 + r;
+        if (y == 0) continue;
+        const float *up = p.m + (size_t) (y - 1) * p.pitch;
+        float v[4 + 2 * D];
+#pragma unroll
+        for (int j = 0; j < 4 + 2 * D; ++j) {
+            const int x = x0 - D + j;
+            v[j] = (x >= 0 && x < p.pitch) ? up[x] : inf;
+        }
+        unsigned pk = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float rf = RIG ? p.rig[(size_t) y * p.pitch + x0 + i] : 1.f;
+            float cand[2 * D + 1];
+            float best = inf;
+#pragma unroll
+            for (int j = 0; j <= 2 * D; ++j) {
+                cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf, rmap[j])) : v[i + j];
+                best = fminf(best, cand[j]);
+            }
+            pk |= ((unsigned) (bd_argmin<D, LR>(cand, best) & 0xff)) << (8 * i);
+        }
+        *reinterpret_cast<unsigned *>(p.pdx + (size_t) y * p.pitch + x0) = pk;
     }
 }
 
@@ -459,8 +519,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const _
 
     if (warp == 0) {
         bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane);
-    } else if (warp & 3) {
-        bd_compute<D, RIG, LR>(p, ring, hand, desc, hull, mbar, (warp >> 2) * 3 + (warp & 3) - 1, lane);
+    } else {
+        bd_compute<D, RIG, LR>(p, ring, hand, desc, hull, mbar, warp - 1, lane);
     }
     __syncthreads();
     const int y_from = misc[0];

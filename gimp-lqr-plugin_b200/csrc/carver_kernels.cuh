@@ -51,6 +51,8 @@ struct DevP {
     const float *rigmask;
     const float *rigmap; // centred: rigmap[dx], dx in [-delta_x, delta_x]
     int *vpath_x, *nrg_xmin, *nrg_xmax;
+    int4 *fix;          // per band-DP chunk {y0, rows, elo, ehi}: the cells whose parents k_fix_parents recomputes
+    int *fixn;          // number of entries of fix
     unsigned *nrg_pack; // per row: nrg_xmin | (nrg_xmax - nrg_xmin + 1) << 24, for the band DP's window planner
     unsigned long long *cells; // running count of band cells evaluated by the incremental DP
     long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
