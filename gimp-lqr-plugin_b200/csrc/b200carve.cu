@@ -311,9 +311,10 @@ int alloc_maps(B200Carver *c)
     if (c->active) {
         B_TRY(dalloc(c, &c->m, n, true));
         B_TRY(dalloc(c, &c->pdx, n, true));
-        B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, BD_K + 1));
-        B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, BD_K));
-        B_TRY(encode_map(&c->maps.pdx, c->pdx, true, c->pitch, c->h_start, BD_K));
+        const int K = bd_rows(c->delta_x, c->rigidity != 0.f);
+        B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, K + 1));
+        B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, K));
+        B_TRY(encode_map(&c->maps.pdx, c->pdx, true, c->pitch, c->h_start, K));
         c->maps.rig = c->maps.en;
     }
     return B200C_OK;
@@ -403,7 +404,7 @@ void launch_band_dp_d(B200Carver *c)
     const DevP p = view(c);
     const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
     const size_t sm = bd_smem_bytes();
-    const int nfix = (c->h + BD_K - 1) / BD_K;
+    const int nfix = (c->h + 7) / 8;
     if (rig && lr) {
         k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
         k_fix_parents<D, true, true><<<nfix, 256, 0, c->stream>>>(p);
@@ -567,7 +568,7 @@ int gather_rig(B200Carver *c)
     dfree(c, c->rig);
     if (c->rigidity == 0.f) return B200C_OK; // without a mask the factor is 1 everywhere
     B_TRY(dalloc(c, &c->rig, (size_t) c->pitch * c->h_start + 64, true));
-    B_TRY(encode_map(&c->maps.rig, c->rig, false, c->pitch, c->h_start, BD_K));
+    B_TRY(encode_map(&c->maps.rig, c->rig, false, c->pitch, c->h_start, bd_rows(c->delta_x, true)));
     dim3 grid((c->w + 255) / 256, c->h);
     StageScope sc("gather_rig", c->stream);
     k_gather_rig<<<grid, 256, 0, c->stream>>>(view(c));
@@ -732,7 +733,7 @@ int transpose(B200Carver *c)
         B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
         B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
-        B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / BD_K + 4, true));
+        B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / 8 + 4, true));
         for (int x = -c->delta_x; x <= c->delta_x; ++x) {
             float &v = c->rigmap_h[x + c->delta_x];
             v = v * c->w0 / c->h0;
@@ -935,6 +936,8 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     if (c->active) return fail(B200C_ERROR, "carver_init: already active");
     B_TRY(use_device(c));
     if (delta_x > B200C_MAX_DELTA) return fail(B200C_ERROR, "carver_init: delta_x above the engine's limit (120)");
+    c->delta_x = delta_x; // the tensor maps made by alloc_maps depend on both
+    c->rigidity = rigidity;
     if (!c->nrg_active) B_TRY(init_energy_related(c));
     c->active = true;
     B_TRY(alloc_maps(c));
@@ -942,7 +945,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->nrg_xmin, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_xmax, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
-    B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / BD_K + 4, true));
+    B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / 8 + 4, true));
     B_TRY(dalloc(c, &c->fixn_d, 1, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));

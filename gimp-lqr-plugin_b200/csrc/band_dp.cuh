@@ -35,24 +35,28 @@ namespace b200c {
 #define BD_NWARPS 13              // warp 0 producer, warp s+1 = segment s: the first four segments sit on four different sub-partitions
 #define BD_THREADS (BD_NWARPS * 32)
 #define BD_SYNC_THREADS ((BD_NCW + 1) * 32)
-#define BD_K 8                    // rows per chunk = height of a TMA box
+#define BD_KMAX 16                // rows per chunk = height of a TMA box: 16 for delta_x <= 1 without rigidity, else 8
 #define BD_BW 128                 // columns per TMA box
 #define BD_LA 3                   // chunks planned ahead, at most
 #define BD_NRING 8                // descriptor / mbarrier ring
-#define BD_HMAX 8192              // rows whose energy bands fit the shared-memory table
+#define BD_HMAX 4608              // rows whose energy bands fit the shared-memory table
 #define BD_HANDW (BD_NCW * 128)
-#define BD_BOX_M ((BD_K + 1) * BD_BW * 4)
-#define BD_BOX_E (BD_K * BD_BW * 4)
-#define BD_BOX_P (BD_K * BD_BW)
-#define BD_RING_BYTES 175104      // 18 slots without, 12 slots with the rigidity-mask box
+#define BD_RING_BYTES 170496      // 9 slots of 16 rows, 17 of 8 rows, 12 of 8 rows with the rigidity-mask box
 
-template <bool RIG>
+// rows per chunk: a longer chunk amortises the chunk boundary, but its stale halo (rows * delta_x) eats the segment
+__host__ __device__ constexpr int bd_rows(int delta_x, bool rig) { return (delta_x <= 1 && !rig) ? 16 : 8; }
+
+template <int D, bool RIG>
 struct BdSlot {
-    static constexpr int off_e = BD_BOX_M;
-    static constexpr int off_g = BD_BOX_M + BD_BOX_E;
-    static constexpr int off_p = BD_BOX_M + BD_BOX_E + (RIG ? BD_BOX_E : 0);
-    static constexpr int bytes = off_p + BD_BOX_P;
+    static constexpr int K = bd_rows(D, RIG);
+    static constexpr int box_m = (K + 1) * BD_BW * 4, box_e = K * BD_BW * 4, box_p = K * BD_BW;
+    static constexpr int off_e = box_m;
+    static constexpr int off_g = box_m + box_e;
+    static constexpr int off_p = box_m + box_e + (RIG ? box_e : 0);
+    static constexpr int bytes = off_p + box_p;
     static constexpr int nslot = BD_RING_BYTES / bytes;
+    static constexpr int HK = (K * D + 3) & ~3; // columns a segment edge goes stale over one chunk
+    static constexpr int S = 128 - 2 * HK;      // stride of the segments = width of an interior
 };
 
 struct BdDesc {
@@ -65,7 +69,7 @@ struct BdDesc {
 static constexpr size_t bd_smem_bytes()
 {
     return (size_t) BD_RING_BYTES + (size_t) BD_HMAX * 4 + 2 * BD_HANDW * 4 + BD_NRING * sizeof(BdDesc) + 256 + 64 + 64 +
-           64 * 4 + 128;
+           64 * 4 + BD_NCW * 4 * 128 * 4 + 128;
 }
 
 __device__ __forceinline__ unsigned bd_saddr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -137,12 +141,11 @@ __device__ __forceinline__ int bd_argmin(const float (&cand)[2 * D + 1], float b
 }
 
 template <int D, bool RIG, bool LR>
-__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand, const BdDesc *desc, int *hull,
-                                           unsigned long long *mbar, int seg, int lane)
+__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand, float *vring,
+                                           const BdDesc *desc, int *hull, unsigned long long *mbar, int seg, int lane)
 {
-    using SL = BdSlot<RIG>;
-    constexpr int HK = (BD_K * D + 3) & ~3; // columns a segment edge goes stale over one chunk
-    constexpr int S = 128 - 2 * HK;         // stride of the segments = width of an interior
+    using SL = BdSlot<D, RIG>;
+    constexpr int HK = SL::HK, S = SL::S;
     const float inf = __int_as_float(0x7f800000);
     const float tol = __int_as_float(0x3727C5AC); // (double) |d| < 1e-5  <=>  |d| <= this float
     const unsigned full = 0xffffffffu;
@@ -151,8 +154,67 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
     float mp[4] = {0.f, 0.f, 0.f, 0.f}; // row y-1 at this lane's cells
     int hl_lo = 0, hl_hi = 0;           // hand-over range of the previous chunk
+    bool leftb = false;                 // this lane's first column is column 0
     long long t_wait = 0, t_bar = 0, t_rows = 0, t_all = p.dbg ? clock64() : 0;
     int n_rows = 0, n_slow = 0;
+
+    // candidates of cell i: row y-1 at columns x0+i-D .. x0+i+D (plus the rigidity term)
+    auto parents = [&](const float (&prev)[4], float (&v)[4 + 2 * D]) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const float l = __shfl_up_sync(full, prev[4 - D + j], 1);
+            v[j] = leftb ? inf : l; // columns < 0 do not exist; columns >= w hold +inf in the maps (sentinels)
+            v[4 + D + j] = __shfl_down_sync(full, prev[j], 1);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[D + i] = prev[i];
+    };
+    // one row, the fast way: out = en + min(parents); returns whether a cell of this lane is "near"
+    auto eval = [&](const float (&prev)[4], const float4 ce, const float4 co, const float4 cg, float (&out)[4]) -> bool {
+        float v[4 + 2 * D];
+        parents(prev, v);
+        const float en[4] = {ce.x, ce.y, ce.z, ce.w};
+        const float mo[4] = {co.x, co.y, co.z, co.w};
+        const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
+        // near <=> 0 < |d| <= tol <=> 2 <= 2*bits(d) (sign shifted out) <= 2*bits(tol) <=> 2*bits(d) - 2 <= 2*bits(tol) - 2
+        // as unsigned; the minimum over the four cells decides for the lane (IMAD + 3-input integer min: off the
+        // float compare pipe's critical path)
+        unsigned u[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float best = RIG ? __fadd_rn(v[i], __fmul_rn(rf[i], rmap[0])) : v[i];
+#pragma unroll
+            for (int j = 1; j <= 2 * D; ++j)
+                best = fminf(best, RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j]);
+            out[i] = __fadd_rn(en[i], best);
+            u[i] = (unsigned) __float_as_int(__fsub_rn(mo[i], out[i])) * 2u - 2u;
+        }
+        return min(min(u[0], u[1]), min(u[2], u[3])) <= 2u * 0x3727C5ACu - 2u;
+    };
+    // the same row with liblqr's full rule: a near cell keeps its old value when its parent is unchanged
+    auto settle = [&](const float (&prev)[4], const float4 ce, const float4 co, const float4 cg, const unsigned char *pold,
+                      float (&out)[4]) {
+        float v[4 + 2 * D];
+        parents(prev, v);
+        const float en[4] = {ce.x, ce.y, ce.z, ce.w};
+        const float mo[4] = {co.x, co.y, co.z, co.w};
+        const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
+        const unsigned pwo = *reinterpret_cast<const unsigned *>(pold);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float cand[2 * D + 1];
+            float best = inf;
+#pragma unroll
+            for (int j = 0; j <= 2 * D; ++j) {
+                cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
+                best = fminf(best, cand[j]);
+            }
+            out[i] = __fadd_rn(en[i], best);
+            const float df = __fsub_rn(mo[i], out[i]);
+            if (df != 0.f && fabsf(df) <= tol && (int) (signed char) (pwo >> (8 * i)) == bd_argmin<D, LR>(cand, best))
+                out[i] = mo[i];
+        }
+    };
 
     for (int k = 0;; ++k) {
         long long t0 = 0;
@@ -177,16 +239,16 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 #else
             const bool st = interior && x0 >= d.elo && x0 <= d.ehi;
 #endif
-            const bool leftb = x0 == 0; // columns < 0 do not exist; columns >= w hold +inf in the maps (sentinels)
+            leftb = x0 == 0;
 
             int slot = d.slot0 + (c >> 7);
             if (slot >= SL::nslot) slot -= SL::nslot;
             const unsigned char *sb = ring + (size_t) slot * SL::bytes;
             const int cc = c & (BD_BW - 1);
-            const float *op = reinterpret_cast<const float *>(sb) + cc;               // m rows -1 .. 7
-            const float *ep = reinterpret_cast<const float *>(sb + SL::off_e) + cc;   // en rows 0 .. 7
+            const float *op = reinterpret_cast<const float *>(sb) + cc;               // m rows -1 .. K-1
+            const float *ep = reinterpret_cast<const float *>(sb + SL::off_e) + cc;   // en rows 0 .. K-1
             const float *gq = reinterpret_cast<const float *>(sb + SL::off_g) + cc;   // rigidity mask rows (RIG)
-            const unsigned char *pp = sb + SL::off_p + cc;                            // pdx rows 0 .. 7
+            const unsigned char *pp = sb + SL::off_p + cc;                            // pdx rows 0 .. K-1 (settle only)
 
             if (d.y0 > 0) {
                 const float4 v = (x0 >= hl_lo && x0 < hl_hi)
@@ -201,7 +263,6 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             float4 o4 = *reinterpret_cast<const float4 *>(op);
             float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
-            float4 co = o4;
             long long tr0 = 0;
             if (p.dbg) tr0 = clock64();
             unsigned go = (unsigned) d.y0 * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
@@ -215,72 +276,71 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
                 r = 1;
             }
+            // The row loop is SPECULATIVE by one row: row r is computed from row r-1's fast values while the question
+            // "did row r-1 have a near cell?" is still open, so the vote + branch that answers it is off the chain
+            // (loop-carried dependency: shuffle -> 3-input min -> add).  If it did (rare), row r-1 is settled with
+            // the full rule -- its operands are still in the tile, its parents (row r-2) in this warp's value ring --
+            // and row r is redone.
+            float *vr = vring + lane * 4; // [4][128] per warp: the values of the last rows, slot = (row + 1) & 3
+            const float *e0 = ep - (size_t) r * BD_BW, *o0 = op - (size_t) r * BD_BW, *g0 = gq - (size_t) r * BD_BW;
+            const unsigned char *p0 = pp - (size_t) r * BD_BW;
+            *reinterpret_cast<float4 *>(vr + (r & 3) * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]); // row r-1
+            bool pend = false;
+#pragma unroll 2
             for (; r < rows; ++r) {
-                const float4 ce = e4, cg = g4;
-                co = o4;
-                const unsigned char *ppc = pp;
-                ep += BD_BW, op += BD_BW, pp += BD_BW, gq += BD_BW;
+                const float4 ce = e4, co = o4, cg = g4;
+                ep += BD_BW, op += BD_BW, gq += BD_BW;
                 e4 = *reinterpret_cast<const float4 *>(ep);
                 o4 = *reinterpret_cast<const float4 *>(op);
                 if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
-                float v[4 + 2 * D];
-#pragma unroll
-                for (int j = 0; j < D; ++j) {
-                    const float l = __shfl_up_sync(full, mp[4 - D + j], 1);
-                    v[j] = leftb ? inf : l;
-                    v[4 + D + j] = __shfl_down_sync(full, mp[j], 1);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i) v[D + i] = mp[i];
-                const float en[4] = {ce.x, ce.y, ce.z, ce.w};
-                const float mo[4] = {co.x, co.y, co.z, co.w};
-                const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
-                bool near = false;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float best = RIG ? __fadd_rn(v[i], __fmul_rn(rf[i], rmap[0])) : v[i];
-#pragma unroll
-                    for (int j = 1; j <= 2 * D; ++j)
-                        best = fminf(best, RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j]);
-                    mp[i] = __fadd_rn(en[i], best);
-                    const float df = __fsub_rn(mo[i], mp[i]);
-                    near |= df != 0.f && fabsf(df) <= tol;
-                }
+                float nv[4];
+                bool nr = eval(mp, ce, co, cg, nv);
 #ifdef BD_DEBUG_ALWAYS_SLOW
-                near = true;
+                pend = r > (d.y0 == 0 ? 1 : 0);
 #endif
-                if (__any_sync(full, near)) { // rare: a kept cell's ulp-sized drift; needs the arg-min and the stored parent
-                    const unsigned pwo = *reinterpret_cast<const unsigned *>(ppc);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float df = __fsub_rn(mo[i], mp[i]);
-                        if (df != 0.f && fabsf(df) <= tol) {
-                            float cand[2 * D + 1];
-                            float best = inf;
-#pragma unroll
-                            for (int j = 0; j <= 2 * D; ++j) {
-                                cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
-                                best = fminf(best, cand[j]);
-                            }
-                            if ((int) (signed char) (pwo >> (8 * i)) == bd_argmin<D, LR>(cand, best)) mp[i] = mo[i];
-                        }
-                    }
+                if (__any_sync(full, pend)) {
+                    const int q = r - 1; // the pending row; its parents are row r-2
+                    const float4 m2 = *reinterpret_cast<const float4 *>(vr + ((r - 1) & 3) * 128);
+                    const float pr[4] = {m2.x, m2.y, m2.z, m2.w};
+                    float4 qg = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (RIG) qg = *reinterpret_cast<const float4 *>(g0 + (size_t) q * BD_BW);
+                    settle(pr, *reinterpret_cast<const float4 *>(e0 + (size_t) q * BD_BW),
+                           *reinterpret_cast<const float4 *>(o0 + (size_t) q * BD_BW), qg, p0 + (size_t) q * BD_BW, mp);
+                    if (st) *reinterpret_cast<float4 *>(p.m + go - p.pitch) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+                    *reinterpret_cast<float4 *>(vr + (r & 3) * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+                    nr = eval(mp, ce, co, cg, nv);
                     ++n_slow;
                 }
-                if (st) *reinterpret_cast<float4 *>(p.m + go) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+                *reinterpret_cast<float4 *>(vr + ((r + 1) & 3) * 128) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+                if (st) *reinterpret_cast<float4 *>(p.m + go) = make_float4(nv[0], nv[1], nv[2], nv[3]);
                 go += p.pitch;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mp[i] = nv[i];
+                pend = nr;
             }
+            if (__any_sync(full, pend)) { // the last row of the chunk is still open
+                const int q = rows - 1;
+                const float4 m2 = *reinterpret_cast<const float4 *>(vr + ((rows - 1) & 3) * 128);
+                const float pr[4] = {m2.x, m2.y, m2.z, m2.w};
+                float4 qg = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (RIG) qg = *reinterpret_cast<const float4 *>(g0 + (size_t) q * BD_BW);
+                settle(pr, *reinterpret_cast<const float4 *>(e0 + (size_t) q * BD_BW),
+                       *reinterpret_cast<const float4 *>(o0 + (size_t) q * BD_BW), qg, p0 + (size_t) q * BD_BW, mp);
+                if (st) *reinterpret_cast<float4 *>(p.m + go - p.pitch) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+                ++n_slow;
+            }
+            const float4 po = *reinterpret_cast<const float4 *>(o0 + (size_t) (rows - 1) * BD_BW); // old values of the last row
             if (p.dbg) {
                 t_rows += clock64() - tr0;
                 n_rows += rows;
             }
             // hand the last row over and publish the hull of the cells whose VALUE changed in it (a changed parent
-            // alone does not matter to the next row)
+            // alone does not matter to the next row); po = the old values of the last row computed
             if (interior) *reinterpret_cast<float4 *>(hand + (k & 1) * BD_HANDW + (x0 - d.hlo)) = make_float4(mp[0], mp[1], mp[2], mp[3]);
             unsigned chg = 0;
             if (st && (rows > 1 || d.y0 > 0))
-                chg = (mp[0] != co.x ? 1u : 0u) | (mp[1] != co.y ? 2u : 0u) | (mp[2] != co.z ? 4u : 0u) | (mp[3] != co.w ? 8u : 0u);
-            else if (st) // the chunk was row 0 alone: compare with the old row 0
+                chg = (mp[0] != po.x ? 1u : 0u) | (mp[1] != po.y ? 2u : 0u) | (mp[2] != po.z ? 4u : 0u) | (mp[3] != po.w ? 8u : 0u);
+            else if (st) // the chunk was row 0 alone
                 chg = 0xfu;
             int lo = INT_MAX, hi = INT_MIN;
             if (chg) {
@@ -320,7 +380,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 
 // ------------------------------------------------------------------------------------------- producer warp
 struct BdMaps {
-    CUtensorMap m, en, pdx, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x 9 (m) / 128 x 8
+    CUtensorMap m, en, pdx, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
 };
 
 template <int D, bool RIG>
@@ -328,9 +388,8 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
                                             BdDesc *desc, const int *hull, unsigned long long *mbar, volatile int *misc,
                                             int lane)
 {
-    using SL = BdSlot<RIG>;
-    constexpr int HK = (BD_K * D + 3) & ~3;
-    constexpr int S = 128 - 2 * HK;
+    using SL = BdSlot<D, RIG>;
+    constexpr int HK = SL::HK, S = SL::S, K = SL::K;
     const unsigned full = 0xffffffffu;
     int ya = 0;                                  // first row of the next chunk to plan
     int hlo = INT_MAX, hhi = INT_MIN, yl = -1;   // hull of the changed cells of row yl
@@ -350,7 +409,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         if (ya >= p.h) {
             end_y = p.h;
         } else {
-            rows = min(BD_K, p.h - ya);
+            rows = min(K, p.h - ya);
             const int yb = ya + rows - 1;
             int nlo = INT_MAX, nhi = INT_MIN; // extremes of the energy bands of rows (yl, yb]
             for (int j = yl + 1 + lane; j <= yb; j += 32) {
@@ -398,7 +457,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
                 // the fetched columns end at llo + lw: unless that is past the image, the last HK of them go stale too
                 dd->hhi = llo + (ropen ? min(lw, (nseg - 1) * S + 128) : min(lw - HK, nseg * S + HK));
                 if (p.fix) p.fix[kp] = make_int4(ya, rows, elo, ehi);
-                bd_mbar_expect(mb, (unsigned) nb * (unsigned) (BD_BOX_M + BD_BOX_E + BD_BOX_P + (RIG ? BD_BOX_E : 0)));
+                bd_mbar_expect(mb, (unsigned) nb * (unsigned) SL::bytes);
             }
             __syncwarp();
             if (lane < nb) {
@@ -507,6 +566,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const _
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(hull + 64); // [BD_NRING]
     volatile int *misc = reinterpret_cast<volatile int *>(mbar + BD_NRING);
     int *s_red = const_cast<int *>(misc) + 16;
+    float *vals = reinterpret_cast<float *>(s_red + 64); // [BD_NCW][4][128]: each compute warp's last rows
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int y = tid; y < p.h; y += BD_THREADS) nrg[y] = p.nrg_pack[y];
@@ -520,7 +580,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const _
     if (warp == 0) {
         bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane);
     } else {
-        bd_compute<D, RIG, LR>(p, ring, hand, desc, hull, mbar, warp - 1, lane);
+        bd_compute<D, RIG, LR>(p, ring, hand, vals + (size_t) (warp - 1) * 4 * 128, desc, hull, mbar, warp - 1, lane);
     }
     __syncthreads();
     const int y_from = misc[0];

@@ -12,15 +12,17 @@
 namespace b200c {
 
 #define SP_THREADS 512
-#define SP_TILE_BYTES 24576
+#define SP_TILE_BYTES 73728
 #define SP_HMAX 8192
 
 static constexpr size_t sp_smem_bytes() { return 2 * SP_TILE_BYTES + SP_HMAX * 4 + 64; }
 
 __device__ __forceinline__ int sp_rows_per_chunk(int delta_x)
 {
-    int r = (int) sqrtf(5000.f / (float) max(delta_x, 1));
-    return max(4, min(64, r));
+    // a chunk must take longer to chase (~35 cycles per row) than the next one takes to arrive (~2 us), and two
+    // tiles of R rows x (4*R*delta_x + 32) bytes must fit SP_TILE_BYTES each
+    int r = (int) sqrtf(17000.f / (float) max(delta_x, 1));
+    return max(4, min(128, r));
 }
 
 __device__ __forceinline__ void sp_cp_async16(void *dst_smem, const void *src)
@@ -75,23 +77,32 @@ __global__ void __launch_bounds__(SP_THREADS, 1) k_seam_path(DevP p)
             // one dependent shared-memory load per row: xx += pdx[y][xx].  A dead parent (PDX_NONE, -128) cannot occur
             // on a seam (the band DP re-evaluates every cell whose parent was carved); it is flagged after the chunk
             // and the column is clamped there, so a corrupted map can never walk the chase out of its window.
-            const signed char *tr = t - wlo;
+            // (explicit ld.shared with a 32-bit address: the chain is LDS -> IADD -> LDS ...)
+            unsigned ta = (unsigned) __cvta_generic_to_shared(t) - (unsigned) wlo;
             int xx = x, bad = 0;
+            auto lds8 = [](unsigned a) {
+                int v;
+                asm volatile("ld.shared.s8 %0, [%1];" : "=r"(v) : "r"(a));
+                return v;
+            };
+            // the chased quantity is the ADDRESS of the seam's cell: a += d + tw (one 3-input add per row on the chain)
+            unsigned ca = ta + (unsigned) xx;
             if (collect) {
-                for (int y = y_bot; y >= y_top; --y, tr += tw) {
-                    sx[y] = xx;
-                    const int d = tr[xx];
+                for (int y = y_bot; y >= y_top; --y, ta += tw) {
+                    sx[y] = (int) (ca - ta);
+                    const int d = lds8(ca);
                     bad |= d == B200C_PDX_NONE;
-                    xx += d;
+                    ca += (unsigned) d + (unsigned) tw;
                 }
             } else {
-                for (int y = y_bot; y >= y_top; --y, tr += tw) {
-                    p.vpath_x[y] = xx;
-                    const int d = tr[xx];
+                for (int y = y_bot; y >= y_top; --y, ta += tw) {
+                    p.vpath_x[y] = (int) (ca - ta);
+                    const int d = lds8(ca);
                     bad |= d == B200C_PDX_NONE;
-                    xx += d;
+                    ca += (unsigned) d + (unsigned) tw;
                 }
             }
+            xx = (int) (ca - ta);
             if (bad || xx < 0 || xx > p.w - 1) {
                 atomicOr(p.err, 2);
                 xx = min(max(xx, 0), p.w - 1);
