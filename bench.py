@@ -264,7 +264,7 @@ def main():
             device_step(eng, d_in.data_ptr(), d_out.data_ptr())
         stream.synchronize()
         stages = {}
-        for s in ["energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "inflate", "readout"]:
+        for s in ["energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "fix_parents", "inflate", "readout"]:
             n = C.c_long()
             ms = eng.b200c_stage_ms(s.encode(), C.byref(n))
             if n.value:
@@ -303,8 +303,9 @@ def main():
         # algorithmic bytes per launch of the dominant kernel
         if dom == "mmap_update":
             n_l = stages[dom]["launches_per_step"]
-            alg_bytes = 24.0 * cells / max(n_l, 1)  # per band cell: raw id, en, m, least read (16 B) + m, least written (8 B)
-            note = "band DP: 24 B per band cell; latency-bound row-serial chain (one CTA), see DESIGN.md"
+            alg_bytes = 13.0 * cells / max(n_l, 1)  # per evaluated band cell: en 4 + m 4 + parent 1 read, m 4 written
+            note = ("k_band_dp: 13 B per evaluated band cell (compact maps); row-serial chain of h dependent rows on one "
+                    "SM -- latency-bound, not bandwidth-bound, see DESIGN.md section 4")
         elif dom == "mmap_full":
             alg_bytes = 8.0 * (W - SEAMS / 2) * H
             note = "full DP: 8 B/px (en read + m written)"

@@ -399,35 +399,34 @@ int raise_smem_limits()
 }
 
 template <int D>
-void launch_band_dp_d(B200Carver *c)
+void launch_band_dp_d(B200Carver *c, bool fix)
 {
     const DevP p = view(c);
     const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
     const size_t sm = bd_smem_bytes();
     const int nfix = (c->h + 7) / 8;
-    if (rig && lr) {
-        k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-        k_fix_parents<D, true, true><<<nfix, 256, 0, c->stream>>>(p);
-    } else if (rig) {
-        k_band_dp<D, true, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-        k_fix_parents<D, true, false><<<nfix, 256, 0, c->stream>>>(p);
-    } else if (lr) {
-        k_band_dp<D, false, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-        k_fix_parents<D, false, true><<<nfix, 256, 0, c->stream>>>(p);
-    } else {
-        k_band_dp<D, false, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-        k_fix_parents<D, false, false><<<nfix, 256, 0, c->stream>>>(p);
+    if (fix) {
+        if (rig && lr) k_fix_parents<D, true, true><<<nfix, 256, 0, c->stream>>>(p);
+        else if (rig) k_fix_parents<D, true, false><<<nfix, 256, 0, c->stream>>>(p);
+        else if (lr) k_fix_parents<D, false, true><<<nfix, 256, 0, c->stream>>>(p);
+        else k_fix_parents<D, false, false><<<nfix, 256, 0, c->stream>>>(p);
+        return;
     }
+    if (rig && lr) k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    else if (rig) k_band_dp<D, true, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    else if (lr) k_band_dp<D, false, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    else k_band_dp<D, false, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
 }
 
-void launch_band_dp(B200Carver *c)
+// fix == false: the band DP itself (k_band_dp); fix == true: the parents of the cells it evaluated (k_fix_parents)
+void launch_band_dp(B200Carver *c, bool fix)
 {
     switch (c->delta_x) {
-        case 0: launch_band_dp_d<0>(c); break;
-        case 1: launch_band_dp_d<1>(c); break;
-        case 2: launch_band_dp_d<2>(c); break;
-        case 3: launch_band_dp_d<3>(c); break;
-        default: launch_band_dp_d<4>(c); break;
+        case 0: launch_band_dp_d<0>(c, fix); break;
+        case 1: launch_band_dp_d<1>(c, fix); break;
+        case 2: launch_band_dp_d<2>(c, fix); break;
+        case 3: launch_band_dp_d<3>(c, fix); break;
+        default: launch_band_dp_d<4>(c, fix); break;
     }
 }
 
@@ -547,12 +546,20 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             c->leftright ^= 1;
             B_TRY(build_mmap(c));
         } else {
-            StageScope sc("mmap_update", s);
-            if (fast && c->delta_x <= 4 && c->h <= BD_HMAX)
-                launch_band_dp(c);
-            else
-                k_mmap_update<<<1, 512, 0, s>>>(view(c));
-            B_TRY(check_launch("k_mmap_update"));
+            const bool band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
+            {
+                StageScope sc("mmap_update", s);
+                if (band)
+                    launch_band_dp(c, false);
+                else
+                    k_mmap_update<<<1, 512, 0, s>>>(view(c));
+                B_TRY(check_launch("k_mmap_update"));
+            }
+            if (band) {
+                StageScope sc("fix_parents", s);
+                launch_band_dp(c, true);
+                B_TRY(check_launch("k_fix_parents"));
+            }
         }
     } else {
         StageScope sc("finish_vsmap", s);
