@@ -756,15 +756,92 @@ bool not_at_reference(const B200Carver *c)
     return c->w != c->w0 || c->w_start != c->w0 || c->h != c->h0 || c->h_start != c->h0;
 }
 
+// ---- pinned host staging, pooled per process: page-locking tens of MB costs more than moving them, and the plug-in
+// creates a fresh carver for every layer (render.c:222,894), so the buffers outlive the handles.
+struct PinnedBuf {
+    uint8_t *p;
+    size_t cap;
+};
+std::mutex g_pin_mu;
+std::vector<PinnedBuf> g_pin_free;
+constexpr size_t kPinKeep = 6; // buffers kept for reuse
+
+int pinned_acquire(size_t bytes, uint8_t **out, size_t *cap)
+{
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        int best = -1;
+        for (int i = 0; i < (int) g_pin_free.size(); ++i)
+            if (g_pin_free[i].cap >= bytes && (best < 0 || g_pin_free[i].cap < g_pin_free[best].cap)) best = i;
+        if (best >= 0) {
+            *out = g_pin_free[best].p;
+            *cap = g_pin_free[best].cap;
+            g_pin_free.erase(g_pin_free.begin() + best);
+            return B200C_OK;
+        }
+    }
+    *out = nullptr;
+    CU_TRY(cudaHostAlloc((void **) out, bytes, cudaHostAllocDefault));
+    *cap = bytes;
+    return B200C_OK;
+}
+
+void pinned_release(uint8_t *p, size_t cap)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pin_mu);
+        if (g_pin_free.size() < kPinKeep) {
+            g_pin_free.push_back({p, cap});
+            return;
+        }
+    }
+    cudaFreeHost(p);
+}
+
 int ensure_host_out(B200Carver *c, size_t bytes)
 {
     if (bytes <= c->host_out_cap) return B200C_OK;
-    if (c->host_out) cudaFreeHost(c->host_out);
+    pinned_release(c->host_out, c->host_out_cap);
     c->host_out = nullptr;
     c->host_out_cap = 0;
-    CU_TRY(cudaHostAlloc((void **) &c->host_out, bytes, cudaHostAllocDefault));
-    c->host_out_cap = bytes;
-    return B200C_OK;
+    return pinned_acquire(bytes, &c->host_out, &c->host_out_cap);
+}
+
+// pageable host memory -> device through two pinned chunks: the CPU copy of chunk i+1 overlaps the DMA of chunk i
+int upload_pageable(B200Carver *c, void *dst, const void *src, size_t bytes)
+{
+    constexpr size_t kChunk = 4u << 20;
+    if (bytes <= (1u << 20)) {
+        CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream)); // the caller may free `src` right after we return
+        return B200C_OK;
+    }
+    uint8_t *stage[2] = {nullptr, nullptr};
+    size_t cap[2] = {0, 0};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    int rc = B200C_OK;
+    for (int i = 0; i < 2 && rc == B200C_OK; ++i) {
+        rc = pinned_acquire(kChunk, &stage[i], &cap[i]);
+        if (rc == B200C_OK && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(B200C_ERROR, "upload: cudaEventCreate", cudaGetLastError());
+    }
+    size_t off = 0;
+    for (int i = 0; rc == B200C_OK && off < bytes; ++i, off += kChunk) {
+        const int b = i & 1;
+        const size_t n = bytes - off < kChunk ? bytes - off : kChunk;
+        if (i >= 2 && cudaEventSynchronize(ev[b]) != cudaSuccess) rc = fail(B200C_ERROR, "upload: event", cudaGetLastError());
+        memcpy(stage[b], (const uint8_t *) src + off, n);
+        if (rc == B200C_OK && (cudaMemcpyAsync((uint8_t *) dst + off, stage[b], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+                               cudaEventRecord(ev[b], c->stream) != cudaSuccess))
+            rc = fail(B200C_ERROR, "upload: cudaMemcpyAsync", cudaGetLastError());
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == B200C_OK) rc = fail(B200C_ERROR, "upload: sync", cudaGetLastError());
+    for (int i = 0; i < 2; ++i) {
+        if (ev[i]) cudaEventDestroy(ev[i]);
+        pinned_release(stage[i], cap[i]);
+    }
+    return rc;
 }
 
 B200Carver *carver_new_common(int width, int height, int channels)
@@ -864,8 +941,7 @@ B200Carver *b200c_carver_new(const unsigned char *rgb, int width, int height, in
     if (!c) return nullptr;
     const size_t n = (size_t) width * height;
     if (dalloc(c, &c->rgb, n * channels, false) != B200C_OK || dalloc(c, &c->vs, n, true) != B200C_OK ||
-        cudaMemcpyAsync(c->rgb, rgb, n * channels, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess) { // the caller may free `rgb` right after we return
+        upload_pageable(c, c->rgb, rgb, n * channels) != B200C_OK) { // synchronous: the caller may free `rgb` right after
         fail(B200C_NOMEM, "carver_new: device allocation / upload failed", cudaGetLastError());
         b200c_carver_destroy(c);
         return nullptr;
@@ -929,7 +1005,7 @@ void b200c_carver_destroy(B200Carver *c)
     }
     dfree(c, c->dbg_d);
     dfree(c, c->rigmap_d);
-    if (c->host_out) cudaFreeHost(c->host_out);
+    pinned_release(c->host_out, c->host_out_cap);
     if (c->stream) {
         cudaStreamSynchronize(c->stream);
         if (owns_stream) cudaStreamDestroy(c->stream);
