@@ -1,0 +1,83 @@
+"""BASELINE.json configs 2-5 through the product (liblqr-1.so -> libb200carve.so) at FULL size, with the
+size-independent property checks (one pixel per line per seam, output = input minus seam pixels, expected number of
+seam maps).  The oracle is not involved (it takes minutes at these sizes); small-size parity is in tests/.
+
+Usage: python tools/run_configs.py [2 3 4 5] [--batch N]      (config 4: N images on this GPU, default 8)
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+pkg = importlib.import_module("gimp-lqr-plugin_b200")
+synth, render = pkg.synth, pkg.render
+V = render.PlugInVals
+
+
+def check_vmap(vm, n, lines):
+    counts = np.bincount(vm.ravel(), minlength=n + 1)
+    assert counts.shape[0] == n + 1 and np.array_equal(counts[1:], np.full(n, lines)), "seam map: wrong pixel counts"
+
+
+def run(lib, img, vals, **kw):
+    t0 = time.perf_counter()
+    res = render.render_noninteractive(lib, img, vals, **kw)
+    return res, time.perf_counter() - t0
+
+
+def main():
+    which = [int(a) for a in sys.argv[1:] if a.isdigit()] or [2, 3, 4, 5]
+    batch = int(sys.argv[sys.argv.index("--batch") + 1]) if "--batch" in sys.argv else 8
+    lib = pkg.load_product()
+    out = {}
+    if 2 in which:
+        w, h, n = 3840, 2160, 200
+        img = synth.smooth_noise(w, h, 4)
+        run(lib, img[:256, :512].copy(), V(new_width=500, new_height=256))  # warm-up (context, pools)
+        res, dt = run(lib, img, V(new_width=w - n, new_height=h, output_seams=True))
+        assert res.image.shape == (h, w - n, 4) and len(res.vmaps) == 1
+        vm = res.vmaps[0].data
+        check_vmap(vm, n, h)
+        assert np.array_equal(res.image, img[vm == 0].reshape(h, w - n, 4))
+        out["config2"] = {"what": "3840x2160 RGBA, 200 vertical seams", "wall_s": dt, "seams_per_s_e2e": n / dt}
+    if 3 in which:
+        w, h, n = 7680, 4320, 1000
+        img = synth.smooth_noise(w, h, 4, alpha="random")
+        pres, rig = synth.ellipse_mask(w, h), synth.band_mask(w, h)
+        res, dt = run(lib, img, V(new_width=w - n, new_height=h, delta_x=2, rigidity=10.0, output_seams=True),
+                      pres=(pres, 0, 0), rigmask=(rig, 0, 0))
+        assert res.image.shape == (h, w - n, 4) and len(res.vmaps) == 1
+        vm = res.vmaps[0].data
+        check_vmap(vm, n, h)
+        assert np.array_equal(res.image, img[vm == 0].reshape(h, w - n, 4))
+        out["config3"] = {"what": "7680x4320 RGBA, 1000 seams, preservation + rigidity masks, delta_x 2, rigidity 10",
+                          "wall_s": dt, "seams_per_s_e2e": n / dt}
+    if 4 in which:
+        w, h, n = 1920, 1080, 100
+        t0 = time.perf_counter()
+        for i in range(batch):
+            img = synth.smooth_noise(w, h, 4, seed=synth.SEED + i)
+            res = render.render_noninteractive(lib, img, V(new_width=w - n, new_height=h))
+            assert res.image.shape == (h, w - n, 4)
+        dt = time.perf_counter() - t0
+        out["config4"] = {"what": f"{batch} of the 256 x 1920x1080 RGBA images, 100 seams each, sequentially on one GPU "
+                                  "(incl. synthetic image generation on the host)", "wall_s": dt,
+                          "seams_per_s_e2e": batch * n / dt}
+    if 5 in which:
+        w, h = 3840, 2160
+        img = synth.smooth_noise(w, h, 4)
+        res, dt = run(lib, img, V(new_width=w - 400, new_height=h + 200, output_seams=True))
+        assert res.image.shape == (h + 200, w - 400, 4) and len(res.vmaps) == 2
+        check_vmap(res.vmaps[0].data, 400, h)
+        check_vmap(res.vmaps[1].data, 200, w - 400)
+        out["config5"] = {"what": "3840x2160 -> 3440x2360 (W-400, H+200) with seam maps", "wall_s": dt,
+                          "seams_per_s_e2e": 600 / dt}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -18,6 +18,7 @@ STAGES = ["init_raw", "energy_full", "mmap_full", "vpath", "carve", "energy_band
 def main():
     w, h, seams = (int(a) for a in (sys.argv[1:4] if len(sys.argv) >= 4 else (3840, 2160, 200)))
     dx = int(sys.argv[4]) if len(sys.argv) > 4 else 1
+    rigidity = float(sys.argv[5]) if len(sys.argv) > 5 else 0.0
     lib = pkg.load_product()
     eng = C.CDLL(pkg.ENGINE_PATH)
     eng.b200c_stage_ms.restype = C.c_double
@@ -29,7 +30,7 @@ def main():
         eng.b200c_stage_reset()
         l0 = eng.b200c_launch_count()
         c = lib.carver(img)
-        c.init(dx, 0.0)
+        c.init(dx, rigidity)
         c.set_side_switch_frequency(2)
         t0 = time.perf_counter()
         c.resize(w - seams, h)
