@@ -314,6 +314,9 @@ def main():
             note = "index-table shift: 8 B x (W - x_seam) per row"
         dur_s = stages[dom]["us_per_launch"] * 1e-6
         achieved = alg_bytes / dur_s / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one k_band_dp launch, from the committed ncu --set full capture
+        # (profiles/r01_band_dp_ncu_summary.txt: 7.71 MB read, 0 written back before the kernel ends -- the maps are L2-resident)
+        traffic = 7.71e6 if dom == "mmap_update" else None
         mf = stages.get("mmap_full")
         roof_full = None
         if mf:
@@ -322,7 +325,7 @@ def main():
             t_pass = mf["ms_per_step"] / passes * 1e-3
             a_full = 8.0 * (W - SEAMS / 2) * H / t_pass / 1e9
             roof_full = {"bound": "hbm", "achieved": a_full, "peak": peak, "unit": "GB/s", "frac": a_full / peak,
-                         "traffic": None, "kernel": "k_mmap_full_tile (one full m-map DP pass, 8 B/px)",
+                         "traffic": None, "kernel": "k_mmap_full_strips (one full m-map DP pass = h/32 launches, 8 B/px)",
                          "ms_per_pass": t_pass * 1e3}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -339,7 +342,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": dom, "share_of_step": stages[dom]["ms_per_step"] / total_stage,
+                         "traffic": traffic, "kernel": dom, "share_of_step": stages[dom]["ms_per_step"] / total_stage,
                          "peak_source": peak_src, "note": note},
             "roofline_mmap_full": roof_full,
             "kernels": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in stages.items()},

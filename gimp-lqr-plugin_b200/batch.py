@@ -29,14 +29,46 @@ def digest(arr: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(arr).tobytes()).hexdigest()
 
 
-def carve_shard(lib, indices, w, h, new_w, new_h, channels=4, vals: render.PlugInVals | None = None):
-    """Carves the images of one shard through the LqrCarver API; returns {index: (shape, sha256)}."""
-    vals = vals or render.PlugInVals()
-    vals.new_width, vals.new_height = new_w, new_h
-    out = {}
-    for i in indices:
-        res = render.render_noninteractive(lib, batch_image(i, w, h, channels), vals)
-        out[i] = (tuple(res.image.shape), digest(res.image))
+def carve_shard(lib, indices, w, h, new_w, new_h, channels=4, vals: render.PlugInVals | None = None, in_flight: int = 1):
+    """Carves the images of one shard through the LqrCarver API; returns {index: (shape, sha256)}.
+
+    in_flight > 1 keeps that many images in flight on the GPU: one host thread per image, and the engine gives every
+    carver its own CUDA stream, so the row-serial DP chains of different images run on different SMs at the same
+    time -- the only way this path approaches the bandwidth of the device.  The C calls release
+    the GIL; each image's seams stay strictly sequential."""
+    import dataclasses
+    import threading
+
+    base = vals or render.PlugInVals()
+    todo = list(indices)[::-1]
+    out, lock, errors = {}, threading.Lock(), []
+
+    def worker():
+        while True:
+            with lock:
+                if not todo or errors:
+                    return
+                i = todo.pop()
+            try:
+                v = dataclasses.replace(base, new_width=new_w, new_height=new_h)
+                res = render.render_noninteractive(lib, batch_image(i, w, h, channels), v)
+                with lock:
+                    out[i] = (tuple(res.image.shape), digest(res.image))
+            except Exception as e:  # noqa: BLE001 -- reported to the caller below
+                with lock:
+                    errors.append(e)
+
+    n = max(1, min(int(in_flight), len(todo) or 1))
+    if n == 1:
+        worker()
+    else:
+        threads = [threading.Thread(target=worker) for _ in range(n)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    if errors:
+        raise errors[0]
     return out
 
 

@@ -135,6 +135,7 @@ struct B200Carver {
     long long *dbg_d = nullptr;               // role cycle counters (B200C_DBG=1)
     bool owns_stream = true;
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
+    int bd_maxseg = 1 << 20;                  // B200C_BD_MAXSEG: test knob, forces the band DP's wide-window path
 
     float rigidity = 0.f;
     int delta_x = 1;
@@ -199,6 +200,7 @@ DevP view(const B200Carver *c)
     p.read_kind = c->read_kind;
     p.nrg_radius = c->nrg_radius;
     p.use_rig = c->rigidity != 0.f;
+    p.bd_maxseg = c->bd_maxseg;
     p.rgb = c->rgb;
     p.vs = c->vs;
     p.raw = c->raw;
@@ -869,6 +871,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
     {
         const char *g = getenv("B200C_GENERIC");
         c->generic = g && atoi(g) != 0;
+        const char *ms = getenv("B200C_BD_MAXSEG");
+        if (ms && atoi(ms) > 0) c->bd_maxseg = atoi(ms);
 
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;

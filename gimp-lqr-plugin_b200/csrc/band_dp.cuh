@@ -432,7 +432,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             nb = (need + BD_BW - 1) / BD_BW;
             lw = nb * BD_BW;
             ropen = llo + min(lw, (nseg - 1) * S + 128) >= wlim; // fetched AND covered by the last segment
-            if (nseg > BD_NCW || nb > SL::nslot) end_y = ya; // too wide: the exact generic loop takes over at row ya
+            if (nseg > min(BD_NCW, p.bd_maxseg) || nb > SL::nslot) end_y = ya; // too wide: the exact generic loop takes over at row ya
         }
         if (end_y < 0 && nb > slots_free) return false;
         if (end_y >= 0) {
@@ -554,6 +554,105 @@ __global__ void __launch_bounds__(256) k_fix_parents(const DevP p)
     }
 }
 
+// The rows the tiled path cannot take (window wider than BD_NCW segments): the same superset evaluation as
+// update_rows_generic, row by row with the whole CTA, but with the previous row kept in shared memory (the tile ring is
+// free by now) and every operand of a row fetched in one batch of independent loads, so a row costs about one
+// trip to L2 instead of one per candidate.  prev / cur: two row buffers of `cap` floats (cap >= pitch).
+template <int D, bool RIG, bool LR>
+__device__ void bd_rows_wide(const DevP &p, int y_from, int lo, int hi, float *prev, float *cur, int *s_red)
+{
+    constexpr int NB = 8; // cells per thread and batch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarp = nthr >> 5;
+    const float inf = __int_as_float(0x7f800000);
+    float rmap[2 * D + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
+    int plo = 1, phi = 0; // columns of `prev` holding row y-1 (empty: parents come from HBM)
+    unsigned long long cells = 0;
+    for (int y = y_from; y < p.h; ++y) {
+        const size_t o = (size_t) y * p.pitch;
+        const int elo = max(min(lo, p.nrg_xmin[y]) - (y ? D : 0), 0);
+        const int ehi = min(max(hi, p.nrg_xmax[y]) + (y ? D : 0), p.w - 1);
+        if (y > 0) { // parents of the range that row y-1 did not evaluate: unchanged, from HBM
+            const int need_lo = max(elo - D, 0), need_hi = min(ehi + D, p.w - 1);
+            const float *up = p.m + o - p.pitch;
+            if (plo > phi) {
+                for (int x = need_lo + tid; x <= need_hi; x += nthr) prev[x] = up[x];
+            } else {
+                for (int x = need_lo + tid; x < plo; x += nthr) prev[x] = up[x];
+                for (int x = phi + 1 + tid; x <= need_hi; x += nthr) prev[x] = up[x];
+            }
+        }
+        __syncthreads();
+        int first = INT_MAX, last = INT_MIN;
+        for (int base = elo; base <= ehi; base += nthr * NB) {
+            float en[NB], mo[NB], rf[NB];
+            int pd[NB];
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int x = base + j * nthr + tid;
+                en[j] = mo[j] = 0.f, rf[j] = 1.f, pd[j] = 0;
+                if (x <= ehi) {
+                    en[j] = p.en[o + x];
+                    mo[j] = p.m[o + x];
+                    pd[j] = p.pdx[o + x];
+                    if (RIG) rf[j] = p.rig[o + x];
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NB; ++j) {
+                const int x = base + j * nthr + tid;
+                if (x > ehi) continue;
+                float val;
+                if (y == 0) { // row 0: m = en over the energy band; the band carries over to row 1 (A.8)
+                    val = en[j];
+                    p.m[x] = val;
+                    first = min(first, x), last = max(last, x);
+                } else {
+                    float cand[2 * D + 1];
+                    float best = inf;
+#pragma unroll
+                    for (int k = 0; k <= 2 * D; ++k) {
+                        const int xx = x + k - D;
+                        const float pv = (xx >= 0 && xx <= p.w - 1) ? prev[xx] : inf;
+                        cand[k] = RIG ? __fadd_rn(pv, __fmul_rn(rf[j], rmap[k])) : pv;
+                        best = fminf(best, cand[k]);
+                    }
+                    const int bdx = bd_argmin<D, LR>(cand, best);
+                    const float nm = __fadd_rn(en[j], best);
+                    val = mo[j];
+                    if (!keep_old(pd[j], bdx, mo[j], nm)) {
+                        val = nm;
+                        p.m[o + x] = nm;
+                        p.pdx[o + x] = (int8_t) bdx;
+                        first = min(first, x), last = max(last, x);
+                    }
+                }
+                cur[x] = val;
+            }
+        }
+        if (tid == 0 && ehi >= elo) cells += (unsigned long long) (ehi - elo + 1);
+        first = __reduce_min_sync(0xffffffffu, first);
+        last = __reduce_max_sync(0xffffffffu, last);
+        const int buf = (y & 1) * 32;
+        if (lane == 0) {
+            s_red[buf + warp] = first;
+            s_red[buf + 16 + warp] = last;
+        }
+        __syncthreads(); // publishes this row's values (cur) and the per-warp extremes
+        lo = INT_MAX, hi = INT_MIN;
+        for (int i = 0; i < nwarp; ++i) {
+            lo = min(lo, s_red[buf + i]);
+            hi = max(hi, s_red[buf + 16 + i]);
+        }
+        plo = elo, phi = ehi;
+        float *t = prev;
+        prev = cur;
+        cur = t;
+    }
+    if (tid == 0 && p.cells) atomicAdd(p.cells, cells);
+}
+
 template <int D, bool RIG, bool LR>
 __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const __grid_constant__ BdMaps tm)
 {
@@ -584,7 +683,14 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const _
     }
     __syncthreads();
     const int y_from = misc[0];
-    if (y_from < p.h) update_rows_generic(p, y_from, misc[1], misc[2], s_red);
+    if (y_from < p.h) {
+        if (p.dbg && tid == 0) atomicAdd((unsigned long long *) &p.dbg[14], (unsigned long long) (p.h - y_from));
+        constexpr int cap = BD_RING_BYTES / 8; // two row buffers in the tile ring, which nobody uses any more
+        if (p.pitch <= cap)
+            bd_rows_wide<D, RIG, LR>(p, y_from, misc[1], misc[2], reinterpret_cast<float *>(ring), reinterpret_cast<float *>(ring) + cap, s_red);
+        else
+            update_rows_generic(p, y_from, misc[1], misc[2], s_red);
+    }
 }
 
 } // namespace b200c

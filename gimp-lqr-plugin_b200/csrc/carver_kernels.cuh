@@ -40,6 +40,7 @@ struct DevP {
     int leftright;
     int grad_kind, read_kind, nrg_radius;
     int use_rig;       // rigidity != 0
+    int bd_maxseg;     // band DP: widest window (in segments) the tiled path takes (test knob B200C_BD_MAXSEG)
     const uint8_t *rgb;
     int *vs;
     int *raw;

@@ -28,18 +28,24 @@ def engine(pkg, product):
     return eng
 
 
-@pytest.fixture(params=["fast", "generic"])
+@pytest.fixture(params=["fast", "narrow", "generic"])
 def kernel_mode(request):
-    """Every kernel set must match the oracle: "fast" (default: trapezoid-tiled band DP staged with TMA bulk
-    copies, staged backtrack, cluster full DP) and "generic" (B200C_GENERIC=1: the single-CTA kernels everything
-    falls back to).  Read at carver creation."""
-    old = os.environ.get("B200C_GENERIC")
+    """Every kernel set must match the oracle: "fast" (default: trapezoid-tiled band DP fed by 2-D TMA tiles, staged
+    backtrack, strip-tiled full DP), "narrow" (B200C_BD_MAXSEG=1: the band DP hands every window wider than one segment
+    to its in-kernel wide-window row loop, which large images only reach on very wide bands) and "generic"
+    (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at carver creation."""
+    old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_BD_MAXSEG")}
     os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
-    yield request.param
-    if old is None:
-        os.environ.pop("B200C_GENERIC", None)
+    if request.param == "narrow":
+        os.environ["B200C_BD_MAXSEG"] = "1"
     else:
-        os.environ["B200C_GENERIC"] = old
+        os.environ.pop("B200C_BD_MAXSEG", None)
+    yield request.param
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
 
 
 def test_device_is_blackwell(engine):
@@ -203,3 +209,13 @@ def test_full_size_properties_config2(product):
         xs = np.argmax(vm == k, axis=1)
         removed_before = np.array([np.count_nonzero((vm[y, :x] > 0) & (vm[y, :x] < k)) for y, x in enumerate(xs)])
         assert np.abs(np.diff(xs - removed_before)).max() <= 1
+
+
+def test_batch_images_in_flight(product, oracle):
+    """Config 4 shape: several images in flight on one GPU (host threads, one stream per carver) give the same
+    per-image results as the oracle run one by one."""
+    import importlib
+    batch = importlib.import_module("gimp-lqr-plugin_b200.batch")
+    want = batch.carve_shard(oracle, range(12), 160, 90, 150, 90)
+    got = batch.carve_shard(product, range(12), 160, 90, 150, 90, in_flight=6)
+    assert got == want

@@ -67,6 +67,36 @@ def main():
         out["config4"] = {"what": f"{batch} of the 256 x 1920x1080 RGBA images, 100 seams each, sequentially on one GPU "
                                   "(incl. synthetic image generation on the host)", "wall_s": dt,
                           "seams_per_s_e2e": batch * n / dt}
+    if 44 in which:
+        # config 4 with several images in flight on this GPU: one host thread + one CUDA stream per image (the engine
+        # gives every carver its own stream); the row-serial chains of different images overlap on different SMs
+        import threading
+        w, h, n = 1920, 1080, 100
+        nthreads = int(os.environ.get("B200C_THREADS", "16"))
+        imgs = [synth.smooth_noise(w, h, 4, seed=synth.SEED + i) for i in range(batch)]
+        run(lib, imgs[0], V(new_width=w - n, new_height=h))
+        todo = list(range(batch))
+        lock = threading.Lock()
+        shapes = []
+
+        def worker():
+            while True:
+                with lock:
+                    if not todo:
+                        return
+                    i = todo.pop()
+                res = render.render_noninteractive(lib, imgs[i], V(new_width=w - n, new_height=h))
+                shapes.append(res.image.shape)
+
+        t0 = time.perf_counter()
+        ts = [threading.Thread(target=worker) for _ in range(nthreads)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        dt = time.perf_counter() - t0
+        assert len(shapes) == batch and all(sh == (h, w - n, 4) for sh in shapes)
+        out["config4_concurrent"] = {"what": f"{batch} x 1920x1080 RGBA, 100 seams each, {nthreads} images in flight on one GPU "
+                                             "(host threads, one stream per carver)", "wall_s": dt,
+                                     "seams_per_s_e2e": batch * n / dt}
     if 5 in which:
         w, h = 3840, 2160
         img = synth.smooth_noise(w, h, 4)
@@ -76,6 +106,19 @@ def main():
         check_vmap(res.vmaps[1].data, 200, w - 400)
         out["config5"] = {"what": "3840x2160 -> 3440x2360 (W-400, H+200) with seam maps", "wall_s": dt,
                           "seams_per_s_e2e": 600 / dt}
+    if os.environ.get("B200C_TIMING"):
+        import ctypes as C
+        eng = C.CDLL(pkg.ENGINE_PATH)
+        eng.b200c_stage_ms.restype = C.c_double
+        eng.b200c_stage_ms.argtypes = [C.c_char_p, C.POINTER(C.c_long)]
+        st = {}
+        for name in ["energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "fix_parents", "inflate",
+                     "readout", "mask", "gather_rig", "transpose", "flatten", "vmap"]:
+            n = C.c_long()
+            ms = eng.b200c_stage_ms(name.encode(), C.byref(n))
+            if n.value:
+                st[name] = {"ms": round(ms, 2), "launches": n.value, "us_per_launch": round(1e3 * ms / n.value, 1)}
+        out["stages_all_configs"] = st
     print(json.dumps(out, indent=1))
 
 
