@@ -14,8 +14,11 @@
 #include <string.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -810,10 +813,79 @@ int ensure_host_out(B200Carver *c, size_t bytes)
     return pinned_acquire(bytes, &c->host_out, &c->host_out_cap);
 }
 
+// A few helper threads for the host side of large uploads: one core copies pageable memory at ~5 GB/s, well below
+// what the DMA engine moves from pinned memory, so the staging copy of a chunk is split over the helpers.
+class CopyHelpers {
+  public:
+    static CopyHelpers &get()
+    {
+        static CopyHelpers *h = new CopyHelpers; // never destroyed: its threads outlive static destruction
+        return *h;
+    }
+    // memcpy(dst, src, n) split over the helpers and the calling thread; returns when done
+    void copy(uint8_t *dst, const uint8_t *src, size_t n)
+    {
+        const int parts = (int) workers_.size() + 1;
+        if (workers_.empty() || n < (1u << 20)) {
+            memcpy(dst, src, n);
+            return;
+        }
+        const size_t slice = (n / parts + 4095) & ~(size_t) 4095;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = dst, src_ = src, n_ = n, slice_ = slice;
+            pending_ = (int) workers_.size();
+            ++epoch_;
+        }
+        cv_.notify_all();
+        do_slice(0);
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+
+  private:
+    CopyHelpers()
+    {
+        unsigned hc = std::thread::hardware_concurrency();
+        int n = hc >= 8 ? 3 : (hc >= 4 ? 2 : (hc >= 2 ? 1 : 0));
+        const char *e = getenv("B200C_COPY_THREADS");
+        if (e) n = atoi(e) < 0 ? 0 : (atoi(e) > 7 ? 7 : atoi(e));
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this, i] { loop(i + 1); }), workers_.back().detach();
+    }
+    void do_slice(int part)
+    {
+        const size_t a = (size_t) part * slice_;
+        if (a < n_) memcpy(dst_ + a, src_ + a, n_ - a < slice_ ? n_ - a : slice_);
+    }
+    void loop(int part)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return epoch_ != seen; });
+                seen = epoch_;
+            }
+            do_slice(part);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    size_t n_ = 0, slice_ = 0;
+    int pending_ = 0;
+    unsigned long long epoch_ = 0;
+};
+std::mutex g_upload_mu; // one large upload at a time uses the helpers
+
 // pageable host memory -> device through two pinned chunks: the CPU copy of chunk i+1 overlaps the DMA of chunk i
 int upload_pageable(B200Carver *c, void *dst, const void *src, size_t bytes)
 {
-    constexpr size_t kChunk = 4u << 20;
+    constexpr size_t kChunk = 8u << 20;
     if (bytes <= (1u << 20)) {
         CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
         CU_TRY(cudaStreamSynchronize(c->stream)); // the caller may free `src` right after we return
@@ -833,7 +905,10 @@ int upload_pageable(B200Carver *c, void *dst, const void *src, size_t bytes)
         const int b = i & 1;
         const size_t n = bytes - off < kChunk ? bytes - off : kChunk;
         if (i >= 2 && cudaEventSynchronize(ev[b]) != cudaSuccess) rc = fail(B200C_ERROR, "upload: event", cudaGetLastError());
-        memcpy(stage[b], (const uint8_t *) src + off, n);
+        {
+            std::lock_guard<std::mutex> lk(g_upload_mu);
+            CopyHelpers::get().copy(stage[b], (const uint8_t *) src + off, n);
+        }
         if (rc == B200C_OK && (cudaMemcpyAsync((uint8_t *) dst + off, stage[b], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                                cudaEventRecord(ev[b], c->stream) != cudaSuccess))
             rc = fail(B200C_ERROR, "upload: cudaMemcpyAsync", cudaGetLastError());

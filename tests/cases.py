@@ -112,6 +112,13 @@ CASES += [
     case("mid_flat_ties", "flat", 500, 300, 4, V(new_width=470, new_height=300, output_seams=True)),
     case("mid_enlarge", "smooth_noise", 640, 360, 4, V(new_width=700, new_height=380, output_seams=True)),
 ]
+# geometry limits of the tiled band DP: taller than its row table (4608 rows -> generic update kernel), and bands wider
+# than its 12 segments (flat image: every cell ties, the band spans the image -> in-kernel wide-window row loop)
+CASES += [
+    case("taller_than_row_table", "smooth_noise", 40, 4700, 4, V(new_width=36, new_height=4700, output_seams=True)),
+    case("wide_flat_band", "flat", 2600, 48, 4, V(new_width=2592, new_height=48, output_seams=True)),
+    case("wide_iid_dx4", "iid", 2000, 64, 4, V(new_width=1994, new_height=64, delta_x=4, output_seams=True)),
+]
 for _ef in range(7):
     CASES.append(case(f"energy_fn_{_ef}", "smooth_noise", 64, 48, 4,
                       V(new_width=52, new_height=44, nrg_func=_ef, output_seams=True), alpha="random"))
