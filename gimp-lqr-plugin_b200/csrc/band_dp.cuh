@@ -37,6 +37,13 @@ namespace b200c {
 #define BD_SYNC_THREADS ((BD_NCW + 1) * 32)
 #define BD_KMAX 16                // rows per chunk = height of a TMA box: 16 for delta_x <= 1 without rigidity, else 8
 #define BD_BW 128                 // columns per TMA box
+// cycle counters of the roles (B200C_DBG=1 at run time) are compiled in only with -DBD_PROFILE: they cost the
+// compute warps ~100 cycles per chunk
+#ifdef BD_PROFILE
+#define BD_PROF true
+#else
+#define BD_PROF false
+#endif
 #define BD_LA 3                   // chunks planned ahead, at most
 #define BD_NRING 8                // descriptor / mbarrier ring
 #define BD_HMAX 4608              // rows whose energy bands fit the shared-memory table
@@ -154,8 +161,8 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
     float mp[4] = {0.f, 0.f, 0.f, 0.f}; // row y-1 at this lane's cells
     int hl_lo = 0, hl_hi = 0;           // hand-over range of the previous chunk
-    bool leftb = false;                 // this lane's first column is column 0
-    long long t_wait = 0, t_bar = 0, t_rows = 0, t_all = p.dbg ? clock64() : 0;
+    float leftfloor = -inf;             // +inf in the lane whose first column is column 0: its left parents do not exist
+    long long t_wait = 0, t_bar = 0, t_rows = 0, t_all = (BD_PROF && p.dbg) ? clock64() : 0;
     int n_rows = 0, n_slow = 0;
 
     // candidates of cell i: row y-1 at columns x0+i-D .. x0+i+D (plus the rigidity term)
@@ -163,7 +170,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 #pragma unroll
         for (int j = 0; j < D; ++j) {
             const float l = __shfl_up_sync(full, prev[4 - D + j], 1);
-            v[j] = leftb ? inf : l; // columns < 0 do not exist; columns >= w hold +inf in the maps (sentinels)
+            v[j] = fmaxf(l, leftfloor); // columns < 0 do not exist (+inf); columns >= w hold +inf in the maps (sentinels)
             v[4 + D + j] = __shfl_down_sync(full, prev[j], 1);
         }
 #pragma unroll
@@ -218,9 +225,9 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 
     for (int k = 0;; ++k) {
         long long t0 = 0;
-        if (p.dbg) t0 = clock64();
+        if (BD_PROF && p.dbg) t0 = clock64();
         if (!bd_mbar_wait(&mbar[k % BD_NRING], (unsigned) ((k / BD_NRING) & 1))) atomicOr(p.err, 4);
-        if (p.dbg) t_wait += clock64() - t0;
+        if (BD_PROF && p.dbg) t_wait += clock64() - t0;
         const BdDesc d = desc[k % BD_NRING];
         if (d.rows == 0) break;
         int *hull_k = hull + (k & 1) * (2 * BD_NCW);
@@ -239,7 +246,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 #else
             const bool st = interior && x0 >= d.elo && x0 <= d.ehi;
 #endif
-            leftb = x0 == 0;
+            leftfloor = x0 == 0 ? inf : -inf;
 
             int slot = d.slot0 + (c >> 7);
             if (slot >= SL::nslot) slot -= SL::nslot;
@@ -264,7 +271,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
             if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
             long long tr0 = 0;
-            if (p.dbg) tr0 = clock64();
+            if (BD_PROF && p.dbg) tr0 = clock64();
             unsigned go = (unsigned) d.y0 * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
             int r = 0;
             if (d.y0 == 0) { // row 0 of the image: m = en (A.8; true of every cell of the row, evaluated or not)
@@ -286,7 +293,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             const unsigned char *p0 = pp - (size_t) r * BD_BW;
             *reinterpret_cast<float4 *>(vr + (r & 3) * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]); // row r-1
             bool pend = false;
-#pragma unroll 2
+#pragma unroll 4
             for (; r < rows; ++r) {
                 const float4 ce = e4, co = o4, cg = g4;
                 ep += BD_BW, op += BD_BW, gq += BD_BW;
@@ -330,7 +337,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 ++n_slow;
             }
             const float4 po = *reinterpret_cast<const float4 *>(o0 + (size_t) (rows - 1) * BD_BW); // old values of the last row
-            if (p.dbg) {
+            if (BD_PROF && p.dbg) {
                 t_rows += clock64() - tr0;
                 n_rows += rows;
             }
@@ -358,13 +365,13 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             hull_k[2 * seg + 1] = INT_MIN;
         }
         long long t1 = 0;
-        if (p.dbg) t1 = clock64();
+        if (BD_PROF && p.dbg) t1 = clock64();
         bd_bar_chunk();
-        if (p.dbg) t_bar += clock64() - t1;
+        if (BD_PROF && p.dbg) t_bar += clock64() - t1;
         hl_lo = d.hlo;
         hl_hi = d.hhi;
     }
-    if (p.dbg && lane == 0) {
+    if (BD_PROF && p.dbg && lane == 0) {
         atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 0 : 2], (unsigned long long) t_wait);
         atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 1 : 3], (unsigned long long) t_bar);
         if (seg == 0) {
@@ -401,7 +408,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
 
     // plans chunk kp and issues its tiles; false when it has to wait for ring space
     auto plan_issue = [&]() -> bool {
-        const long long tp0 = p.dbg ? clock64() : 0;
+        const long long tp0 = (BD_PROF && p.dbg) ? clock64() : 0;
         BdDesc *dd = desc + (kp % BD_NRING);
         void *mb = &mbar[kp % BD_NRING];
         int end_y = -1;
@@ -477,7 +484,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             ya += rows;
         }
         ++kp;
-        if (p.dbg) t_plan += clock64() - tp0;
+        if (BD_PROF && p.dbg) t_plan += clock64() - tp0;
         return true;
     };
 
@@ -506,7 +513,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
     }
     if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
     if (lane == 0 && p.fixn) *p.fixn = kp - 1; // chunks whose parents k_fix_parents has to recompute (the last is the end marker)
-    if (p.dbg && lane == 0) {
+    if (BD_PROF && p.dbg && lane == 0) {
         atomicAdd((unsigned long long *) &p.dbg[4], (unsigned long long) kp);
         atomicAdd((unsigned long long *) &p.dbg[9], (unsigned long long) t_plan);
     }
@@ -684,7 +691,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const _
     __syncthreads();
     const int y_from = misc[0];
     if (y_from < p.h) {
-        if (p.dbg && tid == 0) atomicAdd((unsigned long long *) &p.dbg[14], (unsigned long long) (p.h - y_from));
+        if (BD_PROF && p.dbg && tid == 0) atomicAdd((unsigned long long *) &p.dbg[14], (unsigned long long) (p.h - y_from));
         constexpr int cap = BD_RING_BYTES / 8; // two row buffers in the tile ring, which nobody uses any more
         if (p.pitch <= cap)
             bd_rows_wide<D, RIG, LR>(p, y_from, misc[1], misc[2], reinterpret_cast<float *>(ring), reinterpret_cast<float *>(ring) + cap, s_red);

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(MF_THREADS) k_mmap_full_strips(const DevP p, i
         go += p.pitch;
         r = 1;
     }
+#pragma unroll 4
     for (; r < rows; ++r, go += p.pitch) {
         float4 e4 = make_float4(inf, inf, inf, inf), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
         if (inmem) {
