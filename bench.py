@@ -315,8 +315,8 @@ def main():
         dur_s = stages[dom]["us_per_launch"] * 1e-6
         achieved = alg_bytes / dur_s / 1e9
         # dram__bytes_read.sum + dram__bytes_write.sum of one k_band_dp launch, from the committed ncu --set full capture
-        # (profiles/r01_band_dp_ncu_summary.txt: 7.71 MB read, 0 written back before the kernel ends -- the maps are L2-resident)
-        traffic = 7.71e6 if dom == "mmap_update" else None
+        # (profiles/r01_band_dp_ncu_summary.txt: 7.73 MB read, 0 written back before the kernel ends -- the maps are L2-resident)
+        traffic = 7.73e6 if dom == "mmap_update" else None
         mf = stages.get("mmap_full")
         roof_full = None
         if mf:
