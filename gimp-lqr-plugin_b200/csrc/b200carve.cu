@@ -130,6 +130,10 @@ struct B200Carver {
     int pitch = 0;
     int *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
     unsigned *nrg_pack = nullptr;
+    int *dyn_d = nullptr;                     // device seam counter of the running build session (DevP::dyn)
+    int w_epoch = 0, vs_epoch = 0;            // width / visibility level at the session's first seam
+    cudaGraphExec_t seam_graph[2] = {nullptr, nullptr}; // one iteration of the per-seam loop, per leftright value
+    bool use_graph = true;                    // B200C_GRAPH=0: launch the kernels one by one
     int4 *fix_d = nullptr;                    // band-DP chunk table for k_fix_parents (+ its count)
     int *fixn_d = nullptr;
     alignas(64) BdMaps maps;                  // TMA tensor maps over the compact arrays (band DP)
@@ -187,6 +191,7 @@ int check_launch(const char *what)
 DevP view(const B200Carver *c)
 {
     DevP p;
+    p.dyn = nullptr;
     p.w = c->w;
     p.h = c->h;
     p.w0 = c->w0;
@@ -223,6 +228,15 @@ DevP view(const B200Carver *c)
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
+    return p;
+}
+
+// the argument block of the per-seam kernels: the same for every seam of a build session (carver_kernels.cuh seam_view)
+DevP view_dyn(const B200Carver *c)
+{
+    DevP p = view(c);
+    p.w = c->w_epoch;
+    p.dyn = c->dyn_d;
     return p;
 }
 
@@ -518,58 +532,106 @@ int inflate(B200Carver *c, int l)
 }
 
 // ---- A.7 per-seam loop ------------------------------------------------------------------------------------
-int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
+// One iteration of the per-seam loop as kernel launches (A.7): backtrack, carve, band energy [, band DP + parent
+// fix-up].  Every kernel takes the session's argument block (view_dyn) and reads the seam number from device memory,
+// so the launches are identical for every seam -- captured once, they are replayed as a CUDA graph.
+int launch_seam_kernels(B200Carver *c, bool with_update)
 {
     cudaStream_t s = c->stream;
     const bool fast = fast_path(c);
-    if (fast) B_TRY(raise_smem_limits());
+    const DevP p = view_dyn(c);
     {
         StageScope sc("vpath", s);
         if (fast)
-            k_seam_path<<<1, SP_THREADS, sp_smem_bytes(), s>>>(view(c));
+            k_seam_path<<<1, SP_THREADS, sp_smem_bytes(), s>>>(p);
         else
-            k_vpath<<<1, 1024, 0, s>>>(view(c));
+            k_vpath<<<1, 1024, 0, s>>>(p);
         B_TRY(check_launch("k_vpath"));
     }
-    const int vs_value = l + c->max_level - 1;
-    c->level++;
-    c->w--;
     {
         StageScope sc("carve", s);
-        k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(view(c), vs_value);
+        k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(p, c->vs_epoch);
         B_TRY(check_launch("k_carve"));
     }
-    c->nrg_uptodate = false;
-    if (c->w > 1) {
-        {
-            StageScope sc("energy_band", s);
-            k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(view(c));
-            B_TRY(check_launch("k_energy_band"));
-        }
-        c->nrg_uptodate = true;
-        if (c->lr_freq && ((l - c->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0) {
-            c->leftright ^= 1;
-            B_TRY(build_mmap(c));
-        } else {
-            const bool band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
-            {
-                StageScope sc("mmap_update", s);
-                if (band)
-                    launch_band_dp(c, false);
-                else
-                    k_mmap_update<<<1, 512, 0, s>>>(view(c));
-                B_TRY(check_launch("k_mmap_update"));
-            }
-            if (band) {
-                StageScope sc("fix_parents", s);
-                launch_band_dp(c, true);
-                B_TRY(check_launch("k_fix_parents"));
-            }
-        }
+    {
+        StageScope sc("energy_band", s);
+        k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(p);
+        B_TRY(check_launch("k_energy_band"));
+    }
+    if (!with_update) return B200C_OK;
+    const bool band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
+    {
+        StageScope sc("mmap_update", s);
+        if (band)
+            launch_band_dp(c, false);
+        else
+            k_mmap_update<<<1, 512, 0, s>>>(p);
+        B_TRY(check_launch("k_mmap_update"));
+    }
+    if (band) {
+        StageScope sc("fix_parents", s);
+        launch_band_dp(c, true);
+        B_TRY(check_launch("k_fix_parents"));
+    }
+    return B200C_OK;
+}
+
+void drop_seam_graphs(B200Carver *c)
+{
+    for (auto &g : c->seam_graph) {
+        if (g) cudaGraphExecDestroy(g);
+        g = nullptr;
+    }
+}
+
+int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
+{
+    cudaStream_t s = c->stream;
+    if (fast_path(c)) B_TRY(raise_smem_limits());
+    const bool last = c->w - 1 <= 1; // the image is about to be one pixel wide
+    const bool lr_switch = !last && c->lr_freq && ((l - c->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0;
+    if (last) {
+        StageScope sc("vpath", s);
+        if (fast_path(c))
+            k_seam_path<<<1, SP_THREADS, sp_smem_bytes(), s>>>(view_dyn(c));
+        else
+            k_vpath<<<1, 1024, 0, s>>>(view_dyn(c));
+        B_TRY(check_launch("k_vpath"));
+        StageScope sc2("carve", s);
+        k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch);
+        B_TRY(check_launch("k_carve"));
+    } else if (lr_switch || !c->use_graph || g_timing) {
+        B_TRY(launch_seam_kernels(c, !lr_switch));
     } else {
+        cudaGraphExec_t &exec = c->seam_graph[c->leftright & 1];
+        if (!exec) {
+            cudaGraph_t graph = nullptr;
+            CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+            const int rc = launch_seam_kernels(c, true);
+            const cudaError_t e = cudaStreamEndCapture(s, &graph);
+            if (rc != B200C_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (e != cudaSuccess) return fail(B200C_ERROR, "cudaStreamEndCapture", e);
+            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e2 != cudaSuccess) return fail(B200C_ERROR, "cudaGraphInstantiate", e2);
+        } else {
+            g_launches += (fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX) ? 5 : 4;
+        }
+        CU_TRY(cudaGraphLaunch(exec, s));
+    }
+    c->level++;
+    c->w--;
+    c->nrg_uptodate = !last;
+    if (last) {
         StageScope sc("finish_vsmap", s);
-        k_finish_vsmap<<<(c->h + 255) / 256, 256, 0, s>>>(view(c));
+        k_finish_vsmap<<<(c->h + 255) / 256, 256, 0, s>>>(view_dyn(c));
         B_TRY(check_launch("k_finish_vsmap"));
+    } else if (lr_switch) {
+        c->leftright ^= 1;
+        B_TRY(build_mmap(c));
     }
     return B200C_OK;
 }
@@ -594,6 +656,11 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
     if (c->lr_freq) lr_switch_interval = (depth - c->max_level - 1) / (int) c->lr_freq + 1;
     if (update_step < 1) update_step = 1;
     const int first = c->max_level;
+    // session: the per-seam kernels get one argument block and count the seams themselves (DevP::dyn starts at -1)
+    drop_seam_graphs(c);
+    c->w_epoch = c->w;
+    c->vs_epoch = first + c->max_level - 1;
+    CU_TRY(cudaMemsetAsync(c->dyn_d, 0xff, sizeof(int), c->stream));
     for (int l = first; l < depth; ++l) {
         if (progress && ((l - first) % update_step) == 0) {
             if (progress(user, l - first)) return fail(B200C_CANCEL, "cancelled by progress callback");
@@ -769,7 +836,9 @@ struct PinnedBuf {
 };
 std::mutex g_pin_mu;
 std::vector<PinnedBuf> g_pin_free;
-constexpr size_t kPinKeep = 6; // buffers kept for reuse
+constexpr size_t kPinKeepBytes = 2ull << 30; // pinned bytes kept for reuse (cudaFreeHost synchronises the device:
+                                             // with many carvers in flight a free per image serialises them all)
+size_t g_pin_bytes = 0;
 
 int pinned_acquire(size_t bytes, uint8_t **out, size_t *cap)
 {
@@ -781,6 +850,7 @@ int pinned_acquire(size_t bytes, uint8_t **out, size_t *cap)
         if (best >= 0) {
             *out = g_pin_free[best].p;
             *cap = g_pin_free[best].cap;
+            g_pin_bytes -= *cap;
             g_pin_free.erase(g_pin_free.begin() + best);
             return B200C_OK;
         }
@@ -796,8 +866,9 @@ void pinned_release(uint8_t *p, size_t cap)
     if (!p) return;
     {
         std::lock_guard<std::mutex> lk(g_pin_mu);
-        if (g_pin_free.size() < kPinKeep) {
+        if (g_pin_bytes + cap <= kPinKeepBytes) {
             g_pin_free.push_back({p, cap});
+            g_pin_bytes += cap;
             return;
         }
     }
@@ -946,6 +1017,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
     {
         const char *g = getenv("B200C_GENERIC");
         c->generic = g && atoi(g) != 0;
+        const char *gr = getenv("B200C_GRAPH");
+        if (gr) c->use_graph = atoi(gr) != 0;
         const char *ms = getenv("B200C_BD_MAXSEG");
         if (ms && atoi(ms) > 0) c->bd_maxseg = atoi(ms);
 
@@ -1066,6 +1139,8 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->fix_d);
     dfree(c, c->fixn_d);
     dfree(c, c->err_d);
+    dfree(c, c->dyn_d);
+    drop_seam_graphs(c);
     if (c->cells_d) {
         unsigned long long n = 0;
         if (cudaMemcpyAsync(&n, c->cells_d, sizeof n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
@@ -1111,6 +1186,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->fixn_d, 1, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
+    B_TRY(dalloc(c, &c->dyn_d, 1, true));
     if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));
     c->delta_x = delta_x;
     c->rigidity = rigidity;

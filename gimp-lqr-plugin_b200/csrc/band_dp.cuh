@@ -524,8 +524,9 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
 // cell of its band (A.8); for a kept cell the arg-min equals the stored parent, so writing the arg-min everywhere
 // in the (larger) evaluated range is the same map.
 template <int D, bool RIG, bool LR>
-__global__ void __launch_bounds__(256) k_fix_parents(const DevP p)
+__global__ void __launch_bounds__(256) k_fix_parents(const DevP pin)
 {
+    const DevP p = seam_view(pin, 1);
     if ((int) blockIdx.x >= *p.fixn) return;
     const int4 f = p.fix[blockIdx.x];
     const int y0 = f.x, rows = f.y, elo = f.z, ehi = f.w;
@@ -661,8 +662,9 @@ __device__ void bd_rows_wide(const DevP &p, int y_from, int lo, int hi, float *p
 }
 
 template <int D, bool RIG, bool LR>
-__global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP p, const __grid_constant__ BdMaps tm)
+__global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const __grid_constant__ BdMaps tm)
 {
+    const DevP p = seam_view(pin, 1);
     extern __shared__ __align__(128) unsigned char bd_smem[];
     unsigned char *ring = bd_smem;
     unsigned *nrg = reinterpret_cast<unsigned *>(ring + BD_RING_BYTES);

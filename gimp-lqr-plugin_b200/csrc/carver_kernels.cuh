@@ -57,8 +57,25 @@ struct DevP {
     unsigned *nrg_pack; // per row: nrg_xmin | (nrg_xmax - nrg_xmin + 1) << 24, for the band DP's window planner
     unsigned long long *cells; // running count of band cells evaluated by the incremental DP
     long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
+    int *dyn;          // seam counter of the current build session, or NULL: see seam_view()
     int *err;          // device error word: bit 0 band left its staged window, bit 1 backtrack met a dead parent, bit 2 bulk copy timed out
 };
+
+// The kernels of the per-seam loop are launched with the SAME arguments for every seam of a session (which is what lets
+// the host replay them as one CUDA graph): p.w is the width before the session's first seam, and the seam counter
+// *p.dyn -- advanced by the backtrack kernel, the first of every iteration -- tells how many seams have gone since.
+// post = 0: the width before this iteration's carve (backtrack); post = 1: after it (carve, energy band, DP).
+__device__ __forceinline__ DevP seam_view(DevP p, int post, int *seam = nullptr)
+{
+    if (p.dyn) {
+        const int i = *reinterpret_cast<volatile int *>(p.dyn);
+        p.w -= i + post;
+        if (seam) *seam = i;
+    } else if (seam) {
+        *seam = 0;
+    }
+    return p;
+}
 
 // ------------------------------------------------------------------------------------------------
 // A.2 pixel reading: 8-bit channel / 255 in double; brightness = mean of colour channels, luma =
@@ -185,8 +202,9 @@ __global__ void __launch_bounds__(256) k_energy_full(DevP p)
 // K1b -- A.8 energy band after a carve (lqr_carver_update_emap): one warp per row derives the row's
 // [nrg_xmin, nrg_xmax] from the seam positions of rows y-radius..y+radius and recomputes that band.
 // p.w is the width AFTER the carve; vpath_x is in pre-carve coordinates.
-__global__ void __launch_bounds__(256) k_energy_band(DevP p)
+__global__ void __launch_bounds__(256) k_energy_band(DevP pin)
 {
+    const DevP p = seam_view(pin, 1);
     const int lane = threadIdx.x & 31;
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (y >= p.h) return;
@@ -278,8 +296,9 @@ __device__ void update_rows_generic(const DevP &p, int y_from, int lo, int hi, i
     if (tid == 0 && p.cells) atomicAdd(p.cells, cells);
 }
 
-__global__ void __launch_bounds__(512) k_mmap_update(DevP p)
+__global__ void __launch_bounds__(512) k_mmap_update(DevP pin)
 {
+    const DevP p = seam_view(pin, 1);
     __shared__ int s_red[64];
     update_rows_generic(p, 0, INT_MAX, INT_MIN, s_red);
 }
@@ -331,10 +350,13 @@ __device__ __forceinline__ int last_row_argmin(const DevP &p, float *s_v, int *s
     return bx < 0 ? 0 : bx;
 }
 
-__global__ void __launch_bounds__(1024) k_vpath(DevP p)
+__global__ void __launch_bounds__(1024) k_vpath(DevP pin)
 {
     __shared__ float s_v[32];
     __shared__ int s_x[32];
+    if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam
+    __syncthreads();
+    const DevP p = seam_view(pin, 0);
     int x = last_row_argmin(p, s_v, s_x);
     if (threadIdx.x != 0) return;
     for (int y = p.h - 1; y >= 0; --y) {
@@ -358,8 +380,11 @@ __global__ void __launch_bounds__(1024) k_vpath(DevP p)
 // slot another thread already overwrote.
 #define B200C_CARVE_THREADS 256
 #define B200C_CARVE_ITEMS 4
-__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP p, int vs_value)
+__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP pin, int vs_value)
 {
+    int seam;
+    const DevP p = seam_view(pin, 1, &seam);
+    vs_value += seam; // the level this seam's pixels get in the visibility map
     const int y = blockIdx.x;
     const size_t o = (size_t) y * p.pitch;
     int *raw = p.raw + (size_t) y * p.raw_stride;
@@ -411,8 +436,9 @@ __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP p, int vs_va
 }
 
 // A.7 finish_vsmap: the image is one pixel wide; the survivors get the largest level.
-__global__ void k_finish_vsmap(DevP p)
+__global__ void k_finish_vsmap(DevP pin)
 {
+    const DevP p = seam_view(pin, 1);
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y < p.h) p.vs[p.raw[(size_t) y * p.raw_stride]] = p.w0;
 }

@@ -97,8 +97,11 @@ __device__ __forceinline__ void sp_build_jumps(const signed char *tile, short *j
     }
 }
 
-__global__ void __launch_bounds__(SP_THREADS, 1) k_seam_path(DevP p)
+__global__ void __launch_bounds__(SP_THREADS, 1) k_seam_path(DevP pin)
 {
+    if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam (this kernel is the first of every iteration)
+    __syncthreads();
+    const DevP p = seam_view(pin, 0);
     extern __shared__ __align__(128) unsigned char sp_smem[];
     signed char *tiles = reinterpret_cast<signed char *>(sp_smem);                  // [3][SP_TILE_BYTES]
     short *jumps = reinterpret_cast<short *>(sp_smem + 3 * SP_TILE_BYTES);           // [2][SP_JUMP_BYTES / 2]

@@ -71,10 +71,11 @@ def main():
         # config 4 with several images in flight on this GPU: one host thread + one CUDA stream per image (the engine
         # gives every carver its own stream); the row-serial chains of different images overlap on different SMs
         import threading
+        harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
         w, h, n = 1920, 1080, 100
         nthreads = int(os.environ.get("B200C_THREADS", "16"))
         imgs = [synth.smooth_noise(w, h, 4, seed=synth.SEED + i) for i in range(batch)]
-        run(lib, imgs[0], V(new_width=w - n, new_height=h))
+        harness.render(pkg.SHIM_PATH, imgs[0], V(new_width=w - n, new_height=h))
         todo = list(range(batch))
         lock = threading.Lock()
         shapes = []
@@ -85,8 +86,9 @@ def main():
                     if not todo:
                         return
                     i = todo.pop()
-                res = render.render_noninteractive(lib, imgs[i], V(new_width=w - n, new_height=h))
-                shapes.append(res.image.shape)
+                # the plug-in's call sequence in C (tests/harness): one ctypes call per image, so the GIL is not in the way
+                out_img, _, _ = harness.render(pkg.SHIM_PATH, imgs[i], V(new_width=w - n, new_height=h))
+                shapes.append(out_img.shape)
 
         t0 = time.perf_counter()
         ts = [threading.Thread(target=worker) for _ in range(nthreads)]
