@@ -14,6 +14,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <functional>
 #include <map>
@@ -66,6 +67,16 @@ struct StageStat {
     long launches = 0;
 };
 std::mutex g_stage_mu;
+
+// host-side wall time per phase of the API calls, summed over all threads (b200c_hostprof_ms; diagnostics only)
+std::atomic<long long> g_hostprof_ns[16];
+struct HostScope {
+    int i;
+    std::chrono::steady_clock::time_point t0;
+    explicit HostScope(int idx) : i(idx), t0(std::chrono::steady_clock::now()) {}
+    ~HostScope() { g_hostprof_ns[i] += std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 std::map<std::string, StageStat> g_stages;
 bool g_timing = false;
 
@@ -109,6 +120,100 @@ thread_local int g_device = -1;
 thread_local cudaStream_t g_ext_stream = nullptr;
 thread_local bool g_use_ext_stream = false;
 
+// ---- lanes: a stream, the upload events and the instantiated per-seam graphs, pooled per process.  Creating and
+// destroying these for every image goes through the driver's global lock; with a dozen carvers in flight on host
+// threads that cost tens of ms per image -- more than the seams.  A carver borrows a lane for its
+// lifetime; graph executables are re-targeted at the next carver's buffers with cudaGraphExecUpdate.
+struct LaneGraph {
+    cudaGraph_t graph = nullptr; // owns the nodes whose handles address the executable's nodes
+    cudaGraphExec_t exec = nullptr;
+    cudaGraphNode_t node[5] = {};
+    int n = 0;
+};
+void lane_graph_reset(LaneGraph *g)
+{
+    if (g->exec) cudaGraphExecDestroy(g->exec);
+    if (g->graph) cudaGraphDestroy(g->graph);
+    *g = LaneGraph();
+}
+struct Lane {
+    int device = 0;
+    bool pooled = false; // owns its stream and goes back to the pool
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t done = nullptr; // blocking-sync event: see carver_sync()
+    std::map<int, LaneGraph> graphs; // per kernel set of the per-seam loop (graph_key)
+};
+std::mutex g_lane_mu;
+std::vector<Lane *> g_lane_free;
+std::atomic<int> g_lanes_busy{0}; // carvers alive in this process
+constexpr size_t kLaneKeep = 64;
+
+void lane_destroy(Lane *l)
+{
+    if (!l) return;
+    for (auto &kv : l->graphs) lane_graph_reset(&kv.second);
+    for (cudaEvent_t e : l->ev)
+        if (e) cudaEventDestroy(e);
+    if (l->done) cudaEventDestroy(l->done);
+    if (l->pooled && l->stream) cudaStreamDestroy(l->stream);
+    delete l;
+}
+
+// ext != nullptr: a private lane around the caller's stream (b200c_set_stream)
+Lane *lane_acquire(int device, bool use_ext, cudaStream_t ext)
+{
+    ++g_lanes_busy;
+    if (!use_ext) {
+        std::lock_guard<std::mutex> lk(g_lane_mu);
+        for (size_t i = 0; i < g_lane_free.size(); ++i)
+            if (g_lane_free[i]->device == device) {
+                Lane *l = g_lane_free[i];
+                g_lane_free.erase(g_lane_free.begin() + i);
+                return l;
+            }
+    }
+    Lane *l = new (std::nothrow) Lane();
+    if (!l) return nullptr;
+    l->device = device;
+    l->pooled = !use_ext;
+    l->stream = ext;
+    bool ok = use_ext || cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&l->ev[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+    if (!ok) {
+        --g_lanes_busy;
+        lane_destroy(l);
+        return nullptr;
+    }
+    return l;
+}
+
+// the lane's stream must be idle
+void lane_release(Lane *l)
+{
+    if (!l) return;
+    --g_lanes_busy;
+    if (l->pooled) {
+        std::lock_guard<std::mutex> lk(g_lane_mu);
+        if (g_lane_free.size() < kLaneKeep) {
+            g_lane_free.push_back(l);
+            return;
+        }
+    }
+    lane_destroy(l);
+}
+
+// With about as many carvers in flight as there are cores (a batch host: one thread per image), threads that spin in
+// cudaStreamSynchronize starve the ones that have work to enqueue; waits then sleep on a blocking event instead, and
+// the upload helpers stay out of the way.  A lone image keeps the spinning wait (lowest latency) and the helpers.
+bool host_crowded()
+{
+    static const int cores = (int) std::thread::hardware_concurrency();
+    return g_lanes_busy.load(std::memory_order_relaxed) * 2 > (cores > 0 ? cores : 1);
+}
+bool host_shared() { return g_lanes_busy.load(std::memory_order_relaxed) > 2; }
+
 } // namespace
 
 struct B200Carver {
@@ -132,7 +237,9 @@ struct B200Carver {
     unsigned *nrg_pack = nullptr;
     int *dyn_d = nullptr;                     // device seam counter of the running build session (DevP::dyn)
     int w_epoch = 0, vs_epoch = 0;            // width / visibility level at the session's first seam
-    cudaGraphExec_t seam_graph[2] = {nullptr, nullptr}; // one iteration of the per-seam loop, per leftright value
+    Lane *lane = nullptr;                     // stream, upload events and per-seam graph executables (pooled)
+    bool graph_fresh[2] = {false, false};     // the lane's graph for this leftright value points at this session
+    LaneGraph *graph[2] = {nullptr, nullptr};
     bool use_graph = true;                    // B200C_GRAPH=0: launch the kernels one by one
     int4 *fix_d = nullptr;                    // band-DP chunk table for k_fix_parents (+ its count)
     int *fixn_d = nullptr;
@@ -140,7 +247,6 @@ struct B200Carver {
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
     long long *dbg_d = nullptr;               // role cycle counters (B200C_DBG=1)
-    bool owns_stream = true;
     bool generic = false;                     // B200C_GENERIC=1: only the generic single-CTA kernels
     int bd_maxseg = 1 << 20;                  // B200C_BD_MAXSEG: test knob, forces the band DP's wide-window path
 
@@ -179,6 +285,17 @@ int use_device(const B200Carver *c)
 {
     CU_TRY(cudaSetDevice(c->device));
     return B200C_OK;
+}
+
+// waits for the carver's queue: spinning, or asleep on the lane's blocking event when the host is crowded
+cudaError_t carver_sync(const B200Carver *c)
+{
+    const Lane *l = c->lane ? c->lane : (c->root ? c->root->lane : nullptr);
+    if (l && l->done && host_crowded()) {
+        const cudaError_t e = cudaEventRecord(l->done, c->stream);
+        return e != cudaSuccess ? e : cudaEventSynchronize(l->done);
+    }
+    return cudaStreamSynchronize(c->stream);
 }
 
 int check_launch(const char *what)
@@ -372,6 +489,12 @@ int raise_smem_limits()
             if (e != cudaSuccess && err == cudaSuccess) err = e;
         };
         set((const void *) k_seam_path, sp_smem_bytes());
+        if (getenv("B200C_CARVEOUT") && atoi(getenv("B200C_CARVEOUT"))) {
+            // experiment: one shared-memory carve-out for every kernel of the per-seam loop
+            auto co = [](const void *fn) { cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); };
+            co((const void *) k_seam_path), co((const void *) k_carve), co((const void *) k_energy_band);
+            co((const void *) k_fix_parents<1, false, false>), co((const void *) k_fix_parents<1, false, true>);
+        }
         set((const void *) k_band_dp<0, false, false>, bd_smem_bytes());
         set((const void *) k_mmap_full_strips<0, false, false>, mf_smem_bytes(0, false));
         set((const void *) k_band_dp<0, false, true>, bd_smem_bytes());
@@ -417,35 +540,31 @@ int raise_smem_limits()
     return B200C_OK;
 }
 
+// fix == false: the band DP itself (k_band_dp); fix == true: the parents of the cells it evaluated (k_fix_parents)
 template <int D>
-void launch_band_dp_d(B200Carver *c, bool fix)
+const void *band_dp_fn_d(bool fix, bool rig, bool lr)
 {
-    const DevP p = view(c);
-    const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
-    const size_t sm = bd_smem_bytes();
-    const int nfix = (c->h + 7) / 8;
     if (fix) {
-        if (rig && lr) k_fix_parents<D, true, true><<<nfix, 256, 0, c->stream>>>(p);
-        else if (rig) k_fix_parents<D, true, false><<<nfix, 256, 0, c->stream>>>(p);
-        else if (lr) k_fix_parents<D, false, true><<<nfix, 256, 0, c->stream>>>(p);
-        else k_fix_parents<D, false, false><<<nfix, 256, 0, c->stream>>>(p);
-        return;
+        if (rig && lr) return (const void *) k_fix_parents<D, true, true>;
+        if (rig) return (const void *) k_fix_parents<D, true, false>;
+        if (lr) return (const void *) k_fix_parents<D, false, true>;
+        return (const void *) k_fix_parents<D, false, false>;
     }
-    if (rig && lr) k_band_dp<D, true, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-    else if (rig) k_band_dp<D, true, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-    else if (lr) k_band_dp<D, false, true><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
-    else k_band_dp<D, false, false><<<1, BD_THREADS, sm, c->stream>>>(p, c->maps);
+    if (rig && lr) return (const void *) k_band_dp<D, true, true>;
+    if (rig) return (const void *) k_band_dp<D, true, false>;
+    if (lr) return (const void *) k_band_dp<D, false, true>;
+    return (const void *) k_band_dp<D, false, false>;
 }
 
-// fix == false: the band DP itself (k_band_dp); fix == true: the parents of the cells it evaluated (k_fix_parents)
-void launch_band_dp(B200Carver *c, bool fix)
+const void *band_dp_fn(const B200Carver *c, bool fix)
 {
+    const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
     switch (c->delta_x) {
-        case 0: launch_band_dp_d<0>(c, fix); break;
-        case 1: launch_band_dp_d<1>(c, fix); break;
-        case 2: launch_band_dp_d<2>(c, fix); break;
-        case 3: launch_band_dp_d<3>(c, fix); break;
-        default: launch_band_dp_d<4>(c, fix); break;
+        case 0: return band_dp_fn_d<0>(fix, rig, lr);
+        case 1: return band_dp_fn_d<1>(fix, rig, lr);
+        case 2: return band_dp_fn_d<2>(fix, rig, lr);
+        case 3: return band_dp_fn_d<3>(fix, rig, lr);
+        default: return band_dp_fn_d<4>(fix, rig, lr);
     }
 }
 
@@ -532,56 +651,98 @@ int inflate(B200Carver *c, int l)
 }
 
 // ---- A.7 per-seam loop ------------------------------------------------------------------------------------
-// One iteration of the per-seam loop as kernel launches (A.7): backtrack, carve, band energy [, band DP + parent
-// fix-up].  Every kernel takes the session's argument block (view_dyn) and reads the seam number from device memory,
-// so the launches are identical for every seam -- captured once, they are replayed as a CUDA graph.
+// One iteration of the per-seam loop (A.7) is a fixed list of kernel launches: backtrack, carve, band energy [, band DP
+// + parent fix-up].  Every kernel takes the session's argument block (view_dyn) and reads the seam number from device
+// memory, so the list is the same for every seam of a session: it is launched kernel by kernel, or -- as nodes of a
+// CUDA graph built from the same list -- replayed with one call per seam.
+struct SeamLaunch {
+    const char *stage; // StageScope / error name
+    const void *fn;
+    dim3 grid, block;
+    size_t smem;
+    int second; // second kernel argument after the DevP block: 0 none, 1 the session's visibility epoch, 2 the tensor maps
+};
+
+int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[5])
+{
+    const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
+    int n = 0;
+    if (fast)
+        out[n++] = {"vpath", (const void *) k_seam_path, dim3(1), dim3(SP_THREADS), sp_smem_bytes(), 0};
+    else
+        out[n++] = {"vpath", (const void *) k_vpath, dim3(1), dim3(1024), 0, 0};
+    out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1};
+    out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + 7) / 8), dim3(256), 0, 0};
+    if (!with_update) return n;
+    if (band) {
+        out[n++] = {"mmap_update", band_dp_fn(c, false), dim3(1), dim3(BD_THREADS), bd_smem_bytes(), 2};
+        out[n++] = {"fix_parents", band_dp_fn(c, true), dim3((c->h + 7) / 8), dim3(256), 0, 0};
+    } else {
+        out[n++] = {"mmap_update", (const void *) k_mmap_update, dim3(1), dim3(512), 0, 0};
+    }
+    return n;
+}
+
 int launch_seam_kernels(B200Carver *c, bool with_update)
 {
-    cudaStream_t s = c->stream;
-    const bool fast = fast_path(c);
-    const DevP p = view_dyn(c);
-    {
-        StageScope sc("vpath", s);
-        if (fast)
-            k_seam_path<<<1, SP_THREADS, sp_smem_bytes(), s>>>(p);
-        else
-            k_vpath<<<1, 1024, 0, s>>>(p);
-        B_TRY(check_launch("k_vpath"));
-    }
-    {
-        StageScope sc("carve", s);
-        k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(p, c->vs_epoch);
-        B_TRY(check_launch("k_carve"));
-    }
-    {
-        StageScope sc("energy_band", s);
-        k_energy_band<<<(c->h + 7) / 8, 256, 0, s>>>(p);
-        B_TRY(check_launch("k_energy_band"));
-    }
-    if (!with_update) return B200C_OK;
-    const bool band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
-    {
-        StageScope sc("mmap_update", s);
-        if (band)
-            launch_band_dp(c, false);
-        else
-            k_mmap_update<<<1, 512, 0, s>>>(p);
-        B_TRY(check_launch("k_mmap_update"));
-    }
-    if (band) {
-        StageScope sc("fix_parents", s);
-        launch_band_dp(c, true);
-        B_TRY(check_launch("k_fix_parents"));
+    SeamLaunch L[5];
+    const int n = seam_launch_list(c, with_update, L);
+    DevP p = view_dyn(c);
+    int epoch = c->vs_epoch;
+    for (int i = 0; i < n; ++i) {
+        StageScope sc(L[i].stage, c->stream);
+        void *args[2] = {&p, L[i].second == 2 ? (void *) &c->maps : (void *) &epoch};
+        const cudaError_t e = cudaLaunchKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, c->stream);
+        if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
     }
     return B200C_OK;
 }
 
-void drop_seam_graphs(B200Carver *c)
+void drop_seam_graphs(B200Carver *c) { c->graph_fresh[0] = c->graph_fresh[1] = false; }
+
+// which kernels one iteration consists of: the lane keeps one executable per set
+int graph_key(const B200Carver *c)
 {
-    for (auto &g : c->seam_graph) {
-        if (g) cudaGraphExecDestroy(g);
-        g = nullptr;
+    const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
+    return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4);
+}
+
+// Points the lane's graph for the current kernel set at this carver's session: the first time the nodes are added and
+// the graph instantiated, later only the node parameters of the executable change.  (Stream capture is not used: with
+// other host threads waiting on their own streams, cudaStreamBeginCapture was measured to block for tens of ms.)
+int seam_graph_prepare(B200Carver *c, LaneGraph **out)
+{
+    LaneGraph &g = c->lane->graphs[graph_key(c)];
+    SeamLaunch L[5];
+    const int n = seam_launch_list(c, true, L);
+    DevP p = view_dyn(c);
+    int epoch = c->vs_epoch;
+    if (g.exec && g.n != n) lane_graph_reset(&g);
+    const bool fresh = g.exec == nullptr;
+    if (fresh) CU_TRY(cudaGraphCreate(&g.graph, 0));
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < n && e == cudaSuccess; ++i) {
+        void *args[2] = {&p, L[i].second == 2 ? (void *) &c->maps : (void *) &epoch};
+        cudaKernelNodeParams kp = {};
+        kp.func = const_cast<void *>(L[i].fn);
+        kp.gridDim = L[i].grid;
+        kp.blockDim = L[i].block;
+        kp.sharedMemBytes = (unsigned) L[i].smem;
+        kp.kernelParams = args;
+        if (fresh)
+            e = cudaGraphAddKernelNode(&g.node[i], g.graph, i ? &g.node[i - 1] : nullptr, i ? 1 : 0, &kp);
+        else
+            e = cudaGraphExecKernelNodeSetParams(g.exec, g.node[i], &kp);
     }
+    if (e == cudaSuccess && fresh) e = cudaGraphInstantiate(&g.exec, g.graph, 0);
+    if (e != cudaSuccess) {
+        lane_graph_reset(&g);
+        return fail(B200C_ERROR, "seam graph", e);
+    }
+    g.n = n;
+    g_launches += n;
+    *out = &g;
+    return B200C_OK;
 }
 
 int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
@@ -603,23 +764,16 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     } else if (lr_switch || !c->use_graph || g_timing) {
         B_TRY(launch_seam_kernels(c, !lr_switch));
     } else {
-        cudaGraphExec_t &exec = c->seam_graph[c->leftright & 1];
-        if (!exec) {
-            cudaGraph_t graph = nullptr;
-            CU_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-            const int rc = launch_seam_kernels(c, true);
-            const cudaError_t e = cudaStreamEndCapture(s, &graph);
-            if (rc != B200C_OK) {
-                if (graph) cudaGraphDestroy(graph);
-                return rc;
-            }
-            if (e != cudaSuccess) return fail(B200C_ERROR, "cudaStreamEndCapture", e);
-            const cudaError_t e2 = cudaGraphInstantiate(&exec, graph, 0);
-            cudaGraphDestroy(graph);
-            if (e2 != cudaSuccess) return fail(B200C_ERROR, "cudaGraphInstantiate", e2);
+        const int lr = c->leftright & 1;
+        if (!c->graph_fresh[lr]) {
+            HostScope hs(7);
+            B_TRY(seam_graph_prepare(c, &c->graph[lr]));
+            c->graph_fresh[lr] = true;
         } else {
-            g_launches += (fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX) ? 5 : 4;
+            g_launches += c->graph[lr]->n;
         }
+        cudaGraphExec_t exec = c->graph[lr]->exec;
+        HostScope hs(8);
         CU_TRY(cudaGraphLaunch(exec, s));
     }
     c->level++;
@@ -669,9 +823,10 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
     }
     {
         // the staged kernels check their own window invariants on the device; a violation is a hard error
+        HostScope hs(9);
         int err = 0;
         CU_TRY(cudaMemcpyAsync(&err, c->err_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CU_TRY(cudaStreamSynchronize(c->stream));
+        CU_TRY(carver_sync(c));
         if (err) {
             char msg[96];
             snprintf(msg, sizeof msg, "seam loop: device invariant violated (code %d)", err);
@@ -959,36 +1114,49 @@ int upload_pageable(B200Carver *c, void *dst, const void *src, size_t bytes)
     constexpr size_t kChunk = 8u << 20;
     if (bytes <= (1u << 20)) {
         CU_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
-        CU_TRY(cudaStreamSynchronize(c->stream)); // the caller may free `src` right after we return
+        CU_TRY(carver_sync(c)); // the caller may free `src` right after we return
         return B200C_OK;
     }
     uint8_t *stage[2] = {nullptr, nullptr};
     size_t cap[2] = {0, 0};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaEvent_t *ev = (c->lane ? c->lane : c->root->lane)->ev; // attached carvers run on their root's lane
     int rc = B200C_OK;
     for (int i = 0; i < 2 && rc == B200C_OK; ++i) {
+        HostScope hs(2);
         rc = pinned_acquire(kChunk, &stage[i], &cap[i]);
-        if (rc == B200C_OK && cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess)
-            rc = fail(B200C_ERROR, "upload: cudaEventCreate", cudaGetLastError());
     }
     size_t off = 0;
     for (int i = 0; rc == B200C_OK && off < bytes; ++i, off += kChunk) {
         const int b = i & 1;
         const size_t n = bytes - off < kChunk ? bytes - off : kChunk;
-        if (i >= 2 && cudaEventSynchronize(ev[b]) != cudaSuccess) rc = fail(B200C_ERROR, "upload: event", cudaGetLastError());
-        {
-            std::lock_guard<std::mutex> lk(g_upload_mu);
-            CopyHelpers::get().copy(stage[b], (const uint8_t *) src + off, n);
+        if (i >= 2) {
+            HostScope hs(6);
+            if (cudaEventSynchronize(ev[b]) != cudaSuccess) rc = fail(B200C_ERROR, "upload: event", cudaGetLastError());
         }
+        {
+            std::unique_lock<std::mutex> lk(g_upload_mu, std::defer_lock);
+            const bool helpers = !host_shared(); // several carvers in flight: their own threads are the parallelism
+            if (helpers) {
+                HostScope hw(3);
+                lk.lock();
+            }
+            HostScope hc(4);
+            if (helpers)
+                CopyHelpers::get().copy(stage[b], (const uint8_t *) src + off, n);
+            else
+                memcpy(stage[b], (const uint8_t *) src + off, n);
+        }
+        HostScope hs5(5);
         if (rc == B200C_OK && (cudaMemcpyAsync((uint8_t *) dst + off, stage[b], n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
                                cudaEventRecord(ev[b], c->stream) != cudaSuccess))
             rc = fail(B200C_ERROR, "upload: cudaMemcpyAsync", cudaGetLastError());
     }
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == B200C_OK) rc = fail(B200C_ERROR, "upload: sync", cudaGetLastError());
-    for (int i = 0; i < 2; ++i) {
-        if (ev[i]) cudaEventDestroy(ev[i]);
-        pinned_release(stage[i], cap[i]);
+    {
+        HostScope hs(6);
+        if (carver_sync(c) != cudaSuccess && rc == B200C_OK) rc = fail(B200C_ERROR, "upload: sync", cudaGetLastError());
     }
+    HostScope hs2(2);
+    for (int i = 0; i < 2; ++i) pinned_release(stage[i], cap[i]);
     return rc;
 }
 
@@ -1008,6 +1176,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
     std::call_once(once, [] {
         const char *t = getenv("B200C_TIMING");
         if (t) g_timing = atoi(t) != 0;
+        const char *bs = getenv("B200C_BLOCKING_SYNC");
+        if (bs && atoi(bs)) cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync);
     });
     B200Carver *c = new (std::nothrow) B200Carver();
     if (!c) {
@@ -1024,16 +1194,12 @@ B200Carver *carver_new_common(int width, int height, int channels)
 
     }
     c->device = g_device >= 0 ? g_device : g_device_tls_default;
-    if (g_use_ext_stream) {
-        c->stream = g_ext_stream;
-        c->owns_stream = false;
-    }
-    if (cudaSetDevice(c->device) != cudaSuccess ||
-        (c->owns_stream && cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)) {
+    if (cudaSetDevice(c->device) != cudaSuccess || !(c->lane = lane_acquire(c->device, g_use_ext_stream, g_ext_stream))) {
         fail(B200C_ERROR, "carver_new: cannot create stream", cudaGetLastError());
         delete c;
         return nullptr;
     }
+    c->stream = c->lane->stream;
     {
         // keep freed blocks in the pool: the per-resize maps are reallocated at every inflate/flatten
         static std::mutex mu;
@@ -1059,10 +1225,17 @@ B200Carver *carver_new_common(int width, int height, int channels)
 
 } // namespace
 
+// A batch host keeps one stream per image in flight; the driver maps streams onto CUDA_DEVICE_MAX_CONNECTIONS hardware
+// queues (8 by default) and streams that share a queue serialise -- measured: 16 images in flight ran their per-seam
+// chains two by two.  Ask for 32 queues unless the host process chose a value; this runs at load time, before the
+// first CUDA call of this library creates the context (no effect if the process initialised CUDA earlier).
+__attribute__((constructor)) static void b200c_on_load() { setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0); }
+
 // =================================================================================================== C ABI
 extern "C" {
 
 int b200c_abi_version(void) { return B200C_ABI_VERSION; }
+double b200c_hostprof_ms(int idx) { return idx >= 0 && idx < 16 ? g_hostprof_ns[idx].load() * 1e-6 : 0.0; }
 const char *b200c_last_error(void) { return g_err.c_str(); }
 
 int b200c_device_count(void)
@@ -1089,10 +1262,19 @@ B200Carver *b200c_carver_new(const unsigned char *rgb, int width, int height, in
         fail(B200C_ERROR, "carver_new: NULL image");
         return nullptr;
     }
-    B200Carver *c = carver_new_common(width, height, channels);
+    B200Carver *c;
+    {
+        HostScope hs(0);
+        c = carver_new_common(width, height, channels);
+    }
     if (!c) return nullptr;
     const size_t n = (size_t) width * height;
-    if (dalloc(c, &c->rgb, n * channels, false) != B200C_OK || dalloc(c, &c->vs, n, true) != B200C_OK ||
+    bool ok;
+    {
+        HostScope hs(1);
+        ok = dalloc(c, &c->rgb, n * channels, false) == B200C_OK && dalloc(c, &c->vs, n, true) == B200C_OK;
+    }
+    if (!ok ||
         upload_pageable(c, c->rgb, rgb, n * channels) != B200C_OK) { // synchronous: the caller may free `rgb` right after
         fail(B200C_NOMEM, "carver_new: device allocation / upload failed", cudaGetLastError());
         b200c_carver_destroy(c);
@@ -1122,10 +1304,10 @@ B200Carver *b200c_carver_new_device(const void *d_rgb, int width, int height, in
 void b200c_carver_destroy(B200Carver *c)
 {
     if (!c) return;
+    HostScope hs(11);
     cudaSetDevice(c->device);
     for (B200Carver *a : c->attached) b200c_carver_destroy(a);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    const bool owns_stream = c->root == nullptr && c->owns_stream; // attached carvers run on their root's queue
+    if (c->stream) carver_sync(c);
     dfree(c, c->rgb);
     if (!c->root) dfree(c, c->vs);
     free_maps(c);
@@ -1144,14 +1326,14 @@ void b200c_carver_destroy(B200Carver *c)
     if (c->cells_d) {
         unsigned long long n = 0;
         if (cudaMemcpyAsync(&n, c->cells_d, sizeof n, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
-            cudaStreamSynchronize(c->stream) == cudaSuccess)
+            carver_sync(c) == cudaSuccess)
             g_update_cells += n;
     }
     dfree(c, c->cells_d);
     if (c->dbg_d) {
         long long v[16];
         if (cudaMemcpyAsync(v, c->dbg_d, sizeof v, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
-            cudaStreamSynchronize(c->stream) == cudaSuccess) {
+            carver_sync(c) == cudaSuccess) {
             fprintf(stderr, "b200c dbg:");
             for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", v[i]);
             fprintf(stderr, "\n");
@@ -1160,10 +1342,8 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->dbg_d);
     dfree(c, c->rigmap_d);
     pinned_release(c->host_out, c->host_out_cap);
-    if (c->stream) {
-        cudaStreamSynchronize(c->stream);
-        if (owns_stream) cudaStreamDestroy(c->stream);
-    }
+    if (c->stream) carver_sync(c);
+    lane_release(c->lane); // attached carvers gave theirs back when they joined the root's queue
     delete c;
 }
 
@@ -1205,11 +1385,11 @@ int b200c_carver_attach(B200Carver *root, B200Carver *aux)
     if (root->device != aux->device) return fail(B200C_ERROR, "carver_attach: carvers live on different devices");
     B_TRY(use_device(root));
     // the aux carver's own queue must be idle before it starts sharing the root's maps and stream
-    CU_TRY(cudaStreamSynchronize(aux->stream));
+    CU_TRY(carver_sync(aux));
     dfree(aux, aux->vs);
-    CU_TRY(cudaStreamSynchronize(aux->stream));
-    if (aux->owns_stream) cudaStreamDestroy(aux->stream);
-    aux->owns_stream = false;
+    CU_TRY(carver_sync(aux));
+    lane_release(aux->lane);
+    aux->lane = nullptr;
     aux->stream = root->stream; // one queue per carver family keeps every structural op ordered
     aux->vs = root->vs;
     aux->root = root;
@@ -1282,7 +1462,7 @@ static int mask_common(B200Carver *c, const unsigned char *rgb, int channels, in
             B_TRY(check_launch("mask kernel"));
         }
         dfree(c, d_mask);
-        CU_TRY(cudaStreamSynchronize(c->stream)); // the caller frees the mask right after (io_functions.c:97,128)
+        CU_TRY(carver_sync(c)); // the caller frees the mask right after (io_functions.c:97,128)
     }
     if (is_bias) c->nrg_uptodate = false;
     if (was_transposed != c->transposed) B_TRY(transpose(c));
@@ -1369,6 +1549,7 @@ static int readout_to(B200Carver *c, uint8_t *d_out)
 int b200c_carver_readout(B200Carver *c, const unsigned char **host_pixels)
 {
     if (!c || !host_pixels) return fail(B200C_ERROR, "readout: NULL");
+    HostScope hs(10);
     B_TRY(use_device(c));
     const size_t bytes = (size_t) c->w * c->h * c->channels;
     B_TRY(ensure_host_out(c, bytes));
@@ -1377,7 +1558,7 @@ int b200c_carver_readout(B200Carver *c, const unsigned char **host_pixels)
     B_TRY(readout_to(c, d_out));
     CU_TRY(cudaMemcpyAsync(c->host_out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
     dfree(c, d_out);
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(carver_sync(c));
     *host_pixels = c->host_out;
     return B200C_OK;
 }
@@ -1405,7 +1586,7 @@ int b200c_carver_vmap(B200Carver *c, int *out_host)
     }
     CU_TRY(cudaMemcpyAsync(out_host, d_out, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     dfree(c, d_out);
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(carver_sync(c));
     return B200C_OK;
 }
 
@@ -1426,7 +1607,7 @@ int b200c_carver_true_energy(B200Carver *c, float *out_host)
     }
     CU_TRY(cudaMemcpyAsync(out_host, d_out, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     dfree(c, d_out);
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(carver_sync(c));
     return B200C_OK;
 }
 
@@ -1445,7 +1626,7 @@ int b200c_carver_sync(B200Carver *c)
 {
     if (!c) return fail(B200C_ERROR, "sync: NULL");
     B_TRY(use_device(c));
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(carver_sync(c));
     return B200C_OK;
 }
 
@@ -1459,7 +1640,7 @@ int b200c_debug_build(B200Carver *c, int n_seams)
     B_TRY(gather_rig(c));
     B_TRY(build_mmap(c));
     if (n_seams > 0) B_TRY(build_vsmap(c, c->max_level + n_seams, 1, nullptr, nullptr, false));
-    CU_TRY(cudaStreamSynchronize(c->stream));
+    CU_TRY(carver_sync(c));
     return B200C_OK;
 }
 
@@ -1481,7 +1662,7 @@ long b200c_debug_fetch(B200Carver *c, int what, void *out, long cap)
             k_export_physical<<<grid, 256, 0, c->stream>>>(view(c), what - B200C_DBG_EN, tmp);
             if (n > cap) n = cap;
             const bool ok = cudaMemcpyAsync(out, tmp, (size_t) n * 4, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
-                            cudaStreamSynchronize(c->stream) == cudaSuccess;
+                            carver_sync(c) == cudaSuccess;
             dfree(c, tmp);
             return ok ? n : -1;
         }
@@ -1494,7 +1675,7 @@ long b200c_debug_fetch(B200Carver *c, int what, void *out, long cap)
     }
     if (!src) return 0;
     if (n > cap) n = cap;
-    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return -1;
+    if (carver_sync(c) != cudaSuccess) return -1;
     if (cudaMemcpy(out, src, (size_t) n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
     return n;
 }

@@ -9,6 +9,7 @@
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -56,14 +57,12 @@ static void *try_open(const char *path)
         }                                                                         \
     } while (0)
 
-static int engine_load(void)
+static int engine_load_once(void)
 {
     Dl_info info;
     char path[4096];
-    if (g_eng_state) return g_eng_state > 0;
-    g_eng_state = -1;
     g_eng.dl = try_open(getenv("B200CARVE_LIB"));
-    if (!g_eng.dl && dladdr((void *) &engine_load, &info) && info.dli_fname) {
+    if (!g_eng.dl && dladdr((void *) &engine_load_once, &info) && info.dli_fname) {
         const char *slash = strrchr(info.dli_fname, '/');
         size_t dir = slash ? (size_t) (slash - info.dli_fname) + 1 : 0;
         if (dir + 32 < sizeof path) {
@@ -99,8 +98,16 @@ static int engine_load(void)
         fprintf(stderr, "liblqr-1 (b200): engine ABI %d, shim built for %d\n", g_eng.abi_version(), B200C_ABI_VERSION);
         return 0;
     }
-    g_eng_state = 1;
     return 1;
+}
+
+/* independent carvers may be driven from different host threads (a batch host): load exactly once */
+static pthread_once_t g_eng_once = PTHREAD_ONCE_INIT;
+static void engine_load_thunk(void) { g_eng_state = engine_load_once() ? 1 : -1; }
+static int engine_load(void)
+{
+    pthread_once(&g_eng_once, engine_load_thunk);
+    return g_eng_state > 0;
 }
 
 /* ------------------------------------------------------------------ handle types */

@@ -60,3 +60,25 @@ def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=N
     vm = vmap.reshape(-1)[: res.vmap_width * res.vmap_height].reshape(res.vmap_height, res.vmap_width).copy() \
         if res.n_vmaps else None
     return img, vm, res
+
+
+def render_batch(lib_path: str, layers, vals: PlugInVals, in_flight: int = 16):
+    """`layers` (equal-shaped uint8 images) through the plug-in call sequence, `in_flight` of them at a time on host
+    threads created in C (harness_render_batch): no Python between the images.  Returns {"wall_ms", "ms_new", ...} with
+    the per-phase times summed over the images."""
+    layers = [np.ascontiguousarray(a, dtype=np.uint8) for a in layers]
+    h, w, bpp = layers[0].shape
+    assert all(a.shape == (h, w, bpp) for a in layers)
+    hv = HarnessVals(w, h, bpp, vals.new_width, vals.new_height, vals.pres_coeff, vals.disc_coeff, vals.rigidity,
+                     vals.delta_x, vals.enl_step, vals.nrg_func, vals.res_order, 0, int(vals.scaleback),
+                     int(vals.no_disc_on_enlarge), 0, 0)
+    lib = _load()
+    lib.harness_render_batch.restype = C.c_int
+    lib.harness_render_batch.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(HarnessVals),
+                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    ptrs = (C.c_void_p * len(layers))(*[a.ctypes.data for a in layers])
+    sums = (C.c_double * 5)()
+    wall = C.c_double()
+    if not lib.harness_render_batch(lib_path.encode(), ptrs, len(layers), in_flight, C.byref(hv), sums, C.byref(wall)):
+        raise RuntimeError("harness_render_batch failed")
+    return dict(zip(("ms_new", "ms_setup", "ms_resize", "ms_scan", "ms_total"), list(sums)), wall_ms=wall.value)

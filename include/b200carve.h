@@ -117,6 +117,11 @@ B200C_API long b200c_launch_count(void);
  * "mmap_update","inflate","readout".  Returns launches counted through *launches. */
 B200C_API double b200c_stage_ms(const char *stage, long *launches);
 B200C_API void b200c_stage_reset(void);
+/* cumulative host wall time (ms, summed over calling threads) the API calls spent in phase `idx`: 0 stream/handle
+ * creation, 1 first device allocations, 2 staging-buffer acquire/release, 3 wait for the staging helpers, 4 staging
+ * memcpy, 5 H2D enqueue, 6 H2D waits, 7 seam-graph capture + instantiate, 8 seam-graph launches, 9 end-of-loop sync,
+ * 10 readout, 11 destroy. */
+B200C_API double b200c_hostprof_ms(int idx);
 
 #ifdef __cplusplus
 }

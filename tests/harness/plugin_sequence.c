@@ -287,3 +287,72 @@ int harness_render(const char *liblqr_path, const unsigned char *layer, const Ha
     res->ms_total = t4 - t0;
     return 1;
 }
+
+/* ---- a batch of independent layers, `nthreads` of them in flight: what a batch host (batch/batch-gimp-lqr.scm run over a
+ * directory) does with one plug-in run per image.  One host thread per image in flight; every run is
+ * the call sequence above.  sums[0..4] receive the per-phase milliseconds summed over the images, *wall_ms the wall time. */
+#include <pthread.h>
+
+typedef struct {
+    const char *path;
+    const unsigned char *const *layers;
+    const HarnessVals *v;
+    int n, next, failed;
+    double sums[5];
+    pthread_mutex_t mu;
+} BatchJob;
+
+static void *batch_worker(void *arg)
+{
+    BatchJob *job = (BatchJob *) arg;
+    const HarnessVals *v = job->v;
+    const size_t ow = (size_t) (v->width > v->new_width ? v->width : v->new_width);
+    const size_t oh = (size_t) (v->height > v->new_height ? v->height : v->new_height);
+    unsigned char *out = (unsigned char *) malloc(ow * oh * v->bpp);
+    double sums[5] = {0, 0, 0, 0, 0};
+    int failed = out == NULL;
+    while (!failed) {
+        HarnessResult res;
+        int i;
+        pthread_mutex_lock(&job->mu);
+        i = job->next < job->n ? job->next++ : -1;
+        pthread_mutex_unlock(&job->mu);
+        if (i < 0) break;
+        if (!harness_render(job->path, job->layers[i], v, NULL, NULL, NULL, out, NULL, &res) ||
+            res.out_width != v->new_width || res.out_height != v->new_height)
+            failed = 1;
+        sums[0] += res.ms_new, sums[1] += res.ms_setup, sums[2] += res.ms_resize, sums[3] += res.ms_scan, sums[4] += res.ms_total;
+    }
+    free(out);
+    pthread_mutex_lock(&job->mu);
+    job->failed |= failed;
+    for (int k = 0; k < 5; k++) job->sums[k] += sums[k];
+    pthread_mutex_unlock(&job->mu);
+    return NULL;
+}
+
+int harness_render_batch(const char *liblqr_path, const unsigned char *const *layers, int n, int nthreads,
+                         const HarnessVals *v, double *sums, double *wall_ms)
+{
+    BatchJob job;
+    pthread_t th[64];
+    double t0;
+    int k;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    memset(&job, 0, sizeof job);
+    job.path = liblqr_path, job.layers = layers, job.v = v, job.n = n;
+    pthread_mutex_init(&job.mu, NULL);
+    t0 = now_ms();
+    for (k = 0; k < nthreads; k++)
+        if (pthread_create(&th[k], NULL, batch_worker, &job) != 0) {
+            nthreads = k;
+            job.failed = 1;
+            break;
+        }
+    for (k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    *wall_ms = now_ms() - t0;
+    for (k = 0; k < 5; k++) sums[k] = job.sums[k];
+    pthread_mutex_destroy(&job.mu);
+    return !job.failed;
+}

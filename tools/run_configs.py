@@ -70,32 +70,24 @@ def main():
     if 44 in which:
         # config 4 with several images in flight on this GPU: one host thread + one CUDA stream per image (the engine
         # gives every carver its own stream); the row-serial chains of different images overlap on different SMs
-        import threading
         harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
-        w, h, n = 1920, 1080, 100
+        w, h, n = 1920, 1080, int(os.environ.get("B200C_SEAMS", "100"))
         nthreads = int(os.environ.get("B200C_THREADS", "16"))
         imgs = [synth.smooth_noise(w, h, 4, seed=synth.SEED + i) for i in range(batch)]
-        harness.render(pkg.SHIM_PATH, imgs[0], V(new_width=w - n, new_height=h))
-        todo = list(range(batch))
-        lock = threading.Lock()
-        shapes = []
-
-        def worker():
-            while True:
-                with lock:
-                    if not todo:
-                        return
-                    i = todo.pop()
-                # the plug-in's call sequence in C (tests/harness): one ctypes call per image, so the GIL is not in the way
-                out_img, _, _ = harness.render(pkg.SHIM_PATH, imgs[i], V(new_width=w - n, new_height=h))
-                shapes.append(out_img.shape)
-
-        t0 = time.perf_counter()
-        ts = [threading.Thread(target=worker) for _ in range(nthreads)]
-        [t.start() for t in ts]
-        [t.join() for t in ts]
-        dt = time.perf_counter() - t0
-        assert len(shapes) == batch and all(sh == (h, w - n, 4) for sh in shapes)
+        # warm-up with the same number of images in flight: staging buffers, streams and graph executables are pooled
+        harness.render_batch(pkg.SHIM_PATH, imgs[:min(batch, 2 * nthreads)], V(new_width=w - n, new_height=h), in_flight=nthreads)
+        import ctypes as C
+        eng = C.CDLL(pkg.ENGINE_PATH)
+        eng.b200c_hostprof_ms.restype = C.c_double
+        names = ["new_common", "new_alloc", "up_pinned", "up_lockwait", "up_memcpy", "up_enqueue", "up_sync", "graph_build",
+                 "graph_launch", "loop_sync", "readout", "destroy", "g_begin", "g_launches", "g_inst_destroy", "g_end"]
+        prof0 = [eng.b200c_hostprof_ms(i) for i in range(len(names))]
+        # the plug-in's call sequence AND the host threads in C (tests/harness): no Python between the images
+        r = harness.render_batch(pkg.SHIM_PATH, imgs, V(new_width=w - n, new_height=h), in_flight=nthreads)
+        dt = r["wall_ms"] * 1e-3
+        out["config4_phase_ms_per_image"] = {k: round(v / batch, 3) for k, v in r.items() if k != "wall_ms"}
+        out["config4_engine_host_ms_per_image"] = {nm: round((eng.b200c_hostprof_ms(i) - prof0[i]) / batch, 3)
+                                                   for i, nm in enumerate(names)}
         out["config4_concurrent"] = {"what": f"{batch} x 1920x1080 RGBA, 100 seams each, {nthreads} images in flight on one GPU "
                                              "(host threads, one stream per carver)", "wall_s": dt,
                                      "seams_per_s_e2e": batch * n / dt}
