@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batch-in-flight", type=int, default=8,
+                    help="N=1 only: also time 2x this many images of the workload, this many in flight (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -288,6 +290,20 @@ def main():
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(out_abi, out_dev), "device-resident and C-ABI paths disagree"
 
+    # ---------------- several images in flight on this GPU (a batch host; SURVEY.md config 4's shape) ---------------
+    # Same workload and C-ABI path as e2e, host threads in C (harness_render_batch), one stream per image: the row-serial
+    # chains of different images overlap on different SMs.  Reported beside the headline, not as it.
+    batch_line = None
+    if world == 1 and args.batch_in_flight > 0:
+        harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+        vals = pkg.render.PlugInVals(new_width=W - SEAMS, new_height=H)
+        k = args.batch_in_flight
+        harness.render_batch(pkg.SHIM_PATH, [img] * k, vals, in_flight=k)  # warm-up: staging buffers, lanes, graphs
+        r = harness.render_batch(pkg.SHIM_PATH, [img] * (2 * k), vals, in_flight=k)
+        batch_line = {"value": 2 * k * SEAMS / (r["wall_ms"] * 1e-3), "unit": UNIT, "images": 2 * k, "in_flight": k,
+                      "wall_ms": r["wall_ms"],
+                      "path": "tests/harness harness_render_batch -> liblqr-1.so, one host thread + one stream per image"}
+
     # ---------------- reduce over ranks ------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -348,6 +364,8 @@ def main():
             "kernels": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in stages.items()},
             "wall_s_timed_region": wall,
         }
+        if batch_line:
+            line["batch_in_flight"] = batch_line
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)

@@ -62,10 +62,10 @@ def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=N
     return img, vm, res
 
 
-def render_batch(lib_path: str, layers, vals: PlugInVals, in_flight: int = 16):
+def render_batch(lib_path: str, layers, vals: PlugInVals, in_flight: int = 16, keep_outputs: bool = False):
     """`layers` (equal-shaped uint8 images) through the plug-in call sequence, `in_flight` of them at a time on host
     threads created in C (harness_render_batch): no Python between the images.  Returns {"wall_ms", "ms_new", ...} with
-    the per-phase times summed over the images."""
+    the per-phase times summed over the images, plus "outputs" (the resized images) when keep_outputs is set."""
     layers = [np.ascontiguousarray(a, dtype=np.uint8) for a in layers]
     h, w, bpp = layers[0].shape
     assert all(a.shape == (h, w, bpp) for a in layers)
@@ -74,11 +74,19 @@ def render_batch(lib_path: str, layers, vals: PlugInVals, in_flight: int = 16):
                      int(vals.no_disc_on_enlarge), 0, 0)
     lib = _load()
     lib.harness_render_batch.restype = C.c_int
-    lib.harness_render_batch.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(HarnessVals),
-                                         C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.harness_render_batch.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int,
+                                         C.POINTER(HarnessVals), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     ptrs = (C.c_void_p * len(layers))(*[a.ctypes.data for a in layers])
+    outs, optrs = None, None
+    if keep_outputs:
+        outs = [np.zeros((max(h, vals.new_height), max(w, vals.new_width), bpp), dtype=np.uint8) for _ in layers]
+        optrs = (C.c_void_p * len(layers))(*[a.ctypes.data for a in outs])
     sums = (C.c_double * 5)()
     wall = C.c_double()
-    if not lib.harness_render_batch(lib_path.encode(), ptrs, len(layers), in_flight, C.byref(hv), sums, C.byref(wall)):
+    if not lib.harness_render_batch(lib_path.encode(), ptrs, optrs, len(layers), in_flight, C.byref(hv), sums, C.byref(wall)):
         raise RuntimeError("harness_render_batch failed")
-    return dict(zip(("ms_new", "ms_setup", "ms_resize", "ms_scan", "ms_total"), list(sums)), wall_ms=wall.value)
+    res = dict(zip(("ms_new", "ms_setup", "ms_resize", "ms_scan", "ms_total"), list(sums)), wall_ms=wall.value)
+    if keep_outputs:
+        nw, nh = vals.new_width, vals.new_height
+        res["outputs"] = [a.reshape(-1)[: nw * nh * bpp].reshape(nh, nw, bpp).copy() for a in outs]
+    return res

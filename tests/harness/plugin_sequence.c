@@ -290,12 +290,13 @@ int harness_render(const char *liblqr_path, const unsigned char *layer, const Ha
 
 /* ---- a batch of independent layers, `nthreads` of them in flight: what a batch host (batch/batch-gimp-lqr.scm run over a
  * directory) does with one plug-in run per image.  One host thread per image in flight; every run is
- * the call sequence above.  sums[0..4] receive the per-phase milliseconds summed over the images, *wall_ms the wall time. */
+ * the call sequence above.  outs: NULL (results dropped) or one output buffer per layer.  sums[0..4] receive the per-phase milliseconds summed over the images, *wall_ms the wall time. */
 #include <pthread.h>
 
 typedef struct {
     const char *path;
     const unsigned char *const *layers;
+    unsigned char *const *outs; /* NULL, or one buffer per layer */
     const HarnessVals *v;
     int n, next, failed;
     double sums[5];
@@ -318,7 +319,7 @@ static void *batch_worker(void *arg)
         i = job->next < job->n ? job->next++ : -1;
         pthread_mutex_unlock(&job->mu);
         if (i < 0) break;
-        if (!harness_render(job->path, job->layers[i], v, NULL, NULL, NULL, out, NULL, &res) ||
+        if (!harness_render(job->path, job->layers[i], v, NULL, NULL, NULL, job->outs ? job->outs[i] : out, NULL, &res) ||
             res.out_width != v->new_width || res.out_height != v->new_height)
             failed = 1;
         sums[0] += res.ms_new, sums[1] += res.ms_setup, sums[2] += res.ms_resize, sums[3] += res.ms_scan, sums[4] += res.ms_total;
@@ -331,8 +332,8 @@ static void *batch_worker(void *arg)
     return NULL;
 }
 
-int harness_render_batch(const char *liblqr_path, const unsigned char *const *layers, int n, int nthreads,
-                         const HarnessVals *v, double *sums, double *wall_ms)
+int harness_render_batch(const char *liblqr_path, const unsigned char *const *layers, unsigned char *const *outs, int n,
+                         int nthreads, const HarnessVals *v, double *sums, double *wall_ms)
 {
     BatchJob job;
     pthread_t th[64];
@@ -341,7 +342,7 @@ int harness_render_batch(const char *liblqr_path, const unsigned char *const *la
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 64) nthreads = 64;
     memset(&job, 0, sizeof job);
-    job.path = liblqr_path, job.layers = layers, job.v = v, job.n = n;
+    job.path = liblqr_path, job.layers = layers, job.outs = outs, job.v = v, job.n = n;
     pthread_mutex_init(&job.mu, NULL);
     t0 = now_ms();
     for (k = 0; k < nthreads; k++)

@@ -219,3 +219,36 @@ def test_batch_images_in_flight(product, oracle):
     want = batch.carve_shard(oracle, range(12), 160, 90, 150, 90)
     got = batch.carve_shard(product, range(12), 160, 90, 150, 90, in_flight=6)
     assert got == want
+
+
+def test_lanes_reused_across_carvers(product, oracle):
+    """Streams and per-seam graph executables are pooled per process (lanes) and re-targeted with
+    cudaGraphExecKernelNodeSetParams: carvers of different sizes, delta_x and rigidity that inherit a lane one after
+    the other -- and several at once from host threads -- still match the oracle."""
+    from concurrent.futures import ThreadPoolExecutor
+    kinds = [(160, 90, 1, 0.0), (200, 120, 1, 0.0), (96, 140, 2, 0.0), (160, 90, 1, 0.5), (130, 77, 1, 0.0), (200, 120, 0, 0.0)]
+
+    def run(lib, i):
+        w, h, dx, rig = kinds[i % len(kinds)]
+        img = synth.smooth_noise(w, h, 4, seed=500 + i)
+        res = render.render_noninteractive(lib, img, V(new_width=w - 12, new_height=h, delta_x=dx, rigidity=rig,
+                                                       output_seams=True))
+        return res.image.tobytes(), res.vmaps[0].data.tobytes()
+
+    want = [run(oracle, i) for i in range(12)]
+    assert [run(product, i) for i in range(12)] == want
+    with ThreadPoolExecutor(4) as ex:
+        assert list(ex.map(lambda i: run(product, i), range(12))) == want
+
+
+def test_c_batch_driver_matches_oracle(pkg, oracle):
+    """tests/harness harness_render_batch: the plug-in call sequence from C host threads, 8 images in flight."""
+    import importlib
+    harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+    w, h, n = 192, 108, 20
+    imgs = [synth.smooth_noise(w, h, 4, seed=700 + i) for i in range(24)]
+    vals = V(new_width=w - n, new_height=h)
+    outs = harness.render_batch(pkg.SHIM_PATH, imgs, vals, in_flight=8, keep_outputs=True)["outputs"]
+    for img, got in zip(imgs, outs):
+        want = render.render_noninteractive(oracle, img, vals).image
+        assert np.array_equal(got, want)

@@ -46,3 +46,14 @@ def test_c_harness_product_vs_oracle(pkg, product, name, kw, masks):
     assert a.shape == b.shape and np.array_equal(a, b)
     assert ra.n_vmaps == rb.n_vmaps and np.array_equal(vma, vmb)
     assert ra.n_progress_updates == rb.n_progress_updates
+
+
+def test_c_batch_driver_on_oracle(pkg, oracle):
+    """harness_render_batch (C host threads, several images in flight) against the oracle library: the driver itself
+    must give every image the result of a lone run.  (The oracle is a plain C library without shared state.)"""
+    w, h, n = 64, 48, 6
+    imgs = [synth.smooth_noise(w, h, 4, seed=900 + i) for i in range(10)]
+    vals = V(new_width=w - n, new_height=h)
+    outs = harness.render_batch(pkg.ORACLE_PATH, imgs, vals, in_flight=4, keep_outputs=True)["outputs"]
+    for img, got in zip(imgs, outs):
+        assert np.array_equal(got, render.render_noninteractive(oracle, img, vals).image)
