@@ -204,13 +204,17 @@ void lane_release(Lane *l)
     lane_destroy(l);
 }
 
-// With about as many carvers in flight as there are cores (a batch host: one thread per image), threads that spin in
-// cudaStreamSynchronize starve the ones that have work to enqueue; waits then sleep on a blocking event instead, and
-// the upload helpers stay out of the way.  A lone image keeps the spinning wait (lowest latency) and the helpers.
+// With many carvers in flight (a batch host: one thread per image), threads that spin in cudaStreamSynchronize get in
+// the way of the ones that have work to enqueue (measured: cudaMemcpyAsync taking ms); waits then sleep on a blocking
+// event instead, and the upload helpers stay out of the way.  A lone image (and its attached carvers) keeps the
+// spinning wait -- lowest latency -- and the helpers.
 bool host_crowded()
 {
-    static const int cores = (int) std::thread::hardware_concurrency();
-    return g_lanes_busy.load(std::memory_order_relaxed) * 2 > (cores > 0 ? cores : 1);
+    static const int limit = [] {
+        const char *e = getenv("B200C_CROWDED"); // carvers alive from which waits sleep (default: 4)
+        return e && atoi(e) > 0 ? atoi(e) : 4;
+    }();
+    return g_lanes_busy.load(std::memory_order_relaxed) > limit;
 }
 bool host_shared() { return g_lanes_busy.load(std::memory_order_relaxed) > 2; }
 
