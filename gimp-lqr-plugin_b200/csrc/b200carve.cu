@@ -493,12 +493,6 @@ int raise_smem_limits()
             if (e != cudaSuccess && err == cudaSuccess) err = e;
         };
         set((const void *) k_seam_path, sp_smem_bytes());
-        if (getenv("B200C_CARVEOUT") && atoi(getenv("B200C_CARVEOUT"))) {
-            // experiment: one shared-memory carve-out for every kernel of the per-seam loop
-            auto co = [](const void *fn) { cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); };
-            co((const void *) k_seam_path), co((const void *) k_carve), co((const void *) k_energy_band);
-            co((const void *) k_fix_parents<1, false, false>), co((const void *) k_fix_parents<1, false, true>);
-        }
         set((const void *) k_band_dp<0, false, false>, bd_smem_bytes());
         set((const void *) k_mmap_full_strips<0, false, false>, mf_smem_bytes(0, false));
         set((const void *) k_band_dp<0, false, true>, bd_smem_bytes());
