@@ -132,12 +132,18 @@ def device_step(eng, d_in_ptr, d_out_ptr):
         eng.b200c_carver_destroy(c)
 
 
+_ABI_OUT = None  # the layer's pixel region the plug-in writes the result into: allocated once, like the drawable
+
+
 def abi_step(lib_path, img, seams=SEAMS):
     """The plug-in's own call sequence in C (tests/harness/plugin_sequence.c: render_init_carver + render_noninteractive +
     write_carver_to_layer, render.c:220-248,318,366,376; io_functions.c:155-164) on host buffers."""
     harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
     vals = pkg.render.PlugInVals(new_width=W - seams, new_height=H)
-    out, _, res = harness.render(lib_path, img, vals)
+    global _ABI_OUT
+    if _ABI_OUT is None:
+        _ABI_OUT = np.zeros(W * H * CH, dtype=np.uint8)
+    out, _, res = harness.render(lib_path, img, vals, out=_ABI_OUT)
     return out, res
 
 

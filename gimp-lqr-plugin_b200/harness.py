@@ -39,8 +39,10 @@ def _load():
     return _lib
 
 
-def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=None, rigmask=None):
-    """Returns (image, first_vmap_or_None, HarnessResult).  Masks must have the layer's size."""
+def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=None, rigmask=None, out=None):
+    """Returns (image, first_vmap_or_None, HarnessResult).  Masks must have the layer's size.  `out`: an optional
+    caller-owned uint8 buffer of at least max(h, new_h) * max(w, new_w) * bpp bytes that receives the layer (the
+    plug-in writes into the drawable's existing pixel region); the returned image is then a view of it."""
     layer = np.ascontiguousarray(layer, dtype=np.uint8)
     h, w, bpp = layer.shape
     masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint8) for m in (pres, disc, rigmask)]
@@ -48,7 +50,12 @@ def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=N
     hv = HarnessVals(w, h, bpp, vals.new_width, vals.new_height, vals.pres_coeff, vals.disc_coeff, vals.rigidity,
                      vals.delta_x, vals.enl_step, vals.nrg_func, vals.res_order, int(vals.output_seams),
                      int(vals.scaleback), int(vals.no_disc_on_enlarge), mbpp, int(vals.resize_aux_layers))
-    out = np.zeros((max(h, vals.new_height), max(w, vals.new_width), bpp), dtype=np.uint8)
+    need = max(h, vals.new_height) * max(w, vals.new_width) * bpp
+    own_out = out is None
+    if own_out:
+        out = np.zeros(need, dtype=np.uint8)
+    elif out.dtype != np.uint8 or not out.flags.c_contiguous or out.size < need:
+        raise ValueError("out: contiguous uint8 buffer of at least %d bytes expected" % need)
     vmap = np.zeros((h, w), dtype=np.int32)
     res = HarnessResult()
     ptr = [None if m is None else m.ctypes.data for m in masks]
@@ -56,7 +63,9 @@ def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=N
                                 vmap.ctypes.data, C.byref(res))
     if not ok:
         raise RuntimeError("harness_render failed")
-    img = out.reshape(-1)[: res.out_width * res.out_height * bpp].reshape(res.out_height, res.out_width, bpp).copy()
+    img = out.reshape(-1)[: res.out_width * res.out_height * bpp].reshape(res.out_height, res.out_width, bpp)
+    if own_out:
+        img = img.copy()
     vm = vmap.reshape(-1)[: res.vmap_width * res.vmap_height].reshape(res.vmap_height, res.vmap_width).copy() \
         if res.n_vmaps else None
     return img, vm, res
