@@ -360,7 +360,9 @@ def main():
                     "d2h_bytes_per_step": (W - SEAMS) * H * CH, "ms_per_step": e2e_ms_max / args.steps,
                     "phases_ms": {k: round(v, 3) for k, v in phases.items()},
                     "path": "tests/harness/plugin_sequence.c -> liblqr-1.so C ABI: lqr_carver_new .. resize .. scan_line "
-                            "loop, pageable host buffers as the plug-in passes them (rank 0 phases)"},
+                            "loop, pageable host buffers as the plug-in passes them (rank 0 phases); the harness keeps freed layer-sized "
+                            "blocks in the malloc heap (mallopt) and writes into a preallocated pixel region, as a "
+                            "long-running host does"},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
