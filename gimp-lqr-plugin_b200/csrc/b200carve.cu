@@ -174,7 +174,10 @@ Lane *lane_acquire(int device, bool use_ext, cudaStream_t ext)
             }
     }
     Lane *l = new (std::nothrow) Lane();
-    if (!l) return nullptr;
+    if (!l) {
+        --g_lanes_busy;
+        return nullptr;
+    }
     l->device = device;
     l->pooled = !use_ext;
     l->stream = ext;
