@@ -13,6 +13,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -1588,6 +1589,98 @@ int b200c_carver_vmap(B200Carver *c, int *out_host)
     CU_TRY(cudaMemcpyAsync(out_host, d_out, n * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     dfree(c, d_out);
     CU_TRY(carver_sync(c));
+    return B200C_OK;
+}
+
+// ---- the plug-in's own loops next to the hot path; no carver involved: they borrow a lane
+namespace {
+struct ScratchLane {
+    Lane *lane = nullptr;
+    int open()
+    {
+        const int device = g_device >= 0 ? g_device : g_device_tls_default;
+        if (cudaSetDevice(device) != cudaSuccess) return fail(B200C_ERROR, "cudaSetDevice", cudaGetLastError());
+        lane = lane_acquire(device, false, nullptr);
+        return lane ? B200C_OK : fail(B200C_ERROR, "cannot create stream", cudaGetLastError());
+    }
+    ~ScratchLane()
+    {
+        if (!lane) return;
+        cudaStreamSynchronize(lane->stream);
+        lane_release(lane);
+    }
+};
+} // namespace
+
+int b200c_vmap_colour(const int *vmap, int w, int h, int depth, const double colour_start[3], const double colour_end[3],
+                      unsigned char *out_rgba)
+{
+    if (!vmap || !colour_start || !colour_end || !out_rgba || w < 1 || h < 1 || depth < 0)
+        return fail(B200C_ERROR, "vmap_colour: bad arguments");
+    ScratchLane sl;
+    B_TRY(sl.open());
+    cudaStream_t s = sl.lane->stream;
+    const size_t n = (size_t) w * h;
+    int *d_in = nullptr;
+    uchar4 *d_out = nullptr;
+    cudaError_t e = cudaMallocAsync((void **) &d_in, n * sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **) &d_out, n * sizeof(uchar4), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, vmap, n * sizeof(int), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        StageScope sc("vmap_colour", s);
+        k_vmap_colour<<<(unsigned) ((n + 255) / 256), 256, 0, s>>>(d_in, n, depth, colour_start[0], colour_start[1],
+                                                                  colour_start[2], colour_end[0], colour_end[1],
+                                                                  colour_end[2], d_out);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_rgba, d_out, n * sizeof(uchar4), cudaMemcpyDeviceToHost, s);
+    if (d_in) cudaFreeAsync(d_in, s);
+    if (d_out) cudaFreeAsync(d_out, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(B200C_ERROR, "vmap_colour", e != cudaSuccess ? e : e2);
+    return B200C_OK;
+}
+
+int b200c_guess_new_size(const unsigned char *mask, int width, int height, int bpp, int has_alpha, int x_off, int y_off,
+                         int old_width, int old_height, int direction, int *new_size)
+{
+    if (!mask || !new_size || width < 1 || height < 1 || bpp < 1 || bpp > 4 || bpp - (has_alpha ? 1 : 0) < 1 ||
+        (direction != 0 && direction != 1))
+        return fail(B200C_ERROR, "guess_new_size: bad arguments");
+    // the part of the mask that lies over the layer (layers_combo.c:324-338)
+    const int x_lo = std::max(0, x_off), x_hi = std::min(old_width, width + x_off);
+    const int y_lo = std::max(0, y_off), y_hi = std::min(old_height, height + y_off);
+    const int old_size = direction == 0 ? old_width : old_height;
+    const int nlines = direction == 0 ? y_hi - y_lo : x_hi - x_lo;
+    const int count = direction == 0 ? x_hi - x_lo : y_hi - y_lo;
+    *new_size = old_size;
+    if (nlines <= 0 || count <= 0) return B200C_OK; // no overlap: nothing to discard
+    // first line / first pixel of a line in mask coordinates
+    const int line0 = direction == 0 ? y_lo - y_off : x_lo - x_off;
+    const int first = direction == 0 ? std::max(0, -x_off) : std::max(0, -y_off);
+    ScratchLane sl;
+    B_TRY(sl.open());
+    cudaStream_t s = sl.lane->stream;
+    const size_t bytes = (size_t) width * height * bpp;
+    unsigned char *d_mask = nullptr;
+    int *d_res = nullptr;
+    int res = 0;
+    cudaError_t e = cudaMallocAsync((void **) &d_mask, bytes, s);
+    if (e == cudaSuccess) e = cudaMallocAsync((void **) &d_res, sizeof(int), s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_mask, mask, bytes, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_res, 0, sizeof(int), s);
+    if (e == cudaSuccess) {
+        StageScope sc("guess_new_size", s);
+        k_guess_mask_size<<<(nlines + 7) / 8, 256, 0, s>>>(d_mask, width, bpp, has_alpha, line0, nlines, first, count,
+                                                          direction, d_res);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&res, d_res, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (d_mask) cudaFreeAsync(d_mask, s);
+    if (d_res) cudaFreeAsync(d_res, s);
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (e != cudaSuccess || e2 != cudaSuccess) return fail(B200C_ERROR, "guess_new_size", e != cudaSuccess ? e : e2);
+    *new_size = old_size - res;
     return B200C_OK;
 }
 

@@ -664,4 +664,58 @@ __global__ void k_energy_export(DevP p, int transposed, float *out)
     out[transposed ? (size_t) j * p.h + i : (size_t) i * p.w + j] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// The plug-in's own host loops next to the hot path, as kernels.
+//
+// write_vmap_to_layer's colouring (reference src/io_functions.c:249-279): seam order k of depth d -> value =
+// (d+1-k)/(d+1) in double; colour = value*start + (1-value)*end, alpha = 0.5*(1+value); bytes = (guchar)(255*x), i.e.
+// truncated.  Built with -fmad=false: the products and the sum round separately, like the reference on x86-64.
+__global__ void __launch_bounds__(256) k_vmap_colour(const int *vmap, size_t n, int depth, double sr, double sg, double sb,
+                                                     double er, double eg, double eb, uchar4 *out)
+{
+    const size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int vs = vmap[i];
+    uchar4 px = make_uchar4(0, 0, 0, 0);
+    if (vs != 0) {
+        const double value = __ddiv_rn((double) (depth + 1 - vs), (double) (depth + 1));
+        const double rest = __dsub_rn(1.0, value);
+        const double rd = __dadd_rn(__dmul_rn(value, sr), __dmul_rn(rest, er));
+        const double gr = __dadd_rn(__dmul_rn(value, sg), __dmul_rn(rest, eg));
+        const double bl = __dadd_rn(__dmul_rn(value, sb), __dmul_rn(rest, eb));
+        const double al = __dmul_rn(0.5, __dadd_rn(1.0, value));
+        px.x = (unsigned char) __double2int_rz(__dmul_rn(255.0, rd));
+        px.y = (unsigned char) __double2int_rz(__dmul_rn(255.0, gr));
+        px.z = (unsigned char) __double2int_rz(__dmul_rn(255.0, bl));
+        px.w = (unsigned char) __double2int_rz(__dmul_rn(255.0, al));
+    }
+    out[i] = px;
+}
+
+// guess_new_size's reduction (reference src/layers_combo.c:347-386): per line (a mask row, or a mask column when
+// vertical) the number of pixels whose intensity -- mean of the colour channels / 255, times alpha / 255 -- reaches
+// 0.5 / colour channels; the maximum over the lines.  One warp per line; *result starts at 0.
+__global__ void __launch_bounds__(256) k_guess_mask_size(const unsigned char *mask, int width, int bpp, int has_alpha,
+                                                         int line0, int nlines, int first, int count, int vertical,
+                                                         int *result)
+{
+    const int line = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (line >= nlines) return;
+    const int c_bpp = bpp - (has_alpha ? 1 : 0);
+    const double thr = __ddiv_rn(0.5, (double) c_bpp);
+    int n = 0;
+    for (int z = lane; z < count; z += 32) {
+        const size_t at = vertical ? (size_t) (first + z) * width + (size_t) (line0 + line)
+                                   : (size_t) (line0 + line) * width + (size_t) (first + z);
+        const unsigned char *px = mask + at * bpp;
+        double sum = 0;
+        for (int k = 0; k < c_bpp; ++k) sum = __dadd_rn(sum, (double) px[k]);
+        sum = __ddiv_rn(sum, (double) (255 * c_bpp));
+        if (has_alpha) sum = __dmul_rn(sum, __ddiv_rn((double) px[bpp - 1], 255.0));
+        n += sum >= thr ? 1 : 0;
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) atomicMax(result, n);
+}
+
 } // namespace b200c

@@ -110,6 +110,19 @@ enum { B200C_DBG_EN = 0, B200C_DBG_M, B200C_DBG_LEAST, B200C_DBG_RAW, B200C_DBG_
 B200C_API int b200c_debug_build(B200Carver *c, int n_seams);
 /* copies a device map to host: returns the number of elements written (<= cap), or -1 */
 B200C_API long b200c_debug_fetch(B200Carver *c, int what, void *out, long cap);
+/* ---- the plug-in's own host loops next to the hot path, device-accelerated.  Host buffers
+ * in and out; the calls return when the result is in place.
+ *
+ * b200c_vmap_colour: the colouring loop of write_vmap_to_layer (reference src/io_functions.c:249-279).  vmap: w*h seam
+ * orders (lqr_vmap_get_data), depth = lqr_vmap_get_depth, colours = r,g,b of the GimpRGB pair (render.c:341-342);
+ * out_rgba: w*h*4 bytes, byte for byte what the reference loop writes into its rows.
+ * b200c_guess_new_size: guess_new_size (reference src/layers_combo.c:274-392) for a discard mask of width x height x
+ * bpp placed at (x_off, y_off) over a layer of old_width x old_height; direction 0 = horizontal (new width), 1 =
+ * vertical (new height). */
+B200C_API int b200c_vmap_colour(const int *vmap, int w, int h, int depth, const double colour_start[3],
+                                const double colour_end[3], unsigned char *out_rgba);
+B200C_API int b200c_guess_new_size(const unsigned char *mask, int width, int height, int bpp, int has_alpha, int x_off,
+                                   int y_off, int old_width, int old_height, int direction, int *new_size);
 /* cumulative number of kernel launches issued by this library in this process */
 B200C_API long b200c_launch_count(void);
 /* cumulative device time (ms) of one stage, measured with CUDA events when B200C_TIMING=1 was set in the

@@ -101,6 +101,23 @@ def main():
         check_vmap(res.vmaps[1].data, 200, w - 400)
         out["config5"] = {"what": "3840x2160 -> 3440x2360 (W-400, H+200) with seam maps", "wall_s": dt,
                           "seams_per_s_e2e": 600 / dt}
+        # the output path of the seam maps (write_vmap_to_layer's colouring, io_functions.c:249-279): engine vs CPU loop
+        ops = importlib.import_module("gimp-lqr-plugin_b200.plugin_ops")
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import plugin_oracle
+        cs, ce = (1.0, 1.0, 0.0), (1.0, 0.0, 0.0)
+        vm = res.vmaps[0]
+        ops.vmap_colour(vm.data, vm.depth, cs, ce)
+        t0 = time.perf_counter()
+        got = [ops.vmap_colour(v.data, v.depth, cs, ce) for v in res.vmaps]
+        t_gpu = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        want = [plugin_oracle.vmap_colour(v.data, v.depth, cs, ce) for v in res.vmaps]
+        t_cpu = time.perf_counter() - t0
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
+        out["config5_vmap_colour"] = {"what": "both seam maps coloured as RGBA, host buffers in and out",
+                                      "engine_ms": t_gpu * 1e3, "cpu_loop_ms": t_cpu * 1e3,
+                                      "mpixel_per_s_engine": sum(v.data.size for v in res.vmaps) / t_gpu / 1e6}
     if os.environ.get("B200C_TIMING"):
         import ctypes as C
         eng = C.CDLL(pkg.ENGINE_PATH)
