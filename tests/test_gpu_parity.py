@@ -252,3 +252,29 @@ def test_c_batch_driver_matches_oracle(pkg, oracle):
     for img, got in zip(imgs, outs):
         want = render.render_noninteractive(oracle, img, vals).image
         assert np.array_equal(got, want)
+
+
+def test_range_extension_without_flatten(product, oracle, kernel_mode):
+    """SURVEY.md section 8(f) rank 3 (interface_I.c:504-529): the interactive dialog asks for sizes outside the range
+    computed so far; the engine runs build_maps again on the already inflated carver (more seams from the current
+    minimum width, Appendix A.9's `vs >= 2*max_level - 1` bookkeeping) -- no flatten, earlier seams unchanged."""
+    img = synth.smooth_noise(120, 90, 4)
+    outs = []
+    for lib in (product, oracle):
+        log = []
+        with lib.carver(img) as c:
+            c.init(1, 0.0)
+            c.set_side_switch_frequency(2)
+            aux = c.attach(synth.iid(120, 90, 3))
+            for tw in (110, 95, 128, 80, 150, 120):
+                c.resize(tw, 90)
+                log.append((c.info(), c.scan_image().copy(), aux.scan_image().copy(), c.vmap_dump().data.copy()))
+        outs.append(log)
+    for i, (a, b) in enumerate(zip(*outs)):
+        assert a[0] == b[0], f"step {i}: info {a[0]} != {b[0]}"
+        for k in (1, 2, 3):
+            assert a[k].shape == b[k].shape and np.array_equal(a[k], b[k]), f"step {i}: output {k} differs"
+    # the first 10 seams are the same pixels in every later, deeper map
+    first, last = outs[0][0][3], outs[0][-1][3]
+    assert np.array_equal((first > 0) & (first <= 10), (last > 0) & (last <= 10))
+    assert np.array_equal(outs[0][-1][1], img)  # back at the reference size: the original
