@@ -56,6 +56,13 @@ def main():
         assert np.array_equal(res.image, img[vm == 0].reshape(h, w - n, 4))
         out["config3"] = {"what": "7680x4320 RGBA, 1000 seams, preservation + rigidity masks, delta_x 2, rigidity 10",
                           "wall_s": dt, "seams_per_s_e2e": n / dt}
+        # the same through the plug-in's call sequence in C (no Python between the calls)
+        harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+        img_c, vm_c, hres = harness.render(pkg.SHIM_PATH, img, V(new_width=w - n, new_height=h, delta_x=2, rigidity=10.0,
+                                                                 output_seams=True), pres=pres, rigmask=rig)
+        assert np.array_equal(img_c, res.image) and np.array_equal(vm_c, vm)
+        out["config3_c_harness"] = {k: round(getattr(hres, k), 2) for k in ("ms_new", "ms_setup", "ms_resize", "ms_scan", "ms_total")}
+        out["config3_c_harness"]["seams_per_s_e2e"] = n / (hres.ms_total * 1e-3)
     if 4 in which:
         w, h, n = 1920, 1080, 100
         t0 = time.perf_counter()
