@@ -99,6 +99,17 @@ def main():
         out["config4_concurrent"] = {"what": f"{batch} x 1920x1080 RGBA, 100 seams each, {nthreads} images in flight on one GPU "
                                              "(host threads, one stream per carver)", "wall_s": dt,
                                      "seams_per_s_e2e": batch * n / dt}
+    if 45 in which:
+        # config 4's CPU side: the oracle port of liblqr through the same C batch driver, 1 thread and all cores
+        harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+        w, h, n = 1920, 1080, 100
+        ncores = os.cpu_count() or 1
+        imgs = [synth.smooth_noise(w, h, 4, seed=synth.SEED + i) for i in range(ncores)]
+        r1 = harness.render_batch(pkg.ORACLE_PATH, imgs[:2], V(new_width=w - n, new_height=h), in_flight=1)
+        rn = harness.render_batch(pkg.ORACLE_PATH, imgs, V(new_width=w - n, new_height=h), in_flight=ncores)
+        out["config4_cpu_oracle"] = {"what": "oracle port of liblqr, 1920x1080 RGBA, 100 seams per image",
+                                     "seams_per_s_1_thread": 2 * n / (r1["wall_ms"] * 1e-3),
+                                     "threads": ncores, "seams_per_s_all_threads": ncores * n / (rn["wall_ms"] * 1e-3)}
     if 5 in which:
         w, h = 3840, 2160
         img = synth.smooth_noise(w, h, 4)
