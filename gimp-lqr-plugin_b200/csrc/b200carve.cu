@@ -27,6 +27,7 @@
 #include "b200carve.h"
 #include "carver_kernels.cuh"
 #include "band_dp.cuh"
+#include "band_tail.cuh"
 #include "seam_path.cuh"
 #include "mmap_full_cluster.cuh"
 
@@ -128,7 +129,7 @@ thread_local bool g_use_ext_stream = false;
 struct LaneGraph {
     cudaGraph_t graph = nullptr; // owns the nodes whose handles address the executable's nodes
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t node[5] = {};
+    cudaGraphNode_t node[6] = {};
     int n = 0;
 };
 void lane_graph_reset(LaneGraph *g)
@@ -251,6 +252,8 @@ struct B200Carver {
     bool use_graph = true;                    // B200C_GRAPH=0: launch the kernels one by one
     int4 *fix_d = nullptr;                    // band-DP chunk table for k_fix_parents (+ its count)
     int *fixn_d = nullptr;
+    int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
+    bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
     alignas(64) BdMaps maps;                  // TMA tensor maps over the compact arrays (band DP)
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
@@ -350,6 +353,7 @@ DevP view(const B200Carver *c)
     p.nrg_pack = c->nrg_pack;
     p.fix = c->fix_d;
     p.fixn = c->fixn_d;
+    p.tail = c->use_tail ? c->tail_d : nullptr;
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
@@ -497,6 +501,11 @@ int raise_smem_limits()
             if (e != cudaSuccess && err == cudaSuccess) err = e;
         };
         set((const void *) k_seam_path, sp_smem_bytes());
+        set((const void *) k_band_tail<0, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<0, true, true>, bt_smem_bytes(true));
+        set((const void *) k_band_tail<1, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<1, true, true>, bt_smem_bytes(true));
+        set((const void *) k_band_tail<2, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<2, true, true>, bt_smem_bytes(true));
+        set((const void *) k_band_tail<3, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<3, true, true>, bt_smem_bytes(true));
+        set((const void *) k_band_tail<4, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<4, true, true>, bt_smem_bytes(true));
         set((const void *) k_band_dp<0, false, false>, bd_smem_bytes());
         set((const void *) k_mmap_full_strips<0, false, false>, mf_smem_bytes(0, false));
         set((const void *) k_band_dp<0, false, true>, bd_smem_bytes());
@@ -556,6 +565,27 @@ const void *band_dp_fn_d(bool fix, bool rig, bool lr)
     if (rig) return (const void *) k_band_dp<D, true, false>;
     if (lr) return (const void *) k_band_dp<D, false, true>;
     return (const void *) k_band_dp<D, false, false>;
+}
+
+template <int D>
+const void *band_tail_fn_d(bool rig, bool lr)
+{
+    if (rig && lr) return (const void *) k_band_tail<D, true, true>;
+    if (rig) return (const void *) k_band_tail<D, true, false>;
+    if (lr) return (const void *) k_band_tail<D, false, true>;
+    return (const void *) k_band_tail<D, false, false>;
+}
+
+const void *band_tail_fn(const B200Carver *c)
+{
+    const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
+    switch (c->delta_x) {
+        case 0: return band_tail_fn_d<0>(rig, lr);
+        case 1: return band_tail_fn_d<1>(rig, lr);
+        case 2: return band_tail_fn_d<2>(rig, lr);
+        case 3: return band_tail_fn_d<3>(rig, lr);
+        default: return band_tail_fn_d<4>(rig, lr);
+    }
 }
 
 const void *band_dp_fn(const B200Carver *c, bool fix)
@@ -663,38 +693,44 @@ struct SeamLaunch {
     dim3 grid, block;
     size_t smem;
     int second; // second kernel argument after the DevP block: 0 none, 1 the session's visibility epoch, 2 the tensor maps
+    bool coop;  // cooperative launch (grid barrier inside)
 };
+constexpr int kSeamLaunchMax = 6;
 
-int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[5])
+int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeamLaunchMax])
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     int n = 0;
     if (fast)
-        out[n++] = {"vpath", (const void *) k_seam_path, dim3(1), dim3(SP_THREADS), sp_smem_bytes(), 0};
+        out[n++] = {"vpath", (const void *) k_seam_path, dim3(1), dim3(SP_THREADS), sp_smem_bytes(), 0, false};
     else
-        out[n++] = {"vpath", (const void *) k_vpath, dim3(1), dim3(1024), 0, 0};
-    out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1};
-    out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + 7) / 8), dim3(256), 0, 0};
+        out[n++] = {"vpath", (const void *) k_vpath, dim3(1), dim3(1024), 0, 0, false};
+    out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false};
+    out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + 7) / 8), dim3(256), 0, 0, false};
     if (!with_update) return n;
     if (band) {
-        out[n++] = {"mmap_update", band_dp_fn(c, false), dim3(1), dim3(BD_THREADS), bd_smem_bytes(), 2};
-        out[n++] = {"fix_parents", band_dp_fn(c, true), dim3((c->h + 7) / 8), dim3(256), 0, 0};
+        out[n++] = {"mmap_update", band_dp_fn(c, false), dim3(1), dim3(BD_THREADS), bd_smem_bytes(), 2, false};
+        if (c->use_tail) // the rows the band kernel could not tile (none, most of the time: the kernel returns at once)
+            out[n++] = {"mmap_tail", band_tail_fn(c), dim3(bt_grid(c->w_epoch, c->delta_x)), dim3(BT_THREADS),
+                        bt_smem_bytes(c->rigidity != 0.f), 0, true};
+        out[n++] = {"fix_parents", band_dp_fn(c, true), dim3((c->h + 7) / 8), dim3(256), 0, 0, false};
     } else {
-        out[n++] = {"mmap_update", (const void *) k_mmap_update, dim3(1), dim3(512), 0, 0};
+        out[n++] = {"mmap_update", (const void *) k_mmap_update, dim3(1), dim3(512), 0, 0, false};
     }
     return n;
 }
 
 int launch_seam_kernels(B200Carver *c, bool with_update)
 {
-    SeamLaunch L[5];
+    SeamLaunch L[kSeamLaunchMax];
     const int n = seam_launch_list(c, with_update, L);
     DevP p = view_dyn(c);
     int epoch = c->vs_epoch;
     for (int i = 0; i < n; ++i) {
         StageScope sc(L[i].stage, c->stream);
         void *args[2] = {&p, L[i].second == 2 ? (void *) &c->maps : (void *) &epoch};
-        const cudaError_t e = cudaLaunchKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, c->stream);
+        const cudaError_t e = L[i].coop ? cudaLaunchCooperativeKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, c->stream)
+                                        : cudaLaunchKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, c->stream);
         if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
     }
     return B200C_OK;
@@ -706,7 +742,8 @@ void drop_seam_graphs(B200Carver *c) { c->graph_fresh[0] = c->graph_fresh[1] = f
 int graph_key(const B200Carver *c)
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
-    return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4);
+    return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4) |
+           (c->use_tail ? 1 << 12 : 0);
 }
 
 // Points the lane's graph for the current kernel set at this carver's session: the first time the nodes are added and
@@ -715,7 +752,7 @@ int graph_key(const B200Carver *c)
 int seam_graph_prepare(B200Carver *c, LaneGraph **out)
 {
     LaneGraph &g = c->lane->graphs[graph_key(c)];
-    SeamLaunch L[5];
+    SeamLaunch L[kSeamLaunchMax];
     const int n = seam_launch_list(c, true, L);
     DevP p = view_dyn(c);
     int epoch = c->vs_epoch;
@@ -731,9 +768,14 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
         kp.blockDim = L[i].block;
         kp.sharedMemBytes = (unsigned) L[i].smem;
         kp.kernelParams = args;
-        if (fresh)
+        if (fresh) {
             e = cudaGraphAddKernelNode(&g.node[i], g.graph, i ? &g.node[i - 1] : nullptr, i ? 1 : 0, &kp);
-        else
+            if (e == cudaSuccess && L[i].coop) {
+                cudaKernelNodeAttrValue v = {};
+                v.cooperative = 1;
+                e = cudaGraphKernelNodeSetAttribute(g.node[i], cudaKernelNodeAttributeCooperative, &v);
+            }
+        } else
             e = cudaGraphExecKernelNodeSetParams(g.exec, g.node[i], &kp);
     }
     if (e == cudaSuccess && fresh) e = cudaGraphInstantiate(&g.exec, g.graph, 0);
@@ -1191,6 +1233,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
         c->generic = g && atoi(g) != 0;
         const char *gr = getenv("B200C_GRAPH");
         if (gr) c->use_graph = atoi(gr) != 0;
+        const char *tl = getenv("B200C_TAIL");
+        if (tl) c->use_tail = atoi(tl) != 0;
         const char *ms = getenv("B200C_BD_MAXSEG");
         if (ms && atoi(ms) > 0) c->bd_maxseg = atoi(ms);
 
@@ -1322,6 +1366,7 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->nrg_pack);
     dfree(c, c->fix_d);
     dfree(c, c->fixn_d);
+    dfree(c, c->tail_d);
     dfree(c, c->err_d);
     dfree(c, c->dyn_d);
     drop_seam_graphs(c);
@@ -1366,6 +1411,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->nrg_pack, (size_t) c->h, true));
     B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / 8 + 4, true));
     B_TRY(dalloc(c, &c->fixn_d, 1, true));
+    B_TRY(dalloc(c, &c->tail_d, 4, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     B_TRY(dalloc(c, &c->dyn_d, 1, true));

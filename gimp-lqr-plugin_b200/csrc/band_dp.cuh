@@ -692,6 +692,10 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const
     }
     __syncthreads();
     const int y_from = misc[0];
+    if (p.tail) { // the multi-SM tail kernel (band_tail.cuh) takes the rows this CTA cannot tile
+        if (tid == 0) p.tail[0] = y_from, p.tail[1] = misc[1], p.tail[2] = misc[2];
+        return;
+    }
     if (y_from < p.h) {
         if (BD_PROF && p.dbg && tid == 0) atomicAdd((unsigned long long *) &p.dbg[14], (unsigned long long) (p.h - y_from));
         constexpr int cap = BD_RING_BYTES / 8; // two row buffers in the tile ring, which nobody uses any more

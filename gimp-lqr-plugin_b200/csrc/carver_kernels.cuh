@@ -58,6 +58,7 @@ struct DevP {
     unsigned long long *cells; // running count of band cells evaluated by the incremental DP
     long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
     int *dyn;          // seam counter of the current build session, or NULL: see seam_view()
+    int *tail;         // band DP -> tail kernel: {first row left to do (h: none), hull lo, hull hi} of this seam, or NULL
     int *err;          // device error word: bit 0 band left its staged window, bit 1 backtrack met a dead parent, bit 2 bulk copy timed out
 };
 

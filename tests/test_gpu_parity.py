@@ -28,18 +28,25 @@ def engine(pkg, product):
     return eng
 
 
-@pytest.fixture(params=["fast", "narrow", "generic"])
+@pytest.fixture(params=["fast", "narrow", "narrow_incta", "generic"])
 def kernel_mode(request):
     """Every kernel set must match the oracle: "fast" (default: trapezoid-tiled band DP fed by 2-D TMA tiles, staged
     backtrack, strip-tiled full DP), "narrow" (B200C_BD_MAXSEG=1: the band DP hands every window wider than one segment
-    to its in-kernel wide-window row loop, which large images only reach on very wide bands) and "generic"
-    (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at carver creation."""
-    old = {k: os.environ.get(k) for k in ("B200C_GENERIC", "B200C_BD_MAXSEG")}
+    -- i.e. nearly every row -- to the multi-SM tail kernel, which large images only reach on very wide bands),
+    "narrow_incta" (the same with B200C_TAIL=0: the band kernel's own wide-window row loop, the fallback without
+    cooperative launch) and "generic" (B200C_GENERIC=1: the single-CTA kernels everything falls back to).  Read at
+    carver creation."""
+    keys = ("B200C_GENERIC", "B200C_BD_MAXSEG", "B200C_TAIL")
+    old = {k: os.environ.get(k) for k in keys}
     os.environ["B200C_GENERIC"] = "1" if request.param == "generic" else "0"
-    if request.param == "narrow":
+    if request.param.startswith("narrow"):
         os.environ["B200C_BD_MAXSEG"] = "1"
     else:
         os.environ.pop("B200C_BD_MAXSEG", None)
+    if request.param == "narrow_incta":
+        os.environ["B200C_TAIL"] = "0"
+    else:
+        os.environ.pop("B200C_TAIL", None)
     yield request.param
     for k, v in old.items():
         if v is None:

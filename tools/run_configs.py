@@ -142,7 +142,7 @@ def main():
         eng.b200c_stage_ms.restype = C.c_double
         eng.b200c_stage_ms.argtypes = [C.c_char_p, C.POINTER(C.c_long)]
         st = {}
-        for name in ["energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "fix_parents", "inflate",
+        for name in ["energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "mmap_tail", "fix_parents", "inflate",
                      "readout", "mask", "gather_rig", "transpose", "flatten", "vmap"]:
             n = C.c_long()
             ms = eng.b200c_stage_ms(name.encode(), C.byref(n))

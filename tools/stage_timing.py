@@ -11,7 +11,7 @@ os.environ.setdefault("B200C_TIMING", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 pkg = importlib.import_module("gimp-lqr-plugin_b200")
 
-STAGES = ["init_raw", "energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "fix_parents", "finish_vsmap",
+STAGES = ["init_raw", "energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "mmap_tail", "fix_parents", "finish_vsmap",
           "inflate", "flatten", "transpose", "readout", "vmap", "mask", "energy_export"]
 
 
