@@ -501,11 +501,16 @@ int raise_smem_limits()
             if (e != cudaSuccess && err == cudaSuccess) err = e;
         };
         set((const void *) k_seam_path, sp_smem_bytes());
-        set((const void *) k_band_tail<0, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<0, true, true>, bt_smem_bytes(true));
-        set((const void *) k_band_tail<1, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<1, true, true>, bt_smem_bytes(true));
-        set((const void *) k_band_tail<2, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<2, true, true>, bt_smem_bytes(true));
-        set((const void *) k_band_tail<3, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<3, true, true>, bt_smem_bytes(true));
-        set((const void *) k_band_tail<4, true, false>, bt_smem_bytes(true)), set((const void *) k_band_tail<4, true, true>, bt_smem_bytes(true));
+        set((const void *) k_band_tail<0, true, false>, bt_smem_bytes(0, true)), set((const void *) k_band_tail<0, true, true>, bt_smem_bytes(0, true));
+        set((const void *) k_band_tail<0, false, false>, bt_smem_bytes(0, false)), set((const void *) k_band_tail<0, false, true>, bt_smem_bytes(0, false));
+        set((const void *) k_band_tail<1, true, false>, bt_smem_bytes(1, true)), set((const void *) k_band_tail<1, true, true>, bt_smem_bytes(1, true));
+        set((const void *) k_band_tail<1, false, false>, bt_smem_bytes(1, false)), set((const void *) k_band_tail<1, false, true>, bt_smem_bytes(1, false));
+        set((const void *) k_band_tail<2, true, false>, bt_smem_bytes(2, true)), set((const void *) k_band_tail<2, true, true>, bt_smem_bytes(2, true));
+        set((const void *) k_band_tail<2, false, false>, bt_smem_bytes(2, false)), set((const void *) k_band_tail<2, false, true>, bt_smem_bytes(2, false));
+        set((const void *) k_band_tail<3, true, false>, bt_smem_bytes(3, true)), set((const void *) k_band_tail<3, true, true>, bt_smem_bytes(3, true));
+        set((const void *) k_band_tail<3, false, false>, bt_smem_bytes(3, false)), set((const void *) k_band_tail<3, false, true>, bt_smem_bytes(3, false));
+        set((const void *) k_band_tail<4, true, false>, bt_smem_bytes(4, true)), set((const void *) k_band_tail<4, true, true>, bt_smem_bytes(4, true));
+        set((const void *) k_band_tail<4, false, false>, bt_smem_bytes(4, false)), set((const void *) k_band_tail<4, false, true>, bt_smem_bytes(4, false));
         set((const void *) k_band_dp<0, false, false>, bd_smem_bytes());
         set((const void *) k_mmap_full_strips<0, false, false>, mf_smem_bytes(0, false));
         set((const void *) k_band_dp<0, false, true>, bd_smem_bytes());
@@ -712,7 +717,7 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
         out[n++] = {"mmap_update", band_dp_fn(c, false), dim3(1), dim3(BD_THREADS), bd_smem_bytes(), 2, false};
         if (c->use_tail) // the rows the band kernel could not tile (none, most of the time: the kernel returns at once)
             out[n++] = {"mmap_tail", band_tail_fn(c), dim3(bt_grid(c->w_epoch, c->delta_x)), dim3(BT_THREADS),
-                        bt_smem_bytes(c->rigidity != 0.f), 0, true};
+                        bt_smem_bytes(c->delta_x > 4 ? 4 : c->delta_x, c->rigidity != 0.f), 0, true};
         out[n++] = {"fix_parents", band_dp_fn(c, true), dim3((c->h + 7) / 8), dim3(256), 0, 0, false};
     } else {
         out[n++] = {"mmap_update", (const void *) k_mmap_update, dim3(1), dim3(512), 0, 0, false};

@@ -6,7 +6,7 @@
 // (DESIGN.md section 5): a cell whose parents' values did not change re-evaluates to "keep" -- with all SMs: column
 // strips of 128 columns per warp, 4 cells per lane, the row in registers, the per-cell rule of the band kernel's
 // settle path (candidates, arg-min, keep-old test).  Strips overlap by rows * delta_x columns (trapezoid), so the
-// strips of one block of BT_ROWS rows are independent; between row blocks the CTAs meet at a grid barrier
+// strips of one block of bt_rows() rows are independent; between row blocks the CTAs meet at a grid barrier
 // (cooperative launch).  The operands of a row block (en, old m, old parents, rigidity mask) do not depend on the
 // chain and are fetched up front with cp.async.
 #pragma once
@@ -18,11 +18,12 @@ namespace b200c {
 
 #define BT_WARPS 4
 #define BT_THREADS (BT_WARPS * 32)
-#define BT_ROWS 8
 
-__host__ __device__ inline int bt_hk(int delta_x) { return (BT_ROWS * delta_x + 3) & ~3; }
-__host__ __device__ inline int bt_strip(int delta_x) { return 128 - 2 * bt_hk(delta_x); }
-static inline size_t bt_smem_bytes(bool rig) { return (size_t) BT_WARPS * BT_ROWS * 128 * (4 + 4 + 1 + (rig ? 4 : 0)); }
+// rows per grid barrier: more rows amortise the barrier, but the strips overlap by rows * delta_x columns on each side
+__host__ __device__ constexpr int bt_rows(int delta_x) { return delta_x <= 2 ? 16 : 8; }
+__host__ __device__ constexpr int bt_hk(int delta_x) { return (bt_rows(delta_x) * delta_x + 3) & ~3; }
+__host__ __device__ constexpr int bt_strip(int delta_x) { return 128 - 2 * bt_hk(delta_x); }
+static inline size_t bt_smem_bytes(int delta_x, bool rig) { return (size_t) BT_WARPS * bt_rows(delta_x) * 128 * (4 + 4 + 1 + (rig ? 4 : 0)); }
 // CTAs that cover the widest row of a session (width w plus the sentinel columns a parent scan can reach)
 static inline int bt_grid(int w, int delta_x) { return (((w + 4 + 3) & ~3) + BT_WARPS * bt_strip(delta_x) - 1) / (BT_WARPS * bt_strip(delta_x)); }
 
@@ -43,7 +44,8 @@ __global__ void __launch_bounds__(BT_THREADS) k_band_tail(const DevP pin)
     if (y_from >= p.h) return; // the same for every thread of the grid
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     extern __shared__ __align__(16) unsigned char bt_smem[];
-    constexpr int R = BT_ROWS, HK = (R * D + 3) & ~3, S = 128 - 2 * HK;
+    constexpr int R = bt_rows(D), HK = bt_hk(D), S = bt_strip(D);
+    static_assert(S >= 32, "strips must keep an interior");
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int strip = blockIdx.x * BT_WARPS + warp;
     const int x0 = strip * S - HK + 4 * lane; // first of this lane's 4 columns
