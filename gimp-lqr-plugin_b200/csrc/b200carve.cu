@@ -862,6 +862,20 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
     // session: the per-seam kernels get one argument block and count the seams themselves (DevP::dyn starts at -1)
     drop_seam_graphs(c);
     c->w_epoch = c->w;
+    if (c->use_tail && fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX) {
+        // the tail kernel needs a grid barrier: every CTA of its grid must be resident at once (cooperative launch)
+        B_TRY(raise_smem_limits());
+        int coop = 0, sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, band_tail_fn(c), BT_THREADS,
+                                                          bt_smem_bytes(c->delta_x, c->rigidity != 0.f)) != cudaSuccess)
+            per_sm = 0;
+        if (!coop || bt_grid(c->w_epoch, c->delta_x) > per_sm * sms) {
+            cudaGetLastError();
+            c->use_tail = false; // the band kernel keeps its own wide-window loop
+        }
+    }
     c->vs_epoch = first + c->max_level - 1;
     CU_TRY(cudaMemsetAsync(c->dyn_d, 0xff, sizeof(int), c->stream));
     for (int l = first; l < depth; ++l) {
