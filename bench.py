@@ -305,9 +305,10 @@ def main():
         vals = pkg.render.PlugInVals(new_width=W - SEAMS, new_height=H)
         k = args.batch_in_flight
         harness.render_batch(pkg.SHIM_PATH, [img] * k, vals, in_flight=k)  # warm-up: staging buffers, lanes, graphs
-        r = harness.render_batch(pkg.SHIM_PATH, [img] * (2 * k), vals, in_flight=k)
+        runs = [harness.render_batch(pkg.SHIM_PATH, [img] * (2 * k), vals, in_flight=k) for _ in range(3)]
+        r = sorted(runs, key=lambda x: x["wall_ms"])[1]  # median of three batches
         batch_line = {"value": 2 * k * SEAMS / (r["wall_ms"] * 1e-3), "unit": UNIT, "images": 2 * k, "in_flight": k,
-                      "wall_ms": r["wall_ms"],
+                      "wall_ms": r["wall_ms"], "batches": "median of 3",
                       "path": "tests/harness harness_render_batch -> liblqr-1.so, one host thread + one stream per image"}
 
     # ---------------- reduce over ranks ------------------------------------------------------------------
