@@ -491,68 +491,49 @@ int build_emap(B200Carver *c)
 
 bool fast_path(const B200Carver *c) { return !c->generic; }
 
-int raise_smem_limits()
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when it is called, and one
+// process may drive several GPUs (b200c_set_device): the opt-in is tracked per device.
+template <int D>
+void raise_smem_limits_d(cudaError_t &err)
 {
-    static std::once_flag once;
-    static cudaError_t err = cudaSuccess;
-    std::call_once(once, [] {
-        auto set = [](const void *fn, size_t bytes) {
-            cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
-            if (e != cudaSuccess && err == cudaSuccess) err = e;
-        };
-        set((const void *) k_seam_path, sp_smem_bytes());
-        set((const void *) k_band_tail<0, true, false>, bt_smem_bytes(0, true)), set((const void *) k_band_tail<0, true, true>, bt_smem_bytes(0, true));
-        set((const void *) k_band_tail<0, false, false>, bt_smem_bytes(0, false)), set((const void *) k_band_tail<0, false, true>, bt_smem_bytes(0, false));
-        set((const void *) k_band_tail<1, true, false>, bt_smem_bytes(1, true)), set((const void *) k_band_tail<1, true, true>, bt_smem_bytes(1, true));
-        set((const void *) k_band_tail<1, false, false>, bt_smem_bytes(1, false)), set((const void *) k_band_tail<1, false, true>, bt_smem_bytes(1, false));
-        set((const void *) k_band_tail<2, true, false>, bt_smem_bytes(2, true)), set((const void *) k_band_tail<2, true, true>, bt_smem_bytes(2, true));
-        set((const void *) k_band_tail<2, false, false>, bt_smem_bytes(2, false)), set((const void *) k_band_tail<2, false, true>, bt_smem_bytes(2, false));
-        set((const void *) k_band_tail<3, true, false>, bt_smem_bytes(3, true)), set((const void *) k_band_tail<3, true, true>, bt_smem_bytes(3, true));
-        set((const void *) k_band_tail<3, false, false>, bt_smem_bytes(3, false)), set((const void *) k_band_tail<3, false, true>, bt_smem_bytes(3, false));
-        set((const void *) k_band_tail<4, true, false>, bt_smem_bytes(4, true)), set((const void *) k_band_tail<4, true, true>, bt_smem_bytes(4, true));
-        set((const void *) k_band_tail<4, false, false>, bt_smem_bytes(4, false)), set((const void *) k_band_tail<4, false, true>, bt_smem_bytes(4, false));
-        set((const void *) k_band_dp<0, false, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<0, false, false>, mf_smem_bytes(0, false));
-        set((const void *) k_band_dp<0, false, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<0, false, true>, mf_smem_bytes(0, false));
-        set((const void *) k_band_dp<0, true, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<0, true, false>, mf_smem_bytes(0, true));
-        set((const void *) k_band_dp<0, true, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<0, true, true>, mf_smem_bytes(0, true));
-        set((const void *) k_band_dp<1, false, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<1, false, false>, mf_smem_bytes(1, false));
-        set((const void *) k_band_dp<1, false, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<1, false, true>, mf_smem_bytes(1, false));
-        set((const void *) k_band_dp<1, true, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<1, true, false>, mf_smem_bytes(1, true));
-        set((const void *) k_band_dp<1, true, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<1, true, true>, mf_smem_bytes(1, true));
-        set((const void *) k_band_dp<2, false, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<2, false, false>, mf_smem_bytes(2, false));
-        set((const void *) k_band_dp<2, false, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<2, false, true>, mf_smem_bytes(2, false));
-        set((const void *) k_band_dp<2, true, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<2, true, false>, mf_smem_bytes(2, true));
-        set((const void *) k_band_dp<2, true, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<2, true, true>, mf_smem_bytes(2, true));
-        set((const void *) k_band_dp<3, false, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<3, false, false>, mf_smem_bytes(3, false));
-        set((const void *) k_band_dp<3, false, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<3, false, true>, mf_smem_bytes(3, false));
-        set((const void *) k_band_dp<3, true, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<3, true, false>, mf_smem_bytes(3, true));
-        set((const void *) k_band_dp<3, true, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<3, true, true>, mf_smem_bytes(3, true));
-        set((const void *) k_band_dp<4, false, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<4, false, false>, mf_smem_bytes(4, false));
-        set((const void *) k_band_dp<4, false, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<4, false, true>, mf_smem_bytes(4, false));
-        set((const void *) k_band_dp<4, true, false>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<4, true, false>, mf_smem_bytes(4, true));
-        set((const void *) k_band_dp<4, true, true>, bd_smem_bytes());
-        set((const void *) k_mmap_full_strips<4, true, true>, mf_smem_bytes(4, true));
-    });
-    if (err != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", err);
+    auto set = [&err](const void *fn, size_t bytes) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
+        if (e != cudaSuccess && err == cudaSuccess) err = e;
+    };
+    set((const void *) k_band_tail<D, true, false>, bt_smem_bytes(D, true));
+    set((const void *) k_band_tail<D, true, true>, bt_smem_bytes(D, true));
+    set((const void *) k_band_tail<D, false, false>, bt_smem_bytes(D, false));
+    set((const void *) k_band_tail<D, false, true>, bt_smem_bytes(D, false));
+    set((const void *) k_band_dp<D, false, false>, bd_smem_bytes());
+    set((const void *) k_band_dp<D, false, true>, bd_smem_bytes());
+    set((const void *) k_band_dp<D, true, false>, bd_smem_bytes());
+    set((const void *) k_band_dp<D, true, true>, bd_smem_bytes());
+    set((const void *) k_mmap_full_strips<D, false, false>, mf_smem_bytes(D, false));
+    set((const void *) k_mmap_full_strips<D, false, true>, mf_smem_bytes(D, false));
+    set((const void *) k_mmap_full_strips<D, true, false>, mf_smem_bytes(D, true));
+    set((const void *) k_mmap_full_strips<D, true, true>, mf_smem_bytes(D, true));
+}
+
+int raise_smem_limits(int device)
+{
+    static std::mutex mu;
+    static std::map<int, cudaError_t> done; // device -> outcome of the opt-in
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(device);
+    if (it == done.end()) {
+        cudaError_t err = cudaSetDevice(device);
+        if (err == cudaSuccess) {
+            cudaError_t e = cudaFuncSetAttribute((const void *) k_seam_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sp_smem_bytes());
+            if (e != cudaSuccess) err = e;
+            raise_smem_limits_d<0>(err);
+            raise_smem_limits_d<1>(err);
+            raise_smem_limits_d<2>(err);
+            raise_smem_limits_d<3>(err);
+            raise_smem_limits_d<4>(err);
+        }
+        it = done.emplace(device, err).first;
+    }
+    if (it->second != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", it->second);
     return B200C_OK;
 }
 
@@ -620,7 +601,7 @@ void launch_mmap_full_d(B200Carver *c, int grid, int y0, int rows)
 int build_mmap(B200Carver *c)
 {
     if (fast_path(c) && c->delta_x <= 4) {
-        B_TRY(raise_smem_limits());
+        B_TRY(raise_smem_limits(c->device));
         const int R = mf_rows(c->delta_x), S = 128 - 2 * mf_hk(c->delta_x);
         const int nstrips = (c->w + 4 + S - 1) / S;
         const int grid = (nstrips + MF_WARPS - 1) / MF_WARPS;
@@ -797,7 +778,7 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
 int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
 {
     cudaStream_t s = c->stream;
-    if (fast_path(c)) B_TRY(raise_smem_limits());
+    if (fast_path(c)) B_TRY(raise_smem_limits(c->device));
     const bool last = c->w - 1 <= 1; // the image is about to be one pixel wide
     const bool lr_switch = !last && c->lr_freq && ((l - c->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0;
     if (last) {
@@ -864,7 +845,7 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
     c->w_epoch = c->w;
     if (c->use_tail && fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX) {
         // the tail kernel needs a grid barrier: every CTA of its grid must be resident at once (cooperative launch)
-        B_TRY(raise_smem_limits());
+        B_TRY(raise_smem_limits(c->device));
         int coop = 0, sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -1311,6 +1292,17 @@ int b200c_device_count(void)
         return 0;
     }
     return n;
+}
+
+int b200c_device_cc(int device)
+{
+    int major = 0, minor = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return major * 10 + minor;
 }
 
 int b200c_set_device(int device)

@@ -41,6 +41,7 @@ B200C_API int b200c_abi_version(void);
 B200C_API const char *b200c_last_error(void);
 B200C_API int b200c_device_count(void);
 B200C_API int b200c_set_device(int device); /* device used by carvers created afterwards on this thread */
+B200C_API int b200c_device_cc(int device);  /* compute capability major * 10 + minor (100 = sm_100), -1 on error */
 
 /* lqr_carver_new (render.c:222,894): copies the 8-bit interleaved image to HBM.  The host buffer stays
  * the caller's (the shim frees it; ownership rule of the Lqr API is the shim's business). */

@@ -107,6 +107,7 @@ struct _LqrCarver {
 
     /* instrumentation for tests / kernel design (not part of liblqr) */
     long stat_update_rows, stat_update_cells, stat_update_maxband;
+    long stat_band_hist[16]; /* rows whose band width w satisfies 2^(i-1) < w <= 2^i (i = 0: w <= 1) */
 };
 
 /* ------------------------------------------------------------------ progress (A.10) */
@@ -384,6 +385,11 @@ static LqrRetVal update_mmap(LqrCarver *r)
         if (x_max >= x_min) {
             r->stat_update_cells += x_max - x_min + 1;
             if (x_max - x_min + 1 > r->stat_update_maxband) r->stat_update_maxband = x_max - x_min + 1;
+            {
+                gint b = 0, bw = x_max - x_min + 1;
+                while ((1 << b) < bw && b < 15) b++;
+                r->stat_band_hist[b]++;
+            }
         }
         for (x = x_min; x <= x_max; x++) {
             gint z = r->raw[y][x], parent;
@@ -1237,6 +1243,11 @@ LQR_PUBLIC void lqr_oracle_update_stats(LqrCarver *r, long out[3])
     out[0] = r->stat_update_rows;
     out[1] = r->stat_update_cells;
     out[2] = r->stat_update_maxband;
+}
+
+LQR_PUBLIC void lqr_oracle_band_hist(LqrCarver *r, long out[16])
+{
+    memcpy(out, r->stat_band_hist, sizeof r->stat_band_hist);
 }
 
 /* state after `n_seams` iterations of the per-seam loop WITHOUT the final inflate, so that the maps can

@@ -56,8 +56,13 @@ def kernel_mode(request):
 
 
 def test_device_is_blackwell(engine):
+    """The engine is built for sm_100a only: the device the tests run on must be compute capability 10.x."""
     engine.b200c_device_count.restype = C.c_int
     assert engine.b200c_device_count() >= 1
+    engine.b200c_device_cc.restype = C.c_int
+    engine.b200c_device_cc.argtypes = [C.c_int]
+    cc = engine.b200c_device_cc(0)
+    assert cc // 10 == 10, f"compute capability {cc / 10} is not Blackwell sm_100"
 
 
 @pytest.mark.parametrize("cs", CASES, ids=CASE_IDS)
@@ -176,6 +181,56 @@ def test_large_image_parity(product, oracle, w, h, seams):
     got = render.render_noninteractive(product, img, vals)
     diffs = cases.results_equal(got, want)
     assert not diffs, "; ".join(diffs)
+
+
+def _assert_same(got, want):
+    diffs = cases.results_equal(got, want)
+    assert not diffs, "; ".join(diffs)
+
+
+def test_full_size_config1(product, oracle):
+    """BASELINE.json configs[0]: 512x512 RGB, 10 vertical seams with the fixed arguments of the batch script
+    (batch/batch-gimp-lqr.scm:33-61: coefficients 1000, rigidity 0, delta_x 1, enl_step 150, nrg_func 3, res_order 0)."""
+    w, h = 512, 512
+    img = synth.smooth_noise(w, h, 3)
+    vals = V(new_width=w - 10, new_height=h, pres_coeff=1000, disc_coeff=1000, rigidity=0.0, delta_x=1, enl_step=150.0,
+             nrg_func=3, res_order=lqr.LQR_RES_ORDER_HOR, output_seams=True)
+    _assert_same(render.render_noninteractive(product, img, vals), render.render_noninteractive(oracle, img, vals))
+
+
+def test_full_size_config2(product, oracle):
+    """BASELINE.json configs[1] at full size: 3840x2160 RGBA, all 200 seams, plug-in defaults (render.c:318)."""
+    w, h, n = 3840, 2160, 200
+    img = synth.smooth_noise(w, h, 4)
+    vals = V(new_width=w - n, new_height=h, output_seams=True)
+    _assert_same(render.render_noninteractive(product, img, vals, log_progress=True),
+                 render.render_noninteractive(oracle, img, vals, log_progress=True))
+
+
+def test_full_size_config3(product, oracle):
+    """BASELINE.json configs[2] at full size: 7680x4320 RGBA (random alpha), 1000 seams, preservation ellipse
+    (pres_coeff 1000), rigidity band mask, rigidity 10 (x3 with a mask, render.c:781-792), delta_x 2.  The CPU oracle
+    needs about a minute for this one."""
+    w, h, n = 7680, 4320, 1000
+    img = synth.smooth_noise(w, h, 4, alpha="random")
+    vals = V(new_width=w - n, new_height=h, delta_x=2, rigidity=10.0, output_seams=True)
+    pres = synth.ellipse_mask(w, h)
+    rig = synth.band_mask(w, h)
+    got = render.render_noninteractive(product, img, vals, pres=pres, rigmask=rig)
+    want = render.render_noninteractive(oracle, img, vals, pres=pres, rigmask=rig)
+    _assert_same(got, want)
+
+
+def test_full_size_config5(product, oracle):
+    """BASELINE.json configs[4] at full size: 3840x2160 -> 3440x2360 (400 seams out, then 200 in along the height),
+    order HOR, both seam maps (lqr_carver_set_dump_vmaps, render.c:239-242,340-346)."""
+    w, h = 3840, 2160
+    img = synth.smooth_noise(w, h, 4)
+    vals = V(new_width=w - 400, new_height=h + 200, output_seams=True)
+    got = render.render_noninteractive(product, img, vals)
+    want = render.render_noninteractive(oracle, img, vals)
+    assert len(got.vmaps) == 2 and got.image.shape == (h + 200, w - 400, 4)
+    _assert_same(got, want)
 
 
 def test_config3_geometry_scaled(product, oracle):
