@@ -272,7 +272,7 @@ def main():
             device_step(eng, d_in.data_ptr(), d_out.data_ptr())
         stream.synchronize()
         stages = {}
-        for s in ["energy_full", "mmap_full", "vpath", "carve", "energy_band", "mmap_update", "mmap_tail", "fix_parents", "inflate", "readout"]:
+        for s in ["energy_full", "mmap_full", "seam_jumps", "vpath", "carve", "energy_band", "mmap_update", "mmap_tail", "fix_parents", "inflate", "readout"]:
             n = C.c_long()
             ms = eng.b200c_stage_ms(s.encode(), C.byref(n))
             if n.value:

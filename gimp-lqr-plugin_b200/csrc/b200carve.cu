@@ -29,6 +29,7 @@
 #include "band_dp.cuh"
 #include "band_tail.cuh"
 #include "seam_path.cuh"
+#include "seam_trace.cuh"
 #include "mmap_full_cluster.cuh"
 
 using namespace b200c;
@@ -129,7 +130,7 @@ thread_local bool g_use_ext_stream = false;
 struct LaneGraph {
     cudaGraph_t graph = nullptr; // owns the nodes whose handles address the executable's nodes
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t node[6] = {};
+    cudaGraphNode_t node[8] = {};
     int n = 0;
 };
 void lane_graph_reset(LaneGraph *g)
@@ -241,6 +242,7 @@ struct B200Carver {
     int *raw = nullptr;                          // index table: x-th visible pixel of row y
     float *en = nullptr, *m = nullptr, *rig = nullptr; // compact maps [h_start][pitch] (DevP)
     int8_t *pdx = nullptr;                       // compact parent offsets
+    int8_t *jump = nullptr;                      // block jump tables of the backtrack (seam_trace.cuh)
     int pitch = 0;
     int *vpath_x = nullptr, *nrg_xmin = nullptr, *nrg_xmax = nullptr;
     unsigned *nrg_pack = nullptr;
@@ -254,6 +256,7 @@ struct B200Carver {
     int *fixn_d = nullptr;
     int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
     bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
+    bool use_trace = true;                    // B200C_TRACE=0: the single-CTA staged backtrack (seam_path.cuh)
     alignas(64) BdMaps maps;                  // TMA tensor maps over the compact arrays (band DP)
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
@@ -343,6 +346,7 @@ DevP view(const B200Carver *c)
     p.en = c->en;
     p.m = c->m;
     p.pdx = c->pdx;
+    p.jump = (signed char *) c->jump;
     p.rig = c->rig;
     p.bias = c->bias;
     p.rigmask = c->rigmask;
@@ -446,6 +450,7 @@ void free_maps(B200Carver *c)
     dfree(c, c->en);
     dfree(c, c->m);
     dfree(c, c->pdx);
+    dfree(c, c->jump);
     dfree(c, c->rig);
     c->nrg_uptodate = false;
 }
@@ -459,10 +464,10 @@ int alloc_maps(B200Carver *c)
     if (c->active) {
         B_TRY(dalloc(c, &c->m, n, true));
         B_TRY(dalloc(c, &c->pdx, n, true));
+        B_TRY(dalloc(c, &c->jump, (size_t) st_nblk(c->h_start, c->delta_x <= 4 ? c->delta_x : 4) * c->pitch + 64, true));
         const int K = bd_rows(c->delta_x, c->rigidity != 0.f);
         B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, K + 1));
         B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, K));
-        B_TRY(encode_map(&c->maps.pdx, c->pdx, true, c->pitch, c->h_start, K));
         c->maps.rig = c->maps.en;
     }
     return B200C_OK;
@@ -524,6 +529,8 @@ int raise_smem_limits(int device)
         cudaError_t err = cudaSetDevice(device);
         if (err == cudaSuccess) {
             cudaError_t e = cudaFuncSetAttribute((const void *) k_seam_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sp_smem_bytes());
+            if (e != cudaSuccess) err = e;
+            e = cudaFuncSetAttribute((const void *) k_seam_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st_chase_smem());
             if (e != cudaSuccess) err = e;
             raise_smem_limits_d<0>(err);
             raise_smem_limits_d<1>(err);
@@ -681,16 +688,31 @@ struct SeamLaunch {
     int second; // second kernel argument after the DevP block: 0 none, 1 the session's visibility epoch, 2 the tensor maps
     bool coop;  // cooperative launch (grid barrier inside)
 };
-constexpr int kSeamLaunchMax = 6;
+constexpr int kSeamLaunchMax = 8;
+
+// the backtrack: jump tables over all SMs + a short chase (seam_trace.cuh); the single-CTA staged chase for delta_x > 4;
+// the plain walk with B200C_GENERIC=1
+int vpath_launch_list(const B200Carver *c, SeamLaunch out[kSeamLaunchMax])
+{
+    int n = 0;
+    if (fast_path(c) && c->delta_x <= 4 && c->h <= ST_HMAX && c->use_trace) {
+        const int nblk = st_nblk(c->h, c->delta_x);
+        if (nblk > 0)
+            out[n++] = {"seam_jumps", (const void *) k_seam_jumps, dim3((c->w_epoch + ST_COLS - 1) / ST_COLS, nblk), dim3(ST_THREADS),
+                        st_jump_smem(c->delta_x), 0, false};
+        out[n++] = {"vpath", (const void *) k_seam_chase, dim3(1), dim3(ST_CHASE_THREADS), st_chase_smem(), 0, false};
+    } else if (fast_path(c)) {
+        out[n++] = {"vpath", (const void *) k_seam_path, dim3(1), dim3(SP_THREADS), sp_smem_bytes(), 0, false};
+    } else {
+        out[n++] = {"vpath", (const void *) k_vpath, dim3(1), dim3(1024), 0, 0, false};
+    }
+    return n;
+}
 
 int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeamLaunchMax])
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
-    int n = 0;
-    if (fast)
-        out[n++] = {"vpath", (const void *) k_seam_path, dim3(1), dim3(SP_THREADS), sp_smem_bytes(), 0, false};
-    else
-        out[n++] = {"vpath", (const void *) k_vpath, dim3(1), dim3(1024), 0, 0, false};
+    int n = vpath_launch_list(c, out);
     out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false};
     out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + 7) / 8), dim3(256), 0, 0, false};
     if (!with_update) return n;
@@ -729,7 +751,7 @@ int graph_key(const B200Carver *c)
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4) |
-           (c->use_tail ? 1 << 12 : 0);
+           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0);
 }
 
 // Points the lane's graph for the current kernel set at this carver's session: the first time the nodes are added and
@@ -782,12 +804,15 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     const bool last = c->w - 1 <= 1; // the image is about to be one pixel wide
     const bool lr_switch = !last && c->lr_freq && ((l - c->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0;
     if (last) {
-        StageScope sc("vpath", s);
-        if (fast_path(c))
-            k_seam_path<<<1, SP_THREADS, sp_smem_bytes(), s>>>(view_dyn(c));
-        else
-            k_vpath<<<1, 1024, 0, s>>>(view_dyn(c));
-        B_TRY(check_launch("k_vpath"));
+        SeamLaunch L[kSeamLaunchMax];
+        const int nv = vpath_launch_list(c, L);
+        DevP pv = view_dyn(c);
+        for (int i = 0; i < nv; ++i) {
+            StageScope sc(L[i].stage, s);
+            void *args[1] = {&pv};
+            const cudaError_t e = cudaLaunchKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, s);
+            if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
+        }
         StageScope sc2("carve", s);
         k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch);
         B_TRY(check_launch("k_carve"));
@@ -1235,6 +1260,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
         if (gr) c->use_graph = atoi(gr) != 0;
         const char *tl = getenv("B200C_TAIL");
         if (tl) c->use_tail = atoi(tl) != 0;
+        const char *tr = getenv("B200C_TRACE");
+        if (tr) c->use_trace = atoi(tr) != 0;
         const char *ms = getenv("B200C_BD_MAXSEG");
         if (ms && atoi(ms) > 0) c->bd_maxseg = atoi(ms);
 

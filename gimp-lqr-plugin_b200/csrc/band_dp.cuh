@@ -29,8 +29,13 @@
 
 #include "carver_kernels.cuh"
 
+#ifndef BD_UNROLL
+#define BD_UNROLL 4 // unroll factor of the band DP's row loop
+#endif
+
 namespace b200c {
 
+constexpr int bd_unroll = BD_UNROLL;
 #define BD_NCW 12                 // compute warps = max segments of a window
 #define BD_NWARPS 13              // warp 0 producer, warp s+1 = segment s: the first four segments sit on four different sub-partitions
 #define BD_THREADS (BD_NWARPS * 32)
@@ -48,7 +53,7 @@ namespace b200c {
 #define BD_NRING 8                // descriptor / mbarrier ring
 #define BD_HMAX 4608              // rows whose energy bands fit the shared-memory table
 #define BD_HANDW (BD_NCW * 128)
-#define BD_RING_BYTES 170496      // 9 slots of 16 rows, 17 of 8 rows, 12 of 8 rows with the rigidity-mask box
+#define BD_RING_BYTES 185856      // 11 slots of 16 rows, 21 of 8 rows, 14 of 8 rows with the rigidity-mask box
 
 // rows per chunk: a longer chunk amortises the chunk boundary, but its stale halo (rows * delta_x) eats the segment
 __host__ __device__ constexpr int bd_rows(int delta_x, bool rig) { return (delta_x <= 1 && !rig) ? 16 : 8; }
@@ -56,11 +61,10 @@ __host__ __device__ constexpr int bd_rows(int delta_x, bool rig) { return (delta
 template <int D, bool RIG>
 struct BdSlot {
     static constexpr int K = bd_rows(D, RIG);
-    static constexpr int box_m = (K + 1) * BD_BW * 4, box_e = K * BD_BW * 4, box_p = K * BD_BW;
+    static constexpr int box_m = (K + 1) * BD_BW * 4, box_e = K * BD_BW * 4;
     static constexpr int off_e = box_m;
     static constexpr int off_g = box_m + box_e;
-    static constexpr int off_p = box_m + box_e + (RIG ? box_e : 0);
-    static constexpr int bytes = off_p + box_p;
+    static constexpr int bytes = off_g + (RIG ? box_e : 0);
     static constexpr int nslot = BD_RING_BYTES / bytes;
     static constexpr int HK = (K * D + 3) & ~3; // columns a segment edge goes stale over one chunk
     static constexpr int S = 128 - 2 * HK;      // stride of the segments = width of an interior
@@ -76,7 +80,7 @@ struct BdDesc {
 static constexpr size_t bd_smem_bytes()
 {
     return (size_t) BD_RING_BYTES + (size_t) BD_HMAX * 4 + 2 * BD_HANDW * 4 + BD_NRING * sizeof(BdDesc) + 256 + 64 + 64 +
-           64 * 4 + BD_NCW * 4 * 128 * 4 + 128;
+           64 * 4 + 128;
 }
 
 __device__ __forceinline__ unsigned bd_saddr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -123,17 +127,18 @@ __device__ __forceinline__ void bd_tma_load_2d(void *dst_smem, const CUtensorMap
 __device__ __forceinline__ void bd_bar_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory"); }
 
 // ------------------------------------------------------------------------------------------- compute warps
-// Everything a single warp issues per row is on the critical path of the whole update (one warp-instruction costs
-// the ALU pipe 2 cycles), so the row body carries only what the NEXT row needs: the new cumulative values.
+// Everything a single warp issues per row is on the critical path of the whole update, so the row body carries only
+// what the NEXT row needs: the new cumulative values.
 //
 //   nm = en + min(parents);  d = m_old - nm
 //   d == 0            -> nothing to decide (nm is m_old)
 //   |d| > tol         -> liblqr stores nm
 //   0 < |d| <= tol    -> "near": liblqr keeps m_old if the parent is unchanged, else stores nm.  Only this case needs
-//                        the arg-min and the stored parent; it is rare (an ulp-sized drift of a kept cell), so it
-//                        is a warp-uniform slow path.
-// The new parent offsets are not needed by the chain at all (the next row reads values, not parents): they are
-// recomputed from the final values by k_fix_parents, in parallel, after this kernel.
+//                        the arg-min and the stored parent.
+// Near rows are rare but not negligible (a few per cent of the rows of a 4K seam: near-ties between two paths), so
+// they are settled one row at a time, one row late (see the row loop).  The new parent offsets are not needed by the
+// chain at all (the next row reads values, not parents): k_fix_parents recomputes them from the final values, in
+// parallel.
 template <int D, bool LR>
 __device__ __forceinline__ int bd_argmin(const float (&cand)[2 * D + 1], float best)
 {
@@ -147,93 +152,137 @@ __device__ __forceinline__ int bd_argmin(const float (&cand)[2 * D + 1], float b
     return bdx;
 }
 
+// candidates of cell i of a lane: row y-1 at columns x0+i-D .. x0+i+D (the rigidity term is added by the callers)
+template <int D>
+__device__ __forceinline__ void bd_parents(const float (&prev)[4], float leftfloor, float (&v)[4 + 2 * D])
+{
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const float l = __shfl_up_sync(full, prev[4 - D + j], 1);
+        v[j] = fmaxf(l, leftfloor); // columns < 0 do not exist (+inf); columns >= w hold +inf in the maps (sentinels)
+        v[4 + D + j] = __shfl_down_sync(full, prev[j], 1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[D + i] = prev[i];
+}
+
+#define BD_NEAR_MAX (2u * 0x3727C5ACu - 2u)
+
+// one row, the fast way: out = en + min(parents); returns the lane's near key (<= BD_NEAR_MAX: a cell is "near").
+// near <=> 0 < |d| <= tol <=> 2 <= 2*bits(d) (sign shifted out) <= 2*bits(tol) <=> 2*bits(d) - 2 <= 2*bits(tol) - 2 as
+// unsigned; the minimum over the four cells decides for the lane.
+template <int D, bool RIG>
+__device__ __forceinline__ unsigned bd_eval(const float (&prev)[4], const float4 ce, const float4 co, const float4 cg,
+                                            const float (&rmap)[2 * D + 1], float leftfloor, float (&out)[4])
+{
+    float v[4 + 2 * D];
+    bd_parents<D>(prev, leftfloor, v);
+    const float en[4] = {ce.x, ce.y, ce.z, ce.w};
+    const float mo[4] = {co.x, co.y, co.z, co.w};
+    const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
+    unsigned u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float best = RIG ? __fadd_rn(v[i], __fmul_rn(rf[i], rmap[0])) : v[i];
+#pragma unroll
+        for (int j = 1; j <= 2 * D; ++j)
+            best = fminf(best, RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j]);
+        out[i] = __fadd_rn(en[i], best);
+        u[i] = (unsigned) __float_as_int(__fsub_rn(mo[i], out[i])) * 2u - 2u;
+    }
+    return min(min(u[0], u[1]), min(u[2], u[3]));
+}
+
+// The slow path of the row loop, kept OUT OF LINE so that the fast path stays a few dozen instructions: row q (the
+// pending one) is settled with liblqr's full rule from its parents `mq` -- a near cell keeps its old value when its
+// parent is unchanged -- stored, and row q+1 is evaluated again from the settled values.
+struct BdSlow {
+    float mq[4], mp[4], nv[4];     // in: parents of the pending row; out: the pending row, the row after it
+    const float *e, *o, *g;         // operands of the pending row in the tile (the next row's are BD_BW floats further)
+    const int8_t *pold;             // old parent offsets of the pending row (HBM)
+    float *dst;                     // where the pending row is stored, or NULL
+    float leftfloor;
+    const float *rigmap;
+    unsigned key;                   // out: near key of the row after
+    int has_next;
+};
+
 template <int D, bool RIG, bool LR>
-__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand, float *vring,
-                                           const BdDesc *desc, int *hull, unsigned long long *mbar, int seg, int lane)
+__device__ __noinline__ void bd_slow_row(BdSlow &c)
+{
+    const float inf = __int_as_float(0x7f800000);
+    const float tol = __int_as_float(0x3727C5AC); // (double) |d| < 1e-5  <=>  |d| <= this float
+    float rmap[2 * D + 1];
+#pragma unroll
+    for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? c.rigmap[j - D] : 0.f;
+    const unsigned pwo = __ldcg(reinterpret_cast<const unsigned *>(c.pold));
+    const float4 ce = *reinterpret_cast<const float4 *>(c.e), co = *reinterpret_cast<const float4 *>(c.o);
+    const float4 cg = RIG ? *reinterpret_cast<const float4 *>(c.g) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float prev[4] = {c.mq[0], c.mq[1], c.mq[2], c.mq[3]};
+    float v[4 + 2 * D];
+    bd_parents<D>(prev, c.leftfloor, v);
+    const float en[4] = {ce.x, ce.y, ce.z, ce.w};
+    const float mo[4] = {co.x, co.y, co.z, co.w};
+    const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float cand[2 * D + 1];
+        float best = inf;
+#pragma unroll
+        for (int j = 0; j <= 2 * D; ++j) {
+            cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
+            best = fminf(best, cand[j]);
+        }
+        out[i] = __fadd_rn(en[i], best);
+        const float df = __fsub_rn(mo[i], out[i]);
+        if (df != 0.f && fabsf(df) <= tol && (int) (signed char) (pwo >> (8 * i)) == bd_argmin<D, LR>(cand, best))
+            out[i] = mo[i];
+        c.mp[i] = out[i];
+    }
+    if (c.dst) *reinterpret_cast<float4 *>(c.dst) = make_float4(out[0], out[1], out[2], out[3]);
+    if (c.has_next) {
+        float nv[4];
+        c.key = bd_eval<D, RIG>(out, *reinterpret_cast<const float4 *>(c.e + BD_BW), *reinterpret_cast<const float4 *>(c.o + BD_BW),
+                                RIG ? *reinterpret_cast<const float4 *>(c.g + BD_BW) : make_float4(1.f, 1.f, 1.f, 1.f), rmap,
+                                c.leftfloor, nv);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c.nv[i] = nv[i];
+    }
+}
+
+// Chunk protocol (one named barrier per chunk, nothing else on the critical path between two chunks): the producer
+// plans chunk k+1 and WAITS for its tiles before it arrives at the barrier that ends chunk k, so a compute warp that
+// leaves that barrier finds descriptor and tiles of chunk k+1 in place -- it never polls an mbarrier itself.
+template <int D, bool RIG, bool LR>
+__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand,
+                                           const BdDesc *desc, int *hull, int seg, int lane)
 {
     using SL = BdSlot<D, RIG>;
     constexpr int HK = SL::HK, S = SL::S;
     const float inf = __int_as_float(0x7f800000);
-    const float tol = __int_as_float(0x3727C5AC); // (double) |d| < 1e-5  <=>  |d| <= this float
     const unsigned full = 0xffffffffu;
     float rmap[2 * D + 1];
 #pragma unroll
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
     float mp[4] = {0.f, 0.f, 0.f, 0.f}; // row y-1 at this lane's cells
     int hl_lo = 0, hl_hi = 0;           // hand-over range of the previous chunk
-    float leftfloor = -inf;             // +inf in the lane whose first column is column 0: its left parents do not exist
-    long long t_wait = 0, t_bar = 0, t_rows = 0, t_all = (BD_PROF && p.dbg) ? clock64() : 0;
+    long long t_bar = 0, t_rows = 0, t_pro = 0, t_epi = 0, t_all = (BD_PROF && p.dbg) ? clock64() : 0;
     int n_rows = 0, n_slow = 0;
+    auto ld4 = [](const float *q) { return *reinterpret_cast<const float4 *>(q); };
+    const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
 
-    // candidates of cell i: row y-1 at columns x0+i-D .. x0+i+D (plus the rigidity term)
-    auto parents = [&](const float (&prev)[4], float (&v)[4 + 2 * D]) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            const float l = __shfl_up_sync(full, prev[4 - D + j], 1);
-            v[j] = fmaxf(l, leftfloor); // columns < 0 do not exist (+inf); columns >= w hold +inf in the maps (sentinels)
-            v[4 + D + j] = __shfl_down_sync(full, prev[j], 1);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[D + i] = prev[i];
-    };
-    // one row, the fast way: out = en + min(parents); returns whether a cell of this lane is "near"
-    auto eval = [&](const float (&prev)[4], const float4 ce, const float4 co, const float4 cg, float (&out)[4]) -> bool {
-        float v[4 + 2 * D];
-        parents(prev, v);
-        const float en[4] = {ce.x, ce.y, ce.z, ce.w};
-        const float mo[4] = {co.x, co.y, co.z, co.w};
-        const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
-        // near <=> 0 < |d| <= tol <=> 2 <= 2*bits(d) (sign shifted out) <= 2*bits(tol) <=> 2*bits(d) - 2 <= 2*bits(tol) - 2
-        // as unsigned; the minimum over the four cells decides for the lane (IMAD + 3-input integer min: off the
-        // float compare pipe's critical path)
-        unsigned u[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float best = RIG ? __fadd_rn(v[i], __fmul_rn(rf[i], rmap[0])) : v[i];
-#pragma unroll
-            for (int j = 1; j <= 2 * D; ++j)
-                best = fminf(best, RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j]);
-            out[i] = __fadd_rn(en[i], best);
-            u[i] = (unsigned) __float_as_int(__fsub_rn(mo[i], out[i])) * 2u - 2u;
-        }
-        return min(min(u[0], u[1]), min(u[2], u[3])) <= 2u * 0x3727C5ACu - 2u;
-    };
-    // the same row with liblqr's full rule: a near cell keeps its old value when its parent is unchanged
-    auto settle = [&](const float (&prev)[4], const float4 ce, const float4 co, const float4 cg, const unsigned char *pold,
-                      float (&out)[4]) {
-        float v[4 + 2 * D];
-        parents(prev, v);
-        const float en[4] = {ce.x, ce.y, ce.z, ce.w};
-        const float mo[4] = {co.x, co.y, co.z, co.w};
-        const float rf[4] = {cg.x, cg.y, cg.z, cg.w};
-        const unsigned pwo = *reinterpret_cast<const unsigned *>(pold);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            float cand[2 * D + 1];
-            float best = inf;
-#pragma unroll
-            for (int j = 0; j <= 2 * D; ++j) {
-                cand[j] = RIG ? __fadd_rn(v[i + j], __fmul_rn(rf[i], rmap[j])) : v[i + j];
-                best = fminf(best, cand[j]);
-            }
-            out[i] = __fadd_rn(en[i], best);
-            const float df = __fsub_rn(mo[i], out[i]);
-            if (df != 0.f && fabsf(df) <= tol && (int) (signed char) (pwo >> (8 * i)) == bd_argmin<D, LR>(cand, best))
-                out[i] = mo[i];
-        }
-    };
-
+    bd_bar_chunk(); // chunk 0 is planned and has landed
     for (int k = 0;; ++k) {
-        long long t0 = 0;
-        if (BD_PROF && p.dbg) t0 = clock64();
-        if (!bd_mbar_wait(&mbar[k % BD_NRING], (unsigned) ((k / BD_NRING) & 1))) atomicOr(p.err, 4);
-        if (BD_PROF && p.dbg) t_wait += clock64() - t0;
+        long long tp0 = 0;
+        if (BD_PROF && p.dbg) tp0 = clock64();
         const BdDesc d = desc[k % BD_NRING];
         if (d.rows == 0) break;
         int *hull_k = hull + (k & 1) * (2 * BD_NCW);
-        const int lw = d.nb * BD_BW;
         if (seg < d.nseg) {
             const int rows = d.rows;
+            const int lw = d.nb * BD_BW;
             const int x0 = d.llo + seg * S + 4 * lane;
             const int c = min(x0 - d.llo, lw - 4);
             // a segment edge next to another segment -- or to columns that were not fetched -- goes stale; an edge
@@ -246,7 +295,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 #else
             const bool st = interior && x0 >= d.elo && x0 <= d.ehi;
 #endif
-            leftfloor = x0 == 0 ? inf : -inf;
+            const float leftfloor = x0 == 0 ? inf : -inf; // +inf in the lane whose first column is column 0
 
             int slot = d.slot0 + (c >> 7);
             if (slot >= SL::nslot) slot -= SL::nslot;
@@ -255,111 +304,91 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             const float *op = reinterpret_cast<const float *>(sb) + cc;               // m rows -1 .. K-1
             const float *ep = reinterpret_cast<const float *>(sb + SL::off_e) + cc;   // en rows 0 .. K-1
             const float *gq = reinterpret_cast<const float *>(sb + SL::off_g) + cc;   // rigidity mask rows (RIG)
-            const unsigned char *pp = sb + SL::off_p + cc;                            // pdx rows 0 .. K-1 (settle only)
 
             if (d.y0 > 0) {
-                const float4 v = (x0 >= hl_lo && x0 < hl_hi)
-                                     ? *reinterpret_cast<const float4 *>(hand + ((k - 1) & 1) * BD_HANDW + (x0 - hl_lo))
-                                     : *reinterpret_cast<const float4 *>(op);
+                const float4 v = (x0 >= hl_lo && x0 < hl_hi) ? ld4(hand + ((k - 1) & 1) * BD_HANDW + (x0 - hl_lo)) : ld4(op);
                 mp[0] = v.x, mp[1] = v.y, mp[2] = v.z, mp[3] = v.w;
             }
-            // operands of the row about to be computed; the next row's are fetched before the chain of this one
-            // (the fetch past the last row reads the neighbouring box of the slot and is never used)
-            op += BD_BW;
-            float4 e4 = *reinterpret_cast<const float4 *>(ep);
-            float4 o4 = *reinterpret_cast<const float4 *>(op);
-            float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-            if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
-            long long tr0 = 0;
-            if (BD_PROF && p.dbg) tr0 = clock64();
-            unsigned go = (unsigned) d.y0 * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
+            op += BD_BW; // row 0 of the chunk
+            const float4 po = ld4(op + (size_t) (rows - 1) * BD_BW); // old values of the last row
+            float *gm = p.m + ((size_t) d.y0 * p.pitch + x0);                          // this lane's cells, row by row
+            const int8_t *gpd = p.pdx + ((size_t) d.y0 * p.pitch + min(x0, p.pitch - 4)); // old parents (slow path only)
             int r = 0;
             if (d.y0 == 0) { // row 0 of the image: m = en (A.8; true of every cell of the row, evaluated or not)
+                const float4 e4 = ld4(ep);
                 mp[0] = e4.x, mp[1] = e4.y, mp[2] = e4.z, mp[3] = e4.w;
-                if (st) *reinterpret_cast<float4 *>(p.m + go) = e4;
-                ep += BD_BW, op += BD_BW, pp += BD_BW, gq += BD_BW, go += p.pitch;
-                e4 = *reinterpret_cast<const float4 *>(ep);
-                o4 = *reinterpret_cast<const float4 *>(op);
-                if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
+                if (st) *reinterpret_cast<float4 *>(gm) = e4;
+                gm += p.pitch;
                 r = 1;
+            }
+            long long tr0 = 0;
+            if (BD_PROF && p.dbg) {
+                tr0 = clock64();
+                t_pro += tr0 - tp0;
             }
             // The row loop is SPECULATIVE by one row: row r is computed from row r-1's fast values while the question
             // "did row r-1 have a near cell?" is still open, so the vote + branch that answers it is off the chain
-            // (loop-carried dependency: shuffle -> 3-input min -> add).  If it did (rare), row r-1 is settled with
-            // the full rule -- its operands are still in the tile, its parents (row r-2) in this warp's value ring --
-            // and row r is redone.
-            float *vr = vring + lane * 4; // [4][128] per warp: the values of the last rows, slot = (row + 1) & 3
-            const float *e0 = ep - (size_t) r * BD_BW, *o0 = op - (size_t) r * BD_BW, *g0 = gq - (size_t) r * BD_BW;
-            const unsigned char *p0 = pp - (size_t) r * BD_BW;
-            *reinterpret_cast<float4 *>(vr + (r & 3) * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]); // row r-1
-            bool pend = false;
-#pragma unroll 4
+            // (loop-carried dependency: shuffle -> 3-input min -> add).  If it did (a few per cent of the rows), the
+            // out-of-line slow path settles row r-1 with the full rule -- its operands are still in the tile, its
+            // parents (row r-2) in registers, its old parent offsets are read from HBM there and only there -- and
+            // redoes row r.
+            float mq[4] = {mp[0], mp[1], mp[2], mp[3]}; // row r-2, final
+            bool pend = false;                          // row r-1 has a near cell in this lane
+            auto slow = [&](int q, float (&nv)[4], unsigned &key, bool has_next) {
+                BdSlow c;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) c.mq[i] = mq[i];
+                c.e = ep + q * BD_BW, c.o = op + q * BD_BW, c.g = gq + q * BD_BW;
+                c.pold = gpd + (size_t) q * p.pitch;
+                c.dst = st ? gm - p.pitch : nullptr;
+                c.leftfloor = leftfloor;
+                c.rigmap = p.rigmap;
+                c.has_next = has_next;
+                bd_slow_row<D, RIG, LR>(c);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) mp[i] = c.mp[i], nv[i] = c.nv[i];
+                key = c.key;
+                ++n_slow;
+            };
+#pragma unroll bd_unroll
             for (; r < rows; ++r) {
-                const float4 ce = e4, co = o4, cg = g4;
-                ep += BD_BW, op += BD_BW, gq += BD_BW;
-                e4 = *reinterpret_cast<const float4 *>(ep);
-                o4 = *reinterpret_cast<const float4 *>(op);
-                if (RIG) g4 = *reinterpret_cast<const float4 *>(gq);
                 float nv[4];
-                bool nr = eval(mp, ce, co, cg, nv);
+                unsigned key = bd_eval<D, RIG>(mp, ld4(ep + r * BD_BW), ld4(op + r * BD_BW), RIG ? ld4(gq + r * BD_BW) : one4, rmap,
+                                               leftfloor, nv);
 #ifdef BD_DEBUG_ALWAYS_SLOW
                 pend = r > (d.y0 == 0 ? 1 : 0);
 #endif
-                if (__any_sync(full, pend)) {
-                    const int q = r - 1; // the pending row; its parents are row r-2
-                    const float4 m2 = *reinterpret_cast<const float4 *>(vr + ((r - 1) & 3) * 128);
-                    const float pr[4] = {m2.x, m2.y, m2.z, m2.w};
-                    float4 qg = make_float4(1.f, 1.f, 1.f, 1.f);
-                    if (RIG) qg = *reinterpret_cast<const float4 *>(g0 + (size_t) q * BD_BW);
-                    settle(pr, *reinterpret_cast<const float4 *>(e0 + (size_t) q * BD_BW),
-                           *reinterpret_cast<const float4 *>(o0 + (size_t) q * BD_BW), qg, p0 + (size_t) q * BD_BW, mp);
-                    if (st) *reinterpret_cast<float4 *>(p.m + go - p.pitch) = make_float4(mp[0], mp[1], mp[2], mp[3]);
-                    *reinterpret_cast<float4 *>(vr + (r & 3) * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]);
-                    nr = eval(mp, ce, co, cg, nv);
-                    ++n_slow;
-                }
-                *reinterpret_cast<float4 *>(vr + ((r + 1) & 3) * 128) = make_float4(nv[0], nv[1], nv[2], nv[3]);
-                if (st) *reinterpret_cast<float4 *>(p.m + go) = make_float4(nv[0], nv[1], nv[2], nv[3]);
-                go += p.pitch;
+                if (__any_sync(full, pend)) slow(r - 1, nv, key, true);
+                if (st) *reinterpret_cast<float4 *>(gm) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+                gm += p.pitch;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mp[i] = nv[i];
-                pend = nr;
+                for (int i = 0; i < 4; ++i) mq[i] = mp[i], mp[i] = nv[i];
+                pend = key <= BD_NEAR_MAX;
             }
             if (__any_sync(full, pend)) { // the last row of the chunk is still open
-                const int q = rows - 1;
-                const float4 m2 = *reinterpret_cast<const float4 *>(vr + ((rows - 1) & 3) * 128);
-                const float pr[4] = {m2.x, m2.y, m2.z, m2.w};
-                float4 qg = make_float4(1.f, 1.f, 1.f, 1.f);
-                if (RIG) qg = *reinterpret_cast<const float4 *>(g0 + (size_t) q * BD_BW);
-                settle(pr, *reinterpret_cast<const float4 *>(e0 + (size_t) q * BD_BW),
-                       *reinterpret_cast<const float4 *>(o0 + (size_t) q * BD_BW), qg, p0 + (size_t) q * BD_BW, mp);
-                if (st) *reinterpret_cast<float4 *>(p.m + go - p.pitch) = make_float4(mp[0], mp[1], mp[2], mp[3]);
-                ++n_slow;
+                float nv[4];
+                unsigned key;
+                slow(rows - 1, nv, key, false);
             }
-            const float4 po = *reinterpret_cast<const float4 *>(o0 + (size_t) (rows - 1) * BD_BW); // old values of the last row
+            long long te0 = 0;
             if (BD_PROF && p.dbg) {
-                t_rows += clock64() - tr0;
+                te0 = clock64();
+                t_rows += te0 - tr0;
                 n_rows += rows;
             }
             // hand the last row over and publish the hull of the cells whose VALUE changed in it (a changed parent
             // alone does not matter to the next row); po = the old values of the last row computed
             if (interior) *reinterpret_cast<float4 *>(hand + (k & 1) * BD_HANDW + (x0 - d.hlo)) = make_float4(mp[0], mp[1], mp[2], mp[3]);
-            unsigned chg = 0;
-            if (st && (rows > 1 || d.y0 > 0))
-                chg = (mp[0] != po.x ? 1u : 0u) | (mp[1] != po.y ? 2u : 0u) | (mp[2] != po.z ? 4u : 0u) | (mp[3] != po.w ? 8u : 0u);
-            else if (st) // the chunk was row 0 alone
-                chg = 0xfu;
-            int lo = INT_MAX, hi = INT_MIN;
-            if (chg) {
-                lo = x0 + __ffs(chg) - 1;
-                hi = x0 + 31 - __clz(chg);
-            }
-            lo = __reduce_min_sync(full, lo);
-            hi = __reduce_max_sync(full, hi);
+            // the hull at lane granularity (4 cells): a superset of the changed cells, which is all the planner needs
+            bool chg = st;
+            if (st && (rows > 1 || d.y0 > 0)) chg = mp[0] != po.x || mp[1] != po.y || mp[2] != po.z || mp[3] != po.w;
+            const unsigned bal = __ballot_sync(full, chg);
             if (lane == 0) {
-                hull_k[2 * seg] = lo;
-                hull_k[2 * seg + 1] = hi;
+                const int xs = d.llo + seg * S;
+                hull_k[2 * seg] = bal ? xs + 4 * (__ffs(bal) - 1) : INT_MAX;
+                hull_k[2 * seg + 1] = bal ? xs + 4 * (31 - __clz(bal)) + 3 : INT_MIN;
             }
+            if (BD_PROF && p.dbg) t_epi += clock64() - te0;
         } else if (lane == 0) {
             hull_k[2 * seg] = INT_MAX;
             hull_k[2 * seg + 1] = INT_MIN;
@@ -372,22 +401,24 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
         hl_hi = d.hhi;
     }
     if (BD_PROF && p.dbg && lane == 0) {
-        atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 0 : 2], (unsigned long long) t_wait);
         atomicAdd((unsigned long long *) &p.dbg[seg == 0 ? 1 : 3], (unsigned long long) t_bar);
         if (seg == 0) {
+            atomicAdd((unsigned long long *) &p.dbg[0], (unsigned long long) t_pro);
+            atomicAdd((unsigned long long *) &p.dbg[2], (unsigned long long) t_epi);
             atomicAdd((unsigned long long *) &p.dbg[5], (unsigned long long) t_rows);
             atomicAdd((unsigned long long *) &p.dbg[6], (unsigned long long) (clock64() - t_all));
             atomicAdd((unsigned long long *) &p.dbg[7], (unsigned long long) n_rows);
             atomicAdd((unsigned long long *) &p.dbg[10], (unsigned long long) n_slow);
         } else {
             atomicAdd((unsigned long long *) &p.dbg[8], (unsigned long long) n_rows);
+            atomicAdd((unsigned long long *) &p.dbg[11], (unsigned long long) n_slow);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------- producer warp
 struct BdMaps {
-    CUtensorMap m, en, pdx, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
+    CUtensorMap m, en, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
 };
 
 template <int D, bool RIG>
@@ -439,7 +470,9 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             nb = (need + BD_BW - 1) / BD_BW;
             lw = nb * BD_BW;
             ropen = llo + min(lw, (nseg - 1) * S + 128) >= wlim; // fetched AND covered by the last segment
-            if (nseg > min(BD_NCW, p.bd_maxseg) || nb > SL::nslot) end_y = ya; // too wide: the exact generic loop takes over at row ya
+            // too wide for the tiled path (a chunk may take at most half of the ring, so that the next chunk always fits
+            // beside the one in use): the tail kernel / the exact generic loop takes over at row ya
+            if (nseg > min(BD_NCW, p.bd_maxseg) || 2 * nb > SL::nslot) end_y = ya;
         }
         if (end_y < 0 && nb > slots_free) return false;
         if (end_y >= 0) {
@@ -475,7 +508,6 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
                 bd_tma_load_2d(sb, &tm.m, cx, ya - 1, mb);
                 bd_tma_load_2d(sb + SL::off_e, &tm.en, cx, ya, mb);
                 if (RIG) bd_tma_load_2d(sb + SL::off_g, &tm.rig, cx, ya, mb);
-                bd_tma_load_2d(sb + SL::off_p, &tm.pdx, cx, ya, mb);
             }
             slot_next += nb;
             if (slot_next >= SL::nslot) slot_next -= SL::nslot;
@@ -488,10 +520,13 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         return true;
     };
 
+    // chunk 0: planned, landed, then the start barrier
+    while (!ended && kp <= BD_LA)
+        if (!plan_issue()) break;
+    if (!bd_mbar_wait(&mbar[0], 0u)) atomicOr(p.err, 4);
+    bd_bar_chunk();
+    long long t_tiles = 0;
     for (int k = 0;; ++k) {
-        // chunk k must be planned by now, and up to BD_LA more while the ring has room
-        while (!ended && kp <= k + BD_LA)
-            if (!plan_issue()) break;
         const BdDesc *dk = desc + (k % BD_NRING);
         const int rows_k = dk->rows, y0_k = dk->y0, nb_k = dk->nb;
         if (rows_k == 0) {
@@ -502,6 +537,16 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             }
             break;
         }
+        // chunk k+1 must be planned (there is always room for it: a chunk takes at most half of the ring) and up to
+        // BD_LA more while the ring has room; then its tiles must have landed before anybody leaves the barrier
+        while (!ended && kp <= k + BD_LA)
+            if (!plan_issue()) break;
+        if (kp < k + 2 && lane == 0) atomicOr(p.err, 4); // cannot happen: see the ring-space rule in plan_issue
+        {
+            const long long tw0 = (BD_PROF && p.dbg) ? clock64() : 0;
+            if (kp >= k + 2 && !bd_mbar_wait(&mbar[(k + 1) % BD_NRING], (unsigned) (((k + 1) / BD_NRING) & 1))) atomicOr(p.err, 4);
+            if (BD_PROF && p.dbg) t_tiles += clock64() - tw0;
+        }
         bd_bar_chunk(); // end of chunk k: its slots are free, the hull of its last row is known
         slots_free += nb_k;
         const int *hull_k = hull + (k & 1) * (2 * BD_NCW);
@@ -511,6 +556,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         hhi = __reduce_max_sync(full, hi);
         yl = y0_k + rows_k - 1;
     }
+    if (BD_PROF && p.dbg && lane == 0) atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) t_tiles);
     if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
     if (lane == 0 && p.fixn) *p.fixn = kp - 1; // chunks whose parents k_fix_parents has to recompute (the last is the end marker)
     if (BD_PROF && p.dbg && lane == 0) {
@@ -674,7 +720,6 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(hull + 64); // [BD_NRING]
     volatile int *misc = reinterpret_cast<volatile int *>(mbar + BD_NRING);
     int *s_red = const_cast<int *>(misc) + 16;
-    float *vals = reinterpret_cast<float *>(s_red + 64); // [BD_NCW][4][128]: each compute warp's last rows
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int y = tid; y < p.h; y += BD_THREADS) nrg[y] = p.nrg_pack[y];
@@ -688,7 +733,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const
     if (warp == 0) {
         bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane);
     } else {
-        bd_compute<D, RIG, LR>(p, ring, hand, vals + (size_t) (warp - 1) * 4 * 128, desc, hull, mbar, warp - 1, lane);
+        bd_compute<D, RIG, LR>(p, ring, hand, desc, hull, warp - 1, lane);
     }
     __syncthreads();
     const int y_from = misc[0];

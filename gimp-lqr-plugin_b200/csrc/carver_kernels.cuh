@@ -47,6 +47,7 @@ struct DevP {
     float *en;         // compact
     float *m;          // compact
     int8_t *pdx;       // compact
+    signed char *jump; // [row blocks][pitch]: net column offset of a path across a block of rows (seam_trace.cuh)
     float *rig;        // compact copy of the rigidity mask (NULL without a mask)
     const float *bias;
     const float *rigmask;

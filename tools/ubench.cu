@@ -125,6 +125,155 @@ __global__ void k_row_body(const float *en_g, float *m_g, long long *cyc, int ro
     m_g[go + 1] = mp[0] + mp[1] + mp[2] + mp[3];
 }
 
+// the same row body with the near vote taken every row but consumed one row late (off the chain)
+__global__ void k_row_body_lag(const float *en_g, float *m_g, long long *cyc, int rows, int pitch)
+{
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float *es = sm + (size_t) warp * 2 * 16 * 128;
+    float *os = es + 16 * 128;
+    for (int i = lane; i < 16 * 128; i += 32) {
+        es[i] = en_g[(i * 13 + warp) % 4096];
+        os[i] = en_g[(i * 7 + warp) % 4096] * 100.f;
+    }
+    __syncthreads();
+    float mp[4] = {1.f + lane, 2.f, 3.f, 4.f};
+    const float inf = __int_as_float(0x7f800000);
+    const float leftfloor = lane == 0 ? inf : -inf;
+    unsigned go = warp * 128 + 4 * lane;
+    int redo = 0;
+    bool pend = false;
+    long long t0 = clock64();
+    for (int r0 = 0; r0 < rows; r0 += 16) {
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+            const float4 e4 = *reinterpret_cast<const float4 *>(es + r * 128 + 4 * lane);
+            const float4 o4 = *reinterpret_cast<const float4 *>(os + r * 128 + 4 * lane);
+            const float l = fmaxf(__shfl_up_sync(0xffffffffu, mp[3], 1), leftfloor);
+            const float rr = __shfl_down_sync(0xffffffffu, mp[0], 1);
+            float nv[4];
+            nv[0] = __fadd_rn(e4.x, fminf(fminf(l, mp[0]), mp[1]));
+            nv[1] = __fadd_rn(e4.y, fminf(fminf(mp[0], mp[1]), mp[2]));
+            nv[2] = __fadd_rn(e4.z, fminf(fminf(mp[1], mp[2]), mp[3]));
+            nv[3] = __fadd_rn(e4.w, fminf(fminf(mp[2], mp[3]), rr));
+            const unsigned u0 = (unsigned) __float_as_int(__fsub_rn(o4.x, nv[0])) * 2u - 2u;
+            const unsigned u1 = (unsigned) __float_as_int(__fsub_rn(o4.y, nv[1])) * 2u - 2u;
+            const unsigned u2 = (unsigned) __float_as_int(__fsub_rn(o4.z, nv[2])) * 2u - 2u;
+            const unsigned u3 = (unsigned) __float_as_int(__fsub_rn(o4.w, nv[3])) * 2u - 2u;
+            const unsigned key = min(min(u0, u1), min(u2, u3));
+            if (__any_sync(0xffffffffu, pend)) {
+                ++redo;
+                nv[0] += 1.f;
+            }
+            *reinterpret_cast<float4 *>(m_g + go) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+            go += pitch;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mp[i] = nv[i];
+            pend = key <= 2u * 0x3727C5ACu - 2u;
+        }
+    }
+    long long t1 = clock64();
+    if (lane == 0) cyc[warp] = t1 - t0;
+    if (threadIdx.x == 0) cyc[nw] = redo;
+    m_g[go + 1] = mp[0] + mp[1] + mp[2] + mp[3];
+}
+
+// near key on the fma pipe: bits(d) * 2 - 2 as an integer multiply-add (the compiler turns the C expression into an
+// IADD3, which shares the alu pipe with the 3-input minima)
+__device__ __forceinline__ unsigned nearkey(float d)
+{
+    unsigned r;
+    asm("mad.lo.u32 %0, %1, 2, 0xfffffffe;" : "=r"(r) : "r"(__float_as_uint(d)));
+    return r;
+}
+
+// Variant: TWO rows per shuffle round.  Each lane also computes the cells one column left and right of its own four on
+// the first row of a pair (from two shuffled values per side), so the second row needs no shuffle: the loop-carried
+// chain is shuffle + 2 x (min3 + add) per two rows.
+template <int VR, bool IMADKEY>
+__global__ void k_row_body2(const float *en_g, float *m_g, long long *cyc, int rows, int pitch)
+{
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float *es = sm + (size_t) warp * 2 * 16 * 136; // en rows with one spare float4 on each side: [16][136]
+    float *os = es + 16 * 136;
+    for (int i = lane; i < 16 * 136; i += 32) {
+        es[i] = en_g[(i * 13 + warp) % 4096];
+        os[i] = en_g[(i * 7 + warp) % 4096] * 100.f;
+    }
+    __syncthreads();
+    float mp[4] = {1.f + lane, 2.f, 3.f, 4.f};
+    const float inf = __int_as_float(0x7f800000);
+    const float leftfloor = lane == 0 ? inf : -inf;
+    unsigned go = warp * 128 + 4 * lane;
+    int redo = 0;
+    long long t0 = clock64();
+    for (int r0 = 0; r0 < rows; r0 += VR) {
+        unsigned umin = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < VR; k += 2) {
+            const int r = (r0 + k) & 15;
+            const float *e = es + r * 136 + 4 + 4 * lane;
+            const float *o = os + r * 136 + 4 + 4 * lane;
+            const float4 e4 = *reinterpret_cast<const float4 *>(e);
+            const float el = e[-1], er = e[4];
+            const float4 o4 = *reinterpret_cast<const float4 *>(o);
+            const float4 f4 = *reinterpret_cast<const float4 *>(e + 136);
+            const float4 q4 = *reinterpret_cast<const float4 *>(o + 136);
+            const float l2 = fmaxf(__shfl_up_sync(0xffffffffu, mp[2], 1), leftfloor);
+            const float l3 = fmaxf(__shfl_up_sync(0xffffffffu, mp[3], 1), leftfloor);
+            const float r0v = __shfl_down_sync(0xffffffffu, mp[0], 1);
+            const float r1v = __shfl_down_sync(0xffffffffu, mp[1], 1);
+            float a[6], b[4];
+            a[0] = fmaxf(__fadd_rn(el, fminf(fminf(l2, l3), mp[0])), leftfloor);
+            a[1] = __fadd_rn(e4.x, fminf(fminf(l3, mp[0]), mp[1]));
+            a[2] = __fadd_rn(e4.y, fminf(fminf(mp[0], mp[1]), mp[2]));
+            a[3] = __fadd_rn(e4.z, fminf(fminf(mp[1], mp[2]), mp[3]));
+            a[4] = __fadd_rn(e4.w, fminf(fminf(mp[2], mp[3]), r0v));
+            a[5] = __fadd_rn(er, fminf(fminf(mp[3], r0v), r1v));
+            b[0] = __fadd_rn(f4.x, fminf(fminf(a[0], a[1]), a[2]));
+            b[1] = __fadd_rn(f4.y, fminf(fminf(a[1], a[2]), a[3]));
+            b[2] = __fadd_rn(f4.z, fminf(fminf(a[2], a[3]), a[4]));
+            b[3] = __fadd_rn(f4.w, fminf(fminf(a[3], a[4]), a[5]));
+            unsigned u[8];
+            const float d0 = __fsub_rn(o4.x, a[1]), d1 = __fsub_rn(o4.y, a[2]), d2 = __fsub_rn(o4.z, a[3]), d3 = __fsub_rn(o4.w, a[4]);
+            const float d4 = __fsub_rn(q4.x, b[0]), d5 = __fsub_rn(q4.y, b[1]), d6 = __fsub_rn(q4.z, b[2]), d7 = __fsub_rn(q4.w, b[3]);
+            if (IMADKEY) {
+                u[0] = nearkey(d0), u[1] = nearkey(d1), u[2] = nearkey(d2), u[3] = nearkey(d3);
+                u[4] = nearkey(d4), u[5] = nearkey(d5), u[6] = nearkey(d6), u[7] = nearkey(d7);
+            } else {
+                u[0] = __float_as_uint(d0) * 2u - 2u, u[1] = __float_as_uint(d1) * 2u - 2u, u[2] = __float_as_uint(d2) * 2u - 2u, u[3] = __float_as_uint(d3) * 2u - 2u;
+                u[4] = __float_as_uint(d4) * 2u - 2u, u[5] = __float_as_uint(d5) * 2u - 2u, u[6] = __float_as_uint(d6) * 2u - 2u, u[7] = __float_as_uint(d7) * 2u - 2u;
+            }
+            umin = min(min(min(umin, u[0]), min(u[1], u[2])), min(min(u[3], u[4]), min(min(u[5], u[6]), u[7])));
+            *reinterpret_cast<float4 *>(m_g + go) = make_float4(a[1], a[2], a[3], a[4]);
+            *reinterpret_cast<float4 *>(m_g + go + pitch) = make_float4(b[0], b[1], b[2], b[3]);
+            go += 2 * pitch;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mp[i] = b[i];
+        }
+        if (__any_sync(0xffffffffu, umin <= 2u * 0x3727C5ACu - 2u)) ++redo;
+    }
+    long long t1 = clock64();
+    if (lane == 0) cyc[warp] = t1 - t0;
+    if (threadIdx.x == 0) cyc[nw] = redo;
+    m_g[go + 1] = mp[0] + mp[1] + mp[2] + mp[3];
+}
+
+template <int VR, bool IMADKEY>
+int run_body2(const char *name, float *d_f, long long *d_c, int rows, int pitch)
+{
+    long long h_c[64];
+    CHECK(cudaFuncSetAttribute(k_row_body2<VR, IMADKEY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int nw : {1, 3, 4, 8}) {
+        const size_t smem = (size_t) nw * 2 * 16 * 136 * 4;
+        for (int rep = 0; rep < 2; ++rep) k_row_body2<VR, IMADKEY><<<1, nw * 32, smem>>>(d_f, d_f + (8 << 20), d_c, rows, pitch);
+        CHECK(cudaMemcpy(h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost));
+        printf("%s, %2d warps: %.1f cycles/row\n", name, nw, (double) h_c[0] / rows);
+    }
+    return 0;
+}
+
 int main()
 {
     float *d_f;
@@ -187,6 +336,16 @@ int main()
         CHECK(cudaMemcpy(h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost));
         printf("row body, vote/16 rows, 1 warp : %.1f cycles/row\n", (double) h_c[0] / rows);
     }
+    for (int nw : {1, 3, 4}) {
+        const size_t smem = (size_t) nw * 2 * 16 * 128 * 4;
+        for (int rep = 0; rep < 2; ++rep) k_row_body_lag<<<1, nw * 32, smem>>>(d_f, d_f + (8 << 20), d_c, rows, pitch);
+        CHECK(cudaMemcpy(h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost));
+        printf("row body, lagged vote every row, %2d warps: %.1f cycles/row (redo %lld)\n", nw, (double) h_c[0] / rows, h_c[nw]);
+    }
+    run_body2<8, false>("2-row steps, vote/8 ", d_f, d_c, rows, pitch);
+    run_body2<8, true>("2-row steps, vote/8, imad key", d_f, d_c, rows, pitch);
+    run_body2<16, true>("2-row steps, vote/16, imad key", d_f, d_c, rows, pitch);
+    run_body2<4, true>("2-row steps, vote/4, imad key", d_f, d_c, rows, pitch);
     CHECK(cudaDeviceSynchronize());
     return 0;
 }
