@@ -257,6 +257,11 @@ struct B200Carver {
     int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
     bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
     bool use_trace = true;                    // B200C_TRACE=0: the single-CTA staged backtrack (seam_path.cuh)
+    // batch session (b200c_batch_build_maps): this carver LEADS, its launches advance the mates too (image = blockIdx.z)
+    std::vector<B200Carver *> mates;
+    DevP *tab_d = nullptr;                    // [2][n]: per-seam argument blocks, then the full-pass ones
+    BdMaps *mtab_d = nullptr;                 // [n] tensor maps
+    int tab_n = 0;
     alignas(64) BdMaps maps;                  // TMA tensor maps over the compact arrays (band DP)
     int *err_d = nullptr;                     // device error word (see DevP::err)
     unsigned long long *cells_d = nullptr;    // band cells visited by the incremental DP
@@ -373,6 +378,35 @@ DevP view_dyn(const B200Carver *c)
     return p;
 }
 
+// ---- batch sessions: one launch advances the leader and its mates; the kernels pick their image by blockIdx.z from a
+// table of argument blocks in HBM (carver_kernels.cuh pick_image).  A lone carver passes no table.
+int batch_n(const B200Carver *c) { return 1 + (int) c->mates.size(); }
+const DevP *tab_dyn(const B200Carver *c) { return c->mates.empty() ? nullptr : c->tab_d; }
+const DevP *tab_static(const B200Carver *c) { return c->mates.empty() ? nullptr : c->tab_d + c->tab_n; }
+const BdMaps *tab_maps(const B200Carver *c) { return c->mates.empty() ? nullptr : c->mtab_d; }
+
+template <class F>
+void for_batch(B200Carver *c, F f)
+{
+    f(c);
+    for (B200Carver *m : c->mates) f(m);
+}
+
+// (re)writes one half of the table: dyn = the per-seam blocks (view_dyn), else the full-pass blocks (view)
+int upload_tab(B200Carver *c, bool dyn)
+{
+    if (c->mates.empty()) return B200C_OK;
+    std::vector<DevP> h;
+    for_batch(c, [&](B200Carver *m) { h.push_back(dyn ? view_dyn(m) : view(m)); });
+    CU_TRY(cudaMemcpyAsync(c->tab_d + (dyn ? 0 : c->tab_n), h.data(), h.size() * sizeof(DevP), cudaMemcpyHostToDevice, c->stream));
+    if (dyn) {
+        std::vector<BdMaps> hm;
+        for_batch(c, [&](B200Carver *m) { hm.push_back(m->maps); });
+        CU_TRY(cudaMemcpyAsync(c->mtab_d, hm.data(), hm.size() * sizeof(BdMaps), cudaMemcpyHostToDevice, c->stream));
+    }
+    return B200C_OK; // pageable sources: staged by the runtime before the calls return
+}
+
 void set_width_one(B200Carver *c, int w1)
 {
     c->w = w1;
@@ -468,6 +502,7 @@ int alloc_maps(B200Carver *c)
         const int K = bd_rows(c->delta_x, c->rigidity != 0.f);
         B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, K + 1));
         B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, K));
+        B_TRY(encode_map(&c->maps.pdx, c->pdx, true, c->pitch, c->h_start, K));
         c->maps.rig = c->maps.en;
     }
     return B200C_OK;
@@ -486,11 +521,12 @@ int init_energy_related(B200Carver *c)
 int build_emap(B200Carver *c)
 {
     if (c->nrg_uptodate) return B200C_OK;
-    dim3 grid((c->pitch + 255) / 256, c->h);
+    B_TRY(upload_tab(c, false));
+    dim3 grid((c->pitch + 255) / 256, c->h, batch_n(c));
     StageScope sc("energy_full", c->stream);
-    k_energy_full<<<grid, 256, 0, c->stream>>>(view(c));
+    k_energy_full<<<grid, 256, 0, c->stream>>>(view(c), tab_static(c));
     B_TRY(check_launch("k_energy_full"));
-    c->nrg_uptodate = true;
+    for_batch(c, [](B200Carver *m) { m->nrg_uptodate = true; });
     return B200C_OK;
 }
 
@@ -594,19 +630,22 @@ const void *band_dp_fn(const B200Carver *c, bool fix)
 }
 
 template <int D>
-void launch_mmap_full_d(B200Carver *c, int grid, int y0, int rows)
+void launch_mmap_full_d(B200Carver *c, int gridx, int y0, int rows)
 {
     const DevP p = view(c);
+    const DevP *tab = tab_static(c);
+    const dim3 grid(gridx, 1, batch_n(c));
     const bool rig = c->rigidity != 0.f, lr = c->leftright != 0;
     const size_t sm = mf_smem_bytes(D, rig);
-    if (rig && lr) k_mmap_full_strips<D, true, true><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
-    else if (rig) k_mmap_full_strips<D, true, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
-    else if (lr) k_mmap_full_strips<D, false, true><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
-    else k_mmap_full_strips<D, false, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows);
+    if (rig && lr) k_mmap_full_strips<D, true, true><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows, tab);
+    else if (rig) k_mmap_full_strips<D, true, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows, tab);
+    else if (lr) k_mmap_full_strips<D, false, true><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows, tab);
+    else k_mmap_full_strips<D, false, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows, tab);
 }
 
 int build_mmap(B200Carver *c)
 {
+    B_TRY(upload_tab(c, false));
     if (fast_path(c) && c->delta_x <= 4) {
         B_TRY(raise_smem_limits(c->device));
         const int R = mf_rows(c->delta_x), S = 128 - 2 * mf_hk(c->delta_x);
@@ -626,7 +665,7 @@ int build_mmap(B200Carver *c)
         return check_launch("k_mmap_full_strips");
     }
     StageScope sc("mmap_full", c->stream);
-    k_mmap_full<<<1, 1024, 0, c->stream>>>(view(c));
+    k_mmap_full<<<dim3(1, 1, batch_n(c)), 1024, 0, c->stream>>>(view(c), tab_static(c));
     return check_launch("k_mmap_full");
 }
 
@@ -728,17 +767,46 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
     return n;
 }
 
+// kernel parameters of one launch of the list: (DevP, table) | (DevP, int, table) | (DevP, BdMaps, table, map table)
+struct SeamArgs {
+    DevP p;
+    int epoch;
+    const DevP *tab;
+    const BdMaps *mtab;
+    void *ptr[4];
+    void **of(const B200Carver *c, const SeamLaunch &l)
+    {
+        int n = 0;
+        ptr[n++] = &p;
+        if (l.second == 1) ptr[n++] = &epoch;
+        if (l.second == 2) ptr[n++] = const_cast<BdMaps *>(&c->maps);
+        ptr[n++] = &tab;
+        if (l.second == 2) ptr[n++] = &mtab;
+        return ptr;
+    }
+};
+SeamArgs seam_args(const B200Carver *c)
+{
+    SeamArgs a;
+    a.p = view_dyn(c);
+    a.epoch = c->vs_epoch;
+    a.tab = tab_dyn(c);
+    a.mtab = tab_maps(c);
+    return a;
+}
+dim3 batch_grid(const B200Carver *c, dim3 g) { return dim3(g.x, g.y, batch_n(c)); }
+
 int launch_seam_kernels(B200Carver *c, bool with_update)
 {
     SeamLaunch L[kSeamLaunchMax];
     const int n = seam_launch_list(c, with_update, L);
-    DevP p = view_dyn(c);
-    int epoch = c->vs_epoch;
+    SeamArgs a = seam_args(c);
     for (int i = 0; i < n; ++i) {
         StageScope sc(L[i].stage, c->stream);
-        void *args[2] = {&p, L[i].second == 2 ? (void *) &c->maps : (void *) &epoch};
-        const cudaError_t e = L[i].coop ? cudaLaunchCooperativeKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, c->stream)
-                                        : cudaLaunchKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, c->stream);
+        void **args = a.of(c, L[i]);
+        const dim3 grid = batch_grid(c, L[i].grid);
+        const cudaError_t e = L[i].coop ? cudaLaunchCooperativeKernel(L[i].fn, grid, L[i].block, args, L[i].smem, c->stream)
+                                        : cudaLaunchKernel(L[i].fn, grid, L[i].block, args, L[i].smem, c->stream);
         if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
     }
     return B200C_OK;
@@ -751,7 +819,7 @@ int graph_key(const B200Carver *c)
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4) |
-           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0);
+           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0) | (c->mates.empty() ? 0 : 1 << 14);
 }
 
 // Points the lane's graph for the current kernel set at this carver's session: the first time the nodes are added and
@@ -762,20 +830,18 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
     LaneGraph &g = c->lane->graphs[graph_key(c)];
     SeamLaunch L[kSeamLaunchMax];
     const int n = seam_launch_list(c, true, L);
-    DevP p = view_dyn(c);
-    int epoch = c->vs_epoch;
+    SeamArgs a = seam_args(c);
     if (g.exec && g.n != n) lane_graph_reset(&g);
     const bool fresh = g.exec == nullptr;
     if (fresh) CU_TRY(cudaGraphCreate(&g.graph, 0));
     cudaError_t e = cudaSuccess;
     for (int i = 0; i < n && e == cudaSuccess; ++i) {
-        void *args[2] = {&p, L[i].second == 2 ? (void *) &c->maps : (void *) &epoch};
         cudaKernelNodeParams kp = {};
         kp.func = const_cast<void *>(L[i].fn);
-        kp.gridDim = L[i].grid;
+        kp.gridDim = batch_grid(c, L[i].grid);
         kp.blockDim = L[i].block;
         kp.sharedMemBytes = (unsigned) L[i].smem;
-        kp.kernelParams = args;
+        kp.kernelParams = a.of(c, L[i]);
         if (fresh) {
             e = cudaGraphAddKernelNode(&g.node[i], g.graph, i ? &g.node[i - 1] : nullptr, i ? 1 : 0, &kp);
             if (e == cudaSuccess && L[i].coop) {
@@ -806,15 +872,14 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
     if (last) {
         SeamLaunch L[kSeamLaunchMax];
         const int nv = vpath_launch_list(c, L);
-        DevP pv = view_dyn(c);
+        SeamArgs a = seam_args(c);
         for (int i = 0; i < nv; ++i) {
             StageScope sc(L[i].stage, s);
-            void *args[1] = {&pv};
-            const cudaError_t e = cudaLaunchKernel(L[i].fn, L[i].grid, L[i].block, args, L[i].smem, s);
+            const cudaError_t e = cudaLaunchKernel(L[i].fn, batch_grid(c, L[i].grid), L[i].block, a.of(c, L[i]), L[i].smem, s);
             if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
         }
         StageScope sc2("carve", s);
-        k_carve<<<c->h, B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch);
+        k_carve<<<dim3(c->h, 1, batch_n(c)), B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch, tab_dyn(c));
         B_TRY(check_launch("k_carve"));
     } else if (lr_switch || !c->use_graph || g_timing) {
         B_TRY(launch_seam_kernels(c, !lr_switch));
@@ -831,15 +896,18 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
         HostScope hs(8);
         CU_TRY(cudaGraphLaunch(exec, s));
     }
-    c->level++;
-    c->w--;
-    c->nrg_uptodate = !last;
+    for_batch(c, [&](B200Carver *m) {
+        m->level++;
+        m->w--;
+        m->nrg_uptodate = !last;
+    });
     if (last) {
         StageScope sc("finish_vsmap", s);
-        k_finish_vsmap<<<(c->h + 255) / 256, 256, 0, s>>>(view_dyn(c));
+        k_finish_vsmap<<<dim3((c->h + 255) / 256, 1, batch_n(c)), 256, 0, s>>>(view_dyn(c), tab_dyn(c));
         B_TRY(check_launch("k_finish_vsmap"));
     } else if (lr_switch) {
-        c->leftright ^= 1;
+        for_batch(c, [](B200Carver *m) { m->leftright ^= 1; });
+        B_TRY(upload_tab(c, true)); // the argument blocks carry the tie rule
         B_TRY(build_mmap(c));
     }
     return B200C_OK;
@@ -854,7 +922,7 @@ int gather_rig(B200Carver *c)
     B_TRY(encode_map(&c->maps.rig, c->rig, false, c->pitch, c->h_start, bd_rows(c->delta_x, true)));
     dim3 grid((c->w + 255) / 256, c->h);
     StageScope sc("gather_rig", c->stream);
-    k_gather_rig<<<grid, 256, 0, c->stream>>>(view(c));
+    k_gather_rig<<<grid, 256, 0, c->stream>>>(view(c), nullptr);
     return check_launch("k_gather_rig");
 }
 
@@ -867,7 +935,8 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
     const int first = c->max_level;
     // session: the per-seam kernels get one argument block and count the seams themselves (DevP::dyn starts at -1)
     drop_seam_graphs(c);
-    c->w_epoch = c->w;
+    for_batch(c, [](B200Carver *m) { m->w_epoch = m->w; });
+    if (!c->mates.empty()) for_batch(c, [](B200Carver *m) { m->use_tail = false; }); // one grid barrier cannot serve many images
     if (c->use_tail && fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX) {
         // the tail kernel needs a grid barrier: every CTA of its grid must be resident at once (cooperative launch)
         B_TRY(raise_smem_limits(c->device));
@@ -882,8 +951,16 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
             c->use_tail = false; // the band kernel keeps its own wide-window loop
         }
     }
-    c->vs_epoch = first + c->max_level - 1;
-    CU_TRY(cudaMemsetAsync(c->dyn_d, 0xff, sizeof(int), c->stream));
+    {
+        cudaError_t e = cudaSuccess;
+        for_batch(c, [&](B200Carver *m) {
+            m->vs_epoch = first + m->max_level - 1;
+            const cudaError_t e1 = cudaMemsetAsync(m->dyn_d, 0xff, sizeof(int), c->stream);
+            if (e == cudaSuccess) e = e1;
+        });
+        CU_TRY(e);
+    }
+    B_TRY(upload_tab(c, true));
     for (int l = first; l < depth; ++l) {
         if (progress && ((l - first) % update_step) == 0) {
             if (progress(user, l - first)) return fail(B200C_CANCEL, "cancelled by progress callback");
@@ -894,8 +971,18 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
         // the staged kernels check their own window invariants on the device; a violation is a hard error
         HostScope hs(9);
         int err = 0;
-        CU_TRY(cudaMemcpyAsync(&err, c->err_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        std::vector<int> errs(batch_n(c), 0);
+        {
+            int i = 0;
+            cudaError_t e = cudaSuccess;
+            for_batch(c, [&](B200Carver *m) {
+                const cudaError_t e1 = cudaMemcpyAsync(&errs[i++], m->err_d, sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+                if (e == cudaSuccess) e = e1;
+            });
+            CU_TRY(e);
+        }
         CU_TRY(carver_sync(c));
+        for (int v : errs) err |= v;
         if (err) {
             char msg[96];
             snprintf(msg, sizeof msg, "seam loop: device invariant violated (code %d)", err);
@@ -903,10 +990,14 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
         }
     }
     if (!do_inflate) return B200C_OK;
-    B_TRY(inflate(c, depth - 1));
-    set_width_one(c, c->w_start);
-    for (B200Carver *a : c->attached) set_width_rec(a, c->w_start);
-    return B200C_OK;
+    int rc = B200C_OK;
+    for_batch(c, [&](B200Carver *m) {
+        if (rc != B200C_OK) return;
+        rc = inflate(m, depth - 1);
+        set_width_one(m, m->w_start);
+        for (B200Carver *a : m->attached) set_width_rec(a, m->w_start);
+    });
+    return rc;
 }
 
 // ---- A.11 flatten / transpose ---------------------------------------------------------------------------------
@@ -1580,6 +1671,69 @@ int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_pro
     B_TRY(build_mmap(c));
     B_TRY(build_vsmap(c, depth, update_step, progress, user, true));
     return B200C_OK;
+}
+
+// A batch of independent images (the reference's own batch use, batch/batch-gimp-lqr.scm:19-66): the
+// same build_maps session for every carver, advanced in lockstep by ONE launch per step on the first carver's queue (image
+// = blockIdx.z, argument blocks in a table in HBM), so the row-serial chains of the images run side by side on the SMs
+// and one host thread drives them all.  The carvers must agree in geometry and knobs (same size, delta_x, level, side
+// switching, no rigidity); anything else is carved one by one.
+int b200c_batch_build_maps(B200Carver **cs, int n, int depth)
+{
+    if (!cs || n < 1) return fail(B200C_ERROR, "batch_build_maps: bad arguments");
+    B200Carver *L = cs[0];
+    bool same = true;
+    for (int i = 0; i < n; ++i) {
+        const B200Carver *m = cs[i];
+        if (!m) return fail(B200C_ERROR, "batch_build_maps: NULL carver");
+        same = same && m->active && !m->root && m->device == L->device && m->w == L->w && m->h == L->h && m->w0 == L->w0 &&
+               m->h0 == L->h0 && m->w_start == L->w_start && m->h_start == L->h_start && m->level == L->level &&
+               m->max_level == L->max_level && m->delta_x == L->delta_x && m->rigidity == 0.f && m->leftright == L->leftright &&
+               m->lr_freq == L->lr_freq && m->generic == L->generic && m->use_trace == L->use_trace &&
+               m->use_graph == L->use_graph && m->bd_maxseg == L->bd_maxseg && m->mates.empty();
+    }
+    if (!same || n == 1 || g_timing) {
+        for (int i = 0; i < n; ++i) B_TRY(b200c_carver_build_maps(cs[i], depth, 1, nullptr, nullptr));
+        return B200C_OK;
+    }
+    if (depth <= L->max_level) return B200C_OK;
+    B_TRY(use_device(L));
+    // every mate's own queue must be idle before its buffers are used from the leader's
+    std::vector<cudaStream_t> own(n);
+    for (int i = 0; i < n; ++i) {
+        CU_TRY(carver_sync(cs[i]));
+        own[i] = cs[i]->stream;
+    }
+    int rc = B200C_OK;
+    const bool tail0 = L->use_tail;
+    L->mates.assign(cs + 1, cs + n);
+    L->tab_n = n;
+    for (int i = 0; i < n; ++i) {
+        cs[i]->stream = L->stream;
+        for (B200Carver *a : cs[i]->attached) a->stream = L->stream;
+    }
+    if (cudaMallocAsync((void **) &L->tab_d, 2 * (size_t) n * sizeof(DevP), L->stream) != cudaSuccess ||
+        cudaMallocAsync((void **) &L->mtab_d, (size_t) n * sizeof(BdMaps), L->stream) != cudaSuccess)
+        rc = fail(B200C_NOMEM, "batch_build_maps: table allocation", cudaGetLastError());
+    if (rc == B200C_OK) {
+        for_batch(L, [](B200Carver *m) { set_width_one(m, m->w_start - m->max_level + 1); });
+        rc = build_emap(L);
+    }
+    if (rc == B200C_OK) rc = build_mmap(L);
+    if (rc == B200C_OK) rc = build_vsmap(L, depth, 1, nullptr, nullptr, true);
+    const cudaError_t es = carver_sync(L);
+    if (es != cudaSuccess && rc == B200C_OK) rc = fail(B200C_ERROR, "batch_build_maps: sync", es);
+    if (L->tab_d) cudaFreeAsync(L->tab_d, L->stream);
+    if (L->mtab_d) cudaFreeAsync(L->mtab_d, L->stream);
+    L->tab_d = nullptr, L->mtab_d = nullptr, L->tab_n = 0;
+    for (int i = 0; i < n; ++i) {
+        cs[i]->stream = own[i];
+        for (B200Carver *a : cs[i]->attached) a->stream = own[i];
+        cs[i]->use_tail = tail0;
+    }
+    L->mates.clear();
+    drop_seam_graphs(L);
+    return rc;
 }
 
 int b200c_carver_set_width(B200Carver *c, int w1)

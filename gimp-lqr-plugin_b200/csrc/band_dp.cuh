@@ -53,7 +53,7 @@ constexpr int bd_unroll = BD_UNROLL;
 #define BD_NRING 8                // descriptor / mbarrier ring
 #define BD_HMAX 4608              // rows whose energy bands fit the shared-memory table
 #define BD_HANDW (BD_NCW * 128)
-#define BD_RING_BYTES 185856      // 11 slots of 16 rows, 21 of 8 rows, 14 of 8 rows with the rigidity-mask box
+#define BD_RING_BYTES 170496      // 9 slots of 16 rows, 17 of 8 rows, 12 of 8 rows with the rigidity-mask box
 
 // rows per chunk: a longer chunk amortises the chunk boundary, but its stale halo (rows * delta_x) eats the segment
 __host__ __device__ constexpr int bd_rows(int delta_x, bool rig) { return (delta_x <= 1 && !rig) ? 16 : 8; }
@@ -61,10 +61,11 @@ __host__ __device__ constexpr int bd_rows(int delta_x, bool rig) { return (delta
 template <int D, bool RIG>
 struct BdSlot {
     static constexpr int K = bd_rows(D, RIG);
-    static constexpr int box_m = (K + 1) * BD_BW * 4, box_e = K * BD_BW * 4;
+    static constexpr int box_m = (K + 1) * BD_BW * 4, box_e = K * BD_BW * 4, box_p = K * BD_BW;
     static constexpr int off_e = box_m;
     static constexpr int off_g = box_m + box_e;
-    static constexpr int bytes = off_g + (RIG ? box_e : 0);
+    static constexpr int off_p = box_m + box_e + (RIG ? box_e : 0); // old parent offsets: read by the slow path only
+    static constexpr int bytes = off_p + box_p;
     static constexpr int nslot = BD_RING_BYTES / bytes;
     static constexpr int HK = (K * D + 3) & ~3; // columns a segment edge goes stale over one chunk
     static constexpr int S = 128 - 2 * HK;      // stride of the segments = width of an interior
@@ -80,7 +81,7 @@ struct BdDesc {
 static constexpr size_t bd_smem_bytes()
 {
     return (size_t) BD_RING_BYTES + (size_t) BD_HMAX * 4 + 2 * BD_HANDW * 4 + BD_NRING * sizeof(BdDesc) + 256 + 64 + 64 +
-           64 * 4 + 128;
+           64 * 4 + BD_NCW * 4 * 128 * 4 + 128;
 }
 
 __device__ __forceinline__ unsigned bd_saddr(const void *p) { return (unsigned) __cvta_generic_to_shared(p); }
@@ -169,6 +170,13 @@ __device__ __forceinline__ void bd_parents(const float (&prev)[4], float leftflo
 
 #define BD_NEAR_MAX (2u * 0x3727C5ACu - 2u)
 
+// four cells to the m-map in HBM (an explicit global-space store: the pointer comes out of an argument block that may
+// itself live in HBM, which the compiler would otherwise treat as a generic address)
+__device__ __forceinline__ void bd_st_global(float *dst, const float (&v)[4])
+{
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
+
 // one row, the fast way: out = en + min(parents); returns the lane's near key (<= BD_NEAR_MAX: a cell is "near").
 // near <=> 0 < |d| <= tol <=> 2 <= 2*bits(d) (sign shifted out) <= 2*bits(tol) <=> 2*bits(d) - 2 <= 2*bits(tol) - 2 as
 // unsigned; the minimum over the four cells decides for the lane.
@@ -198,9 +206,11 @@ __device__ __forceinline__ unsigned bd_eval(const float (&prev)[4], const float4
 // pending one) is settled with liblqr's full rule from its parents `mq` -- a near cell keeps its old value when its
 // parent is unchanged -- stored, and row q+1 is evaluated again from the settled values.
 struct BdSlow {
-    float mq[4], mp[4], nv[4];     // in: parents of the pending row; out: the pending row, the row after it
+    float mp[4], nv[4];            // out: the pending row settled, the row after it redone
+    const float *par;              // in: the pending row's parents (this lane's four cells, in the warp's value ring)
+    float *ring2, *ring3;          // out: where the two rows go in the ring (the fast loop re-enters after them)
     const float *e, *o, *g;         // operands of the pending row in the tile (the next row's are BD_BW floats further)
-    const int8_t *pold;             // old parent offsets of the pending row (HBM)
+    const unsigned char *pold;      // old parent offsets of the pending row (in the tile)
     float *dst;                     // where the pending row is stored, or NULL
     float leftfloor;
     const float *rigmap;
@@ -209,17 +219,18 @@ struct BdSlow {
 };
 
 template <int D, bool RIG, bool LR>
-__device__ __noinline__ void bd_slow_row(BdSlow &c)
+__device__ __forceinline__ void bd_slow_row(BdSlow &c)
 {
     const float inf = __int_as_float(0x7f800000);
     const float tol = __int_as_float(0x3727C5AC); // (double) |d| < 1e-5  <=>  |d| <= this float
     float rmap[2 * D + 1];
 #pragma unroll
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? c.rigmap[j - D] : 0.f;
-    const unsigned pwo = __ldcg(reinterpret_cast<const unsigned *>(c.pold));
+    const unsigned pwo = *reinterpret_cast<const unsigned *>(c.pold);
     const float4 ce = *reinterpret_cast<const float4 *>(c.e), co = *reinterpret_cast<const float4 *>(c.o);
     const float4 cg = RIG ? *reinterpret_cast<const float4 *>(c.g) : make_float4(1.f, 1.f, 1.f, 1.f);
-    const float prev[4] = {c.mq[0], c.mq[1], c.mq[2], c.mq[3]};
+    const float4 pv = *reinterpret_cast<const float4 *>(c.par);
+    const float prev[4] = {pv.x, pv.y, pv.z, pv.w};
     float v[4 + 2 * D];
     bd_parents<D>(prev, c.leftfloor, v);
     const float en[4] = {ce.x, ce.y, ce.z, ce.w};
@@ -242,6 +253,7 @@ __device__ __noinline__ void bd_slow_row(BdSlow &c)
         c.mp[i] = out[i];
     }
     if (c.dst) *reinterpret_cast<float4 *>(c.dst) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4 *>(c.ring2) = make_float4(out[0], out[1], out[2], out[3]);
     if (c.has_next) {
         float nv[4];
         c.key = bd_eval<D, RIG>(out, *reinterpret_cast<const float4 *>(c.e + BD_BW), *reinterpret_cast<const float4 *>(c.o + BD_BW),
@@ -249,15 +261,18 @@ __device__ __noinline__ void bd_slow_row(BdSlow &c)
                                 c.leftfloor, nv);
 #pragma unroll
         for (int i = 0; i < 4; ++i) c.nv[i] = nv[i];
+        *reinterpret_cast<float4 *>(c.ring3) = make_float4(nv[0], nv[1], nv[2], nv[3]);
     }
 }
 
 // Chunk protocol (one named barrier per chunk, nothing else on the critical path between two chunks): the producer
 // plans chunk k+1 and WAITS for its tiles before it arrives at the barrier that ends chunk k, so a compute warp that
-// leaves that barrier finds descriptor and tiles of chunk k+1 in place -- it never polls an mbarrier itself.
+// leaves that barrier finds descriptor and tiles of chunk k+1 in place -- it never polls an mbarrier itself, it reads
+// the producer's "ready" word (and spins on it only when the window is so wide that chunk k+1 did not fit into the
+// ring beside chunk k and is fetched after the barrier).
 template <int D, bool RIG, bool LR>
-__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand,
-                                           const BdDesc *desc, int *hull, int seg, int lane)
+__device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, float *hand, float *vring,
+                                           const BdDesc *desc, int *hull, const volatile int *ready, int seg, int lane)
 {
     using SL = BdSlot<D, RIG>;
     constexpr int HK = SL::HK, S = SL::S;
@@ -277,6 +292,8 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     for (int k = 0;; ++k) {
         long long tp0 = 0;
         if (BD_PROF && p.dbg) tp0 = clock64();
+        while (*ready < k) {} // normally true at once: see the producer
+        __threadfence_block();
         const BdDesc d = desc[k % BD_NRING];
         if (d.rows == 0) break;
         int *hull_k = hull + (k & 1) * (2 * BD_NCW);
@@ -311,14 +328,12 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             }
             op += BD_BW; // row 0 of the chunk
             const float4 po = ld4(op + (size_t) (rows - 1) * BD_BW); // old values of the last row
-            float *gm = p.m + ((size_t) d.y0 * p.pitch + x0);                          // this lane's cells, row by row
-            const int8_t *gpd = p.pdx + ((size_t) d.y0 * p.pitch + min(x0, p.pitch - 4)); // old parents (slow path only)
+            const unsigned char *pp = sb + SL::off_p + cc;                            // pdx rows 0 .. K-1 (slow path only)
             int r = 0;
             if (d.y0 == 0) { // row 0 of the image: m = en (A.8; true of every cell of the row, evaluated or not)
                 const float4 e4 = ld4(ep);
                 mp[0] = e4.x, mp[1] = e4.y, mp[2] = e4.z, mp[3] = e4.w;
-                if (st) *reinterpret_cast<float4 *>(gm) = e4;
-                gm += p.pitch;
+                if (st) *reinterpret_cast<float4 *>(p.m + ((size_t) d.y0 * p.pitch + x0)) = e4;
                 r = 1;
             }
             long long tr0 = 0;
@@ -330,46 +345,86 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             // "did row r-1 have a near cell?" is still open, so the vote + branch that answers it is off the chain
             // (loop-carried dependency: shuffle -> 3-input min -> add).  If it did (a few per cent of the rows), the
             // out-of-line slow path settles row r-1 with the full rule -- its operands are still in the tile, its
-            // parents (row r-2) in registers, its old parent offsets are read from HBM there and only there -- and
+            // parents (row r-2) in the warp's value ring, its old parent offsets in the tile as well -- and
             // redoes row r.
-            float mq[4] = {mp[0], mp[1], mp[2], mp[3]}; // row r-2, final
-            bool pend = false;                          // row r-1 has a near cell in this lane
-            auto slow = [&](int q, float (&nv)[4], unsigned &key, bool has_next) {
+            // The values of the last rows live in a per-warp ring in shared memory (slot = row index relative to the
+            // loop entry, mod 4; slots 3 and 2 hold the two rows before the entry), so that leaving the fast loop for
+            // the slow path needs no register state beyond the row counter: the unrolled fast rows stay free of moves.
+            float *vr = vring + 4 * lane; // [4][128] per warp
+            bool pend = false;            // row r-1 has a near cell in this lane
+            unsigned go = (unsigned) (d.y0 + r) * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
+            int r0 = r;                   // entry row of the fast loop
+            *reinterpret_cast<float4 *>(vr + 3 * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]);
+            unsigned key = 0xffffffffu;
+            auto slow = [&](int q, bool has_next) { // settles row q, redoes row q+1 (-> mp), re-bases the ring after them
                 BdSlow c;
-#pragma unroll
-                for (int i = 0; i < 4; ++i) c.mq[i] = mq[i];
+                c.par = vr + ((q - 1 - r0) & 3) * 128;
+                c.ring2 = vr + 2 * 128, c.ring3 = vr + 3 * 128;
                 c.e = ep + q * BD_BW, c.o = op + q * BD_BW, c.g = gq + q * BD_BW;
-                c.pold = gpd + (size_t) q * p.pitch;
-                c.dst = st ? gm - p.pitch : nullptr;
+                c.pold = pp + q * BD_BW;
+                c.dst = st ? p.m + (go - p.pitch) : nullptr;
                 c.leftfloor = leftfloor;
                 c.rigmap = p.rigmap;
                 c.has_next = has_next;
                 bd_slow_row<D, RIG, LR>(c);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mp[i] = c.mp[i], nv[i] = c.nv[i];
+                for (int i = 0; i < 4; ++i) mp[i] = has_next ? c.nv[i] : c.mp[i];
                 key = c.key;
                 ++n_slow;
             };
-#pragma unroll bd_unroll
-            for (; r < rows; ++r) {
+            // one fast row: returns true when the row before it turns out to be pending (nothing was stored).  The
+            // operands of the row (ce / co / cg) were fetched while the previous row was computed; the next row's are
+            // fetched first thing here (past the last row of the chunk that reads the neighbouring box of the ring and
+            // is never used), so the chain never waits for shared memory.
+            float4 ce = ld4(ep + r * BD_BW), co = ld4(op + r * BD_BW), cg = RIG ? ld4(gq + r * BD_BW) : one4;
+            float *gm = p.m + go; // this lane's cells of the row being computed
+            auto fast_row = [&](const float *e_next, const float *o_next, const float *g_next, int slot) -> bool {
+                const float4 ne = ld4(e_next), no = ld4(o_next), ng = RIG ? ld4(g_next) : one4;
                 float nv[4];
-                unsigned key = bd_eval<D, RIG>(mp, ld4(ep + r * BD_BW), ld4(op + r * BD_BW), RIG ? ld4(gq + r * BD_BW) : one4, rmap,
-                                               leftfloor, nv);
+                key = bd_eval<D, RIG>(mp, ce, co, cg, rmap, leftfloor, nv);
 #ifdef BD_DEBUG_ALWAYS_SLOW
-                pend = r > (d.y0 == 0 ? 1 : 0);
+                pend = e_next > ep + (r0 + 1) * BD_BW;
 #endif
-                if (__any_sync(full, pend)) slow(r - 1, nv, key, true);
-                if (st) *reinterpret_cast<float4 *>(gm) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+#ifdef BD_EXP_NO_SLOW
+                pend = false; // timing experiment only: never leave the fast loop (results are wrong)
+#endif
+                if (__any_sync(full, pend)) return true;
+#ifndef BD_EXP_NO_STORE
+                if (st) bd_st_global(gm, nv);
+#endif
+#ifndef BD_EXP_NO_VRING
+                *reinterpret_cast<float4 *>(vr + slot * 128) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+#endif
                 gm += p.pitch;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) mq[i] = mp[i], mp[i] = nv[i];
+                for (int i = 0; i < 4; ++i) mp[i] = nv[i];
+                ce = ne, co = no, cg = ng;
                 pend = key <= BD_NEAR_MAX;
+                return false;
+            };
+            for (;;) {
+                bool hit = false;
+                for (; r + 4 <= rows; r += 4) { // (r - r0) is a multiple of 4 here: the slots are compile-time constants
+                    const float *e0 = ep + (r + 1) * BD_BW, *o0 = op + (r + 1) * BD_BW, *g0 = gq + (r + 1) * BD_BW;
+                    if (fast_row(e0, o0, g0, 0)) { hit = true; break; }
+                    if (fast_row(e0 + BD_BW, o0 + BD_BW, g0 + BD_BW, 1)) { r += 1; hit = true; break; }
+                    if (fast_row(e0 + 2 * BD_BW, o0 + 2 * BD_BW, g0 + 2 * BD_BW, 2)) { r += 2; hit = true; break; }
+                    if (fast_row(e0 + 3 * BD_BW, o0 + 3 * BD_BW, g0 + 3 * BD_BW, 3)) { r += 3; hit = true; break; }
+                }
+                if (!hit)
+                    for (; r < rows; ++r)
+                        if (fast_row(ep + (r + 1) * BD_BW, op + (r + 1) * BD_BW, gq + (r + 1) * BD_BW, (r - r0) & 3)) { hit = true; break; }
+                if (!hit) break;
+                go = (unsigned) (d.y0 + r) * (unsigned) p.pitch + (unsigned) x0;
+                slow(r - 1, true); // row r-1 settled, row r redone from it: both are final now
+                if (st) bd_st_global(gm, mp);
+                gm += p.pitch;
+                pend = key <= BD_NEAR_MAX;
+                r0 = ++r;
+                ce = ld4(ep + r * BD_BW), co = ld4(op + r * BD_BW), cg = RIG ? ld4(gq + r * BD_BW) : one4;
             }
-            if (__any_sync(full, pend)) { // the last row of the chunk is still open
-                float nv[4];
-                unsigned key;
-                slow(rows - 1, nv, key, false);
-            }
+            go = (unsigned) (d.y0 + rows) * (unsigned) p.pitch + (unsigned) x0;
+            if (__any_sync(full, pend)) slow(rows - 1, false); // the last row of the chunk is still open
             long long te0 = 0;
             if (BD_PROF && p.dbg) {
                 te0 = clock64();
@@ -418,7 +473,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 
 // ------------------------------------------------------------------------------------------- producer warp
 struct BdMaps {
-    CUtensorMap m, en, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
+    CUtensorMap m, en, pdx, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
 };
 
 template <int D, bool RIG>
@@ -470,9 +525,8 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             nb = (need + BD_BW - 1) / BD_BW;
             lw = nb * BD_BW;
             ropen = llo + min(lw, (nseg - 1) * S + 128) >= wlim; // fetched AND covered by the last segment
-            // too wide for the tiled path (a chunk may take at most half of the ring, so that the next chunk always fits
-            // beside the one in use): the tail kernel / the exact generic loop takes over at row ya
-            if (nseg > min(BD_NCW, p.bd_maxseg) || 2 * nb > SL::nslot) end_y = ya;
+            // too wide for the tiled path: the tail kernel / the exact generic loop takes over at row ya
+            if (nseg > min(BD_NCW, p.bd_maxseg) || nb > SL::nslot) end_y = ya;
         }
         if (end_y < 0 && nb > slots_free) return false;
         if (end_y >= 0) {
@@ -508,6 +562,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
                 bd_tma_load_2d(sb, &tm.m, cx, ya - 1, mb);
                 bd_tma_load_2d(sb + SL::off_e, &tm.en, cx, ya, mb);
                 if (RIG) bd_tma_load_2d(sb + SL::off_g, &tm.rig, cx, ya, mb);
+                bd_tma_load_2d(sb + SL::off_p, &tm.pdx, cx, ya, mb);
             }
             slot_next += nb;
             if (slot_next >= SL::nslot) slot_next -= SL::nslot;
@@ -520,13 +575,28 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         return true;
     };
 
+    // misc[4] = the last chunk whose descriptor is written and whose tiles have landed ("ready"); the compute warps
+    // read it once after every barrier and only wait on it when a window is so wide that the next chunk did not fit
+    // into the ring beside the current one
+    auto publish_ready = [&](int kk) {
+        if (!bd_mbar_wait(&mbar[kk % BD_NRING], (unsigned) ((kk / BD_NRING) & 1))) atomicOr(p.err, 4);
+        __threadfence_block();
+        if (lane == 0) misc[4] = kk;
+        __syncwarp();
+    };
+    int ready = -1;
     // chunk 0: planned, landed, then the start barrier
     while (!ended && kp <= BD_LA)
         if (!plan_issue()) break;
-    if (!bd_mbar_wait(&mbar[0], 0u)) atomicOr(p.err, 4);
+    publish_ready(0), ready = 0;
     bd_bar_chunk();
     long long t_tiles = 0;
     for (int k = 0;; ++k) {
+        // a chunk that did not fit before the last barrier is planned now that its predecessor's slots are free: the
+        // compute warps are waiting for it
+        while (!ended && kp <= k + BD_LA)
+            if (!plan_issue()) break;
+        if (ready < k) publish_ready(k), ready = k;
         const BdDesc *dk = desc + (k % BD_NRING);
         const int rows_k = dk->rows, y0_k = dk->y0, nb_k = dk->nb;
         if (rows_k == 0) {
@@ -537,14 +607,10 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             }
             break;
         }
-        // chunk k+1 must be planned (there is always room for it: a chunk takes at most half of the ring) and up to
-        // BD_LA more while the ring has room; then its tiles must have landed before anybody leaves the barrier
-        while (!ended && kp <= k + BD_LA)
-            if (!plan_issue()) break;
-        if (kp < k + 2 && lane == 0) atomicOr(p.err, 4); // cannot happen: see the ring-space rule in plan_issue
+        // if chunk k+1 is planned, its tiles must have landed before anybody leaves the barrier that ends chunk k
         {
             const long long tw0 = (BD_PROF && p.dbg) ? clock64() : 0;
-            if (kp >= k + 2 && !bd_mbar_wait(&mbar[(k + 1) % BD_NRING], (unsigned) (((k + 1) / BD_NRING) & 1))) atomicOr(p.err, 4);
+            if (kp >= k + 2) publish_ready(k + 1), ready = k + 1;
             if (BD_PROF && p.dbg) t_tiles += clock64() - tw0;
         }
         bd_bar_chunk(); // end of chunk k: its slots are free, the hull of its last row is known
@@ -570,8 +636,9 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
 // cell of its band (A.8); for a kept cell the arg-min equals the stored parent, so writing the arg-min everywhere
 // in the (larger) evaluated range is the same map.
 template <int D, bool RIG, bool LR>
-__global__ void __launch_bounds__(256) k_fix_parents(const DevP pin)
+__global__ void __launch_bounds__(256) k_fix_parents(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     if ((int) blockIdx.x >= *p.fixn) return;
     const int4 f = p.fix[blockIdx.x];
@@ -708,8 +775,11 @@ __device__ void bd_rows_wide(const DevP &p, int y_from, int lo, int hi, float *p
 }
 
 template <int D, bool RIG, bool LR>
-__global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const __grid_constant__ BdMaps tm)
+__global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin0, const __grid_constant__ BdMaps tm0, const DevP *tab,
+                                                           const BdMaps *mtab)
 {
+    const DevP pin = pick_image(pin0, tab);
+    const BdMaps &tm = mtab ? mtab[blockIdx.z] : tm0; // tensor maps of this image: kernel parameter, or table in HBM
     const DevP p = seam_view(pin, 1);
     extern __shared__ __align__(128) unsigned char bd_smem[];
     unsigned char *ring = bd_smem;
@@ -720,6 +790,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const
     unsigned long long *mbar = reinterpret_cast<unsigned long long *>(hull + 64); // [BD_NRING]
     volatile int *misc = reinterpret_cast<volatile int *>(mbar + BD_NRING);
     int *s_red = const_cast<int *>(misc) + 16;
+    float *vals = reinterpret_cast<float *>(s_red + 64); // [BD_NCW][4][128]: each compute warp's last rows
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int y = tid; y < p.h; y += BD_THREADS) nrg[y] = p.nrg_pack[y];
@@ -727,13 +798,14 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin, const
         for (int i = 0; i < BD_NRING; ++i) bd_mbar_init(&mbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         misc[0] = p.h;
+        misc[4] = -1;
     }
     __syncthreads();
 
     if (warp == 0) {
         bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane);
     } else {
-        bd_compute<D, RIG, LR>(p, ring, hand, desc, hull, warp - 1, lane);
+        bd_compute<D, RIG, LR>(p, ring, hand, vals + (size_t) (warp - 1) * 4 * 128, desc, hull, misc + 4, warp - 1, lane);
     }
     __syncthreads();
     const int y_from = misc[0];

@@ -37,8 +37,9 @@ __device__ __forceinline__ void bt_cp_async(void *dst_smem, const void *src, int
 
 // p.tail = {first row left, ...} written by k_band_dp of the same seam; p.tail[0] >= h: nothing to do
 template <int D, bool RIG, bool LR>
-__global__ void __launch_bounds__(BT_THREADS) k_band_tail(const DevP pin)
+__global__ void __launch_bounds__(BT_THREADS) k_band_tail(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     const int y_from = *reinterpret_cast<volatile int *>(p.tail);
     if (y_from >= p.h) return; // the same for every thread of the grid

@@ -67,6 +67,10 @@ struct DevP {
 // the host replay them as one CUDA graph): p.w is the width before the session's first seam, and the seam counter
 // *p.dyn -- advanced by the backtrack kernel, the first of every iteration -- tells how many seams have gone since.
 // post = 0: the width before this iteration's carve (backtrack); post = 1: after it (carve, energy band, DP).
+// Every kernel of the seam search takes its carver's argument block by value AND an optional table of blocks in HBM: a
+// batch session (b200c_batch_build_maps) advances many images with ONE launch per step, image = blockIdx.z.
+__device__ __forceinline__ DevP pick_image(const DevP &p0, const DevP *tab) { return tab ? tab[blockIdx.z] : p0; }
+
 __device__ __forceinline__ DevP seam_view(DevP p, int post, int *seam = nullptr)
 {
     if (p.dyn) {
@@ -182,8 +186,9 @@ __global__ void k_init_raw(int *raw, int w, int h)
 }
 
 // compact copy of the rigidity mask in current coordinates (start of a build_maps session)
-__global__ void __launch_bounds__(256) k_gather_rig(DevP p)
+__global__ void __launch_bounds__(256) k_gather_rig(const DevP p0, const DevP *tab)
 {
+    const DevP p = pick_image(p0, tab);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= p.w || y >= p.h) return;
@@ -191,8 +196,9 @@ __global__ void __launch_bounds__(256) k_gather_rig(DevP p)
 }
 
 // K1 -- A.3 full energy map (lqr_carver_build_emap): one thread per visible pixel.
-__global__ void __launch_bounds__(256) k_energy_full(DevP p)
+__global__ void __launch_bounds__(256) k_energy_full(const DevP p0, const DevP *tab)
 {
+    const DevP p = pick_image(p0, tab);
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= p.pitch || y >= p.h) return;
@@ -204,8 +210,9 @@ __global__ void __launch_bounds__(256) k_energy_full(DevP p)
 // K1b -- A.8 energy band after a carve (lqr_carver_update_emap): one warp per row derives the row's
 // [nrg_xmin, nrg_xmax] from the seam positions of rows y-radius..y+radius and recomputes that band.
 // p.w is the width AFTER the carve; vpath_x is in pre-carve coordinates.
-__global__ void __launch_bounds__(256) k_energy_band(DevP pin)
+__global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     const int lane = threadIdx.x & 31;
     const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -231,8 +238,9 @@ __global__ void __launch_bounds__(256) k_energy_band(DevP pin)
 // K2 (generic) -- A.5 full m-map DP (lqr_carver_build_mmap): one CTA walks the rows, the row is spread
 // over the threads, a block barrier separates dependent rows.  Correct for any width / delta_x; the
 // cluster kernel of mmap_full_cluster.cuh is the fast path.
-__global__ void __launch_bounds__(1024) k_mmap_full(DevP p)
+__global__ void __launch_bounds__(1024) k_mmap_full(const DevP p0, const DevP *tab)
 {
+    const DevP p = pick_image(p0, tab);
     for (int x = threadIdx.x; x < p.pitch; x += blockDim.x) p.m[x] = p.en[x]; // incl. the +inf sentinels
     __syncthreads();
     for (int y = 1; y < p.h; ++y) {
@@ -298,8 +306,9 @@ __device__ void update_rows_generic(const DevP &p, int y_from, int lo, int hi, i
     if (tid == 0 && p.cells) atomicAdd(p.cells, cells);
 }
 
-__global__ void __launch_bounds__(512) k_mmap_update(DevP pin)
+__global__ void __launch_bounds__(512) k_mmap_update(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     __shared__ int s_red[64];
     update_rows_generic(p, 0, INT_MAX, INT_MIN, s_red);
@@ -352,8 +361,9 @@ __device__ __forceinline__ int last_row_argmin(const DevP &p, float *s_v, int *s
     return bx < 0 ? 0 : bx;
 }
 
-__global__ void __launch_bounds__(1024) k_vpath(DevP pin)
+__global__ void __launch_bounds__(1024) k_vpath(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     __shared__ float s_v[32];
     __shared__ int s_x[32];
     if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam
@@ -382,8 +392,9 @@ __global__ void __launch_bounds__(1024) k_vpath(DevP pin)
 // slot another thread already overwrote.
 #define B200C_CARVE_THREADS 256
 #define B200C_CARVE_ITEMS 4
-__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP pin, int vs_value)
+__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, int vs_value, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     int seam;
     const DevP p = seam_view(pin, 1, &seam);
     vs_value += seam; // the level this seam's pixels get in the visibility map
@@ -438,8 +449,9 @@ __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(DevP pin, int vs_
 }
 
 // A.7 finish_vsmap: the image is one pixel wide; the survivors get the largest level.
-__global__ void k_finish_vsmap(DevP pin)
+__global__ void k_finish_vsmap(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     const int y = blockIdx.x * blockDim.x + threadIdx.x;
     if (y < p.h) p.vs[p.raw[(size_t) y * p.raw_stride]] = p.w0;

@@ -31,6 +31,7 @@ typedef struct {
     int (*bias_add_rgb_area)(B200Carver *, const unsigned char *, int, int, int, int, int, int);
     int (*rigmask_add_rgb_area)(B200Carver *, const unsigned char *, int, int, int, int, int);
     int (*build_maps)(B200Carver *, int, int, b200c_progress_fn, void *);
+    int (*batch_build_maps)(B200Carver **, int, int);
     int (*set_width)(B200Carver *, int);
     int (*flatten)(B200Carver *);
     int (*transpose)(B200Carver *);
@@ -87,6 +88,7 @@ static int engine_load_once(void)
     BIND(bias_add_rgb_area, "b200c_carver_bias_add_rgb_area");
     BIND(rigmask_add_rgb_area, "b200c_carver_rigmask_add_rgb_area");
     BIND(build_maps, "b200c_carver_build_maps");
+    BIND(batch_build_maps, "b200c_batch_build_maps");
     BIND(set_width, "b200c_carver_set_width");
     BIND(flatten, "b200c_carver_flatten");
     BIND(transpose, "b200c_carver_transpose");
@@ -523,6 +525,100 @@ LqrRetVal lqr_carver_resize(LqrCarver *r, gint w1, gint h1)
         if (ret == LQR_OK) ret = resize_direction(r, w1, TRUE);
     }
     if (ret != LQR_OK) fprintf(stderr, "liblqr-1 (b200): resize failed: %s\n", g_eng.last_error());
+    return ret;
+}
+
+/* ------------------------------------------------------------------ batch of independent images
+ * The plug-in's batch use (batch/batch-gimp-lqr.scm:19-66: one image per call) as ONE call: the resize driver above
+ * for n carvers in lockstep.  Carvers that agree in geometry and knobs share every launch of the engine (one host
+ * thread, the images' row-serial chains side by side on the SMs); results are those of n separate lqr_carver_resize
+ * calls.  Carvers that do not agree are resized one after the other. */
+static gboolean batch_compatible(LqrCarver **rs, gint n)
+{
+    gint i;
+    for (i = 0; i < n; i++) {
+        LqrCarver *a = rs[0], *b = rs[i];
+        if (!b || b->root) return FALSE;
+        if (EG(a, B200C_W) != EG(b, B200C_W) || EG(a, B200C_H) != EG(b, B200C_H) ||
+            EG(a, B200C_W_START) != EG(b, B200C_W_START) || EG(a, B200C_H_START) != EG(b, B200C_H_START) ||
+            EG(a, B200C_W0) != EG(b, B200C_W0) || EG(a, B200C_H0) != EG(b, B200C_H0) ||
+            EG(a, B200C_TRANSPOSED) != EG(b, B200C_TRANSPOSED) || EG(a, B200C_LEVEL) != EG(b, B200C_LEVEL) ||
+            EG(a, B200C_MAX_LEVEL) != EG(b, B200C_MAX_LEVEL) || a->enl_step != b->enl_step ||
+            a->resize_order != b->resize_order)
+            return FALSE;
+    }
+    return TRUE;
+}
+
+static LqrRetVal resize_direction_batch(LqrCarver **rs, gint n, gint target, gboolean along_w, B200Carver **engs)
+{
+    LqrCarver *r = rs[0];
+    gboolean need_flip = along_w ? EG(r, B200C_TRANSPOSED) : !EG(r, B200C_TRANSPOSED);
+    gint ref = need_flip ? EG(r, B200C_H_START) : EG(r, B200C_W_START);
+    gint cur = need_flip ? EG(r, B200C_H) : EG(r, B200C_W);
+    gint delta = target - ref, gamma = target - cur, delta_max = step_limit(r->enl_step, ref), i;
+    const gint total = gamma > 0 ? gamma : -gamma;
+
+    if (delta < 0) {
+        delta = -delta;
+        delta_max = delta;
+    }
+    for (i = 0; i < n && total; i++) {
+        LqrProgress *p = rs[i]->progress;
+        if (p && p->init) p->init(along_w ? p->init_width_message : p->init_height_message);
+    }
+    while (gamma) {
+        gint delta0 = delta < delta_max ? delta : delta_max, new_w, w_start;
+        delta -= delta0;
+        if (along_w ? EG(r, B200C_TRANSPOSED) : !EG(r, B200C_TRANSPOSED))
+            for (i = 0; i < n; i++) LQR_CATCH((LqrRetVal) g_eng.transpose(rs[i]->eng));
+        w_start = EG(r, B200C_W_START);
+        new_w = target < w_start + delta_max ? target : w_start + delta_max;
+        gamma = target - new_w;
+        LQR_CATCH((LqrRetVal) g_eng.batch_build_maps(engs, n, delta0 + 1));
+        for (i = 0; i < n; i++) {
+            LQR_CATCH((LqrRetVal) g_eng.set_width(rs[i]->eng, new_w));
+            if (rs[i]->dump_vmaps) LQR_CATCH(vmap_internal_dump(rs[i]));
+        }
+        if (new_w < target) {
+            for (i = 0; i < n; i++) LQR_CATCH((LqrRetVal) g_eng.flatten(rs[i]->eng));
+            delta_max = step_limit(r->enl_step, EG(r, B200C_W_START));
+        }
+    }
+    for (i = 0; i < n && total; i++) {
+        LqrProgress *p = rs[i]->progress;
+        if (p && p->end) p->end(along_w ? p->end_width_message : p->end_height_message);
+    }
+    return LQR_OK;
+}
+
+LqrRetVal lqr_b200_batch_resize(LqrCarver **rs, gint n, gint w1, gint h1)
+{
+    LqrRetVal ret = LQR_OK;
+    B200Carver **engs;
+    gint i;
+    LQR_CATCH_F(rs != NULL && n >= 1);
+    LQR_CATCH_F((w1 >= 1) && (h1 >= 1));
+    for (i = 0; i < n; i++) LQR_CATCH_F(rs[i] != NULL);
+    if (n == 1 || !batch_compatible(rs, n)) {
+        for (i = 0; i < n && ret == LQR_OK; i++) ret = lqr_carver_resize(rs[i], w1, h1);
+        return ret;
+    }
+    engs = (B200Carver **) malloc(sizeof(B200Carver *) * (size_t) n);
+    LQR_CATCH_MEM(engs);
+    for (i = 0; i < n; i++) {
+        engs[i] = rs[i]->eng;
+        invalidate_lines(rs[i]);
+    }
+    if (rs[0]->resize_order == LQR_RES_ORDER_HOR) {
+        ret = resize_direction_batch(rs, n, w1, TRUE, engs);
+        if (ret == LQR_OK) ret = resize_direction_batch(rs, n, h1, FALSE, engs);
+    } else {
+        ret = resize_direction_batch(rs, n, h1, FALSE, engs);
+        if (ret == LQR_OK) ret = resize_direction_batch(rs, n, w1, TRUE, engs);
+    }
+    free(engs);
+    if (ret != LQR_OK) fprintf(stderr, "liblqr-1 (b200): batch resize failed: %s\n", g_eng.last_error());
     return ret;
 }
 

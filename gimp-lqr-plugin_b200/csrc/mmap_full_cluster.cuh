@@ -28,8 +28,9 @@ __device__ __forceinline__ void mf_cp_async16(void *dst_smem, const void *src)
 
 // rows [y0, y0 + rows) of the full DP for one strip per warp; row y0-1 of m is final in HBM (y0 == 0: no parents)
 template <int D, bool RIG, bool LR>
-__global__ void __launch_bounds__(MF_THREADS) k_mmap_full_strips(const DevP p, int y0, int rows)
+__global__ void __launch_bounds__(MF_THREADS) k_mmap_full_strips(const DevP p0, int y0, int rows, const DevP *tab)
 {
+    const DevP p = pick_image(p0, tab);
     extern __shared__ __align__(16) unsigned char mf_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int R = mf_rows(D), HK = mf_hk(D), S = 128 - 2 * HK;

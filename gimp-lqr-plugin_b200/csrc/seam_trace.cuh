@@ -7,7 +7,8 @@
 //   k_seam_jumps   grid (column chunks, row blocks[, images]): every CTA stages the parent offsets of its R rows x
 //                  (ST_COLS + 2 R delta_x) columns in shared memory and one thread per column walks them:
 //                  J[b][x] = (column a path entering block b at column x leaves it with) - x, one signed byte,
-//                  ST_BAD when the path meets a parent that was carved away.  All SMs, ~1 byte read per cell.
+//                  (0 when the path meets a parent that was carved away: the re-walk below notices).  All SMs, ~1 byte
+//                  read per cell.
 //   k_seam_chase   one CTA per image: arg-min of the last row of m; then the chase, one dependent shared-memory load
 //                  per BLOCK: the jump rows of a GROUP of blocks are fetched around the column the chase holds (a path
 //                  drifts at most R delta_x columns per block, so block k of the group needs 2 k R delta_x + 1 columns:
@@ -23,7 +24,6 @@ namespace b200c {
 
 #define ST_COLS 256
 #define ST_THREADS 256
-#define ST_BAD (-128)
 #define ST_CHASE_THREADS 1024
 #define ST_HMAX 8192
 #define ST_MAXBLK ((ST_HMAX + 27) / 28 + 1)
@@ -48,8 +48,9 @@ __device__ __forceinline__ DevP seam_view_next(DevP p)
     return p;
 }
 
-__global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin)
+__global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view_next(pin);
     extern __shared__ __align__(16) unsigned char st_smem[];
     const int D = max(p.delta_x, 1), R = st_rows(p.delta_x), reach = R * D;
@@ -75,11 +76,13 @@ __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin)
         bad |= d == B200C_PDX_NONE;
         xx = min(max(xx + (d == B200C_PDX_NONE ? 0 : d), 0), tw - 1);
     }
-    p.jump[(size_t) b * p.pitch + x] = bad ? (signed char) ST_BAD : (signed char) (xx + tlo - x);
+    // a path that meets a dead parent gets jump 0: the chase kernel re-walks every block row by row and notices
+    p.jump[(size_t) b * p.pitch + x] = bad ? (signed char) 0 : (signed char) (xx + tlo - x);
 }
 
-__global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP pin)
+__global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP pin0, const DevP *tab)
 {
+    const DevP pin = pick_image(pin0, tab);
     if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam
     __syncthreads();
     const DevP p = seam_view(pin, 0);
@@ -113,26 +116,24 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
                 off += e - a;
             }
             roff[tid] = off;
-            rcol[tid] = max(xg - tid * reach, 0) & ~15;
+            rcol[tid] = off - (max(xg - tid * reach, 0) & ~15); // stage index of column 0 of this row
         }
         __syncthreads();
         for (int k = tid >> 5; k < g; k += ST_CHASE_THREADS / 32) { // a warp per row of the triangle; copies are asynchronous
-            const int a = rcol[k], e = min((xg + k * reach + 16) & ~15, p.pitch), pieces = (e - a) >> 4;
+            const int a = max(xg - k * reach, 0) & ~15, e = min((xg + k * reach + 16) & ~15, p.pitch), pieces = (e - a) >> 4;
             const signed char *src = p.jump + (size_t) (b0 + k) * p.pitch + a;
             for (int i = tid & 31; i < pieces; i += 32) st_cp16(stage + roff[k] + (i << 4), src + (i << 4));
         }
         st_cp_wait();
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) { // the chain: one shared-memory load + one add per block
+            const signed char *S = reinterpret_cast<const signed char *>(stage);
             int x = xg;
-            bool bad = false;
+#pragma unroll 4
             for (int k = 0; k < g; ++k) {
-                const int j = reinterpret_cast<const signed char *>(stage)[roff[k] + x - rcol[k]];
-                bad |= j == ST_BAD;
-                x = min(max(x + (j == ST_BAD ? 0 : j), 0), p.w - 1);
+                x += S[rcol[k] + x];
                 ent[b0 + k + 1] = x;
             }
-            if (bad) s_bad = 1;
         }
         __syncthreads();
     }
@@ -162,7 +163,7 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
                 sx[y] = xx + lo;
                 const int d = t[(ybot - y) * twf + xx];
                 bad |= d == B200C_PDX_NONE;
-                xx = min(max(xx + (d == B200C_PDX_NONE ? 0 : d), 0), twf - 1);
+                xx += d == B200C_PDX_NONE ? 0 : d; // a live parent is at most delta_x columns away: xx stays in the tile
             }
             if (bad || xx + lo != ent[b + 1]) s_bad = 1;
         }

@@ -99,3 +99,34 @@ def render_batch(lib_path: str, layers, vals: PlugInVals, in_flight: int = 16, k
         nw, nh = vals.new_width, vals.new_height
         res["outputs"] = [a.reshape(-1)[: nw * nh * bpp].reshape(nh, nw, bpp).copy() for a in outs]
     return res
+
+
+def render_lockstep(lib_path: str, layers, vals: PlugInVals, group: int = 32, in_flight: int = 2, keep_outputs: bool = False):
+    """The same batch through harness_render_lockstep: groups of `group` images are set up one after the other, resized
+    by ONE lqr_b200_batch_resize call (shared launches on the device, one host thread per group) and written back;
+    `in_flight` groups at a time, so the copies of one group overlap the seams of another."""
+    layers = [np.ascontiguousarray(a, dtype=np.uint8) for a in layers]
+    h, w, bpp = layers[0].shape
+    assert all(a.shape == (h, w, bpp) for a in layers)
+    hv = HarnessVals(w, h, bpp, vals.new_width, vals.new_height, vals.pres_coeff, vals.disc_coeff, vals.rigidity,
+                     vals.delta_x, vals.enl_step, vals.nrg_func, vals.res_order, 0, int(vals.scaleback),
+                     int(vals.no_disc_on_enlarge), 0, 0)
+    lib = _load()
+    lib.harness_render_lockstep.restype = C.c_int
+    lib.harness_render_lockstep.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int,
+                                            C.POINTER(HarnessVals), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    ptrs = (C.c_void_p * len(layers))(*[a.ctypes.data for a in layers])
+    outs, optrs = None, None
+    if keep_outputs:
+        outs = [np.zeros((max(h, vals.new_height), max(w, vals.new_width), bpp), dtype=np.uint8) for _ in layers]
+        optrs = (C.c_void_p * len(layers))(*[a.ctypes.data for a in outs])
+    sums = (C.c_double * 5)()
+    wall = C.c_double()
+    if not lib.harness_render_lockstep(lib_path.encode(), ptrs, optrs, len(layers), group, in_flight, C.byref(hv), sums,
+                                       C.byref(wall)):
+        raise RuntimeError("harness_render_lockstep failed")
+    res = dict(zip(("ms_new", "ms_setup", "ms_resize", "ms_scan", "ms_total"), list(sums)), wall_ms=wall.value)
+    if keep_outputs:
+        nw, nh = vals.new_width, vals.new_height
+        res["outputs"] = [a.reshape(-1)[: nw * nh * bpp].reshape(nh, nw, bpp).copy() for a in outs]
+    return res

@@ -345,3 +345,18 @@ class Carver:
             out.append(lib.lqr_carver_list_current(it))
             it = lib.lqr_carver_list_next(it)
         return out
+
+
+def batch_resize(lib: LqrLib, carvers, w1: int, h1: int):
+    """lqr_b200_batch_resize (product only): the resize driver for a batch of independent carvers in lockstep -- carvers
+    of equal geometry and knobs share every launch of the engine; others are resized one after the other.  Libraries
+    without the entry point (the CPU oracle) get plain lqr_carver_resize calls."""
+    fn = getattr(lib.dll, "lqr_b200_batch_resize", None)
+    if fn is None:
+        for c in carvers:
+            c.resize(w1, h1)
+        return
+    fn.restype = _I
+    fn.argtypes = [C.POINTER(_P), _I, _I, _I]
+    arr = (_P * len(carvers))(*[c.handle for c in carvers])
+    _check(fn(arr, len(carvers), w1, h1), "lqr_b200_batch_resize")

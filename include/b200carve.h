@@ -68,6 +68,10 @@ B200C_API int b200c_carver_rigmask_add_rgb_area(B200Carver *c, const unsigned ch
  * per-seam loop (backtrack, carve, band energy, band DP / side switch) up to `depth`, inflate, width reset.
  * `progress` (may be NULL) is invoked on the calling thread when seam_index % update_step == 0. */
 B200C_API int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user);
+/* The same build_maps session for n independent carvers of equal geometry and knobs (a batch of images, the reference's
+ * batch use: batch/batch-gimp-lqr.scm:19-66), advanced in lockstep: ONE launch per step for all of them (image =
+ * blockIdx.z), one host thread.  Carvers that do not agree are carved one by one.  Returns when all are done. */
+B200C_API int b200c_batch_build_maps(B200Carver **carvers, int n, int depth);
 /* lqr_carver_set_width (A.1), mirrored onto attached carvers */
 B200C_API int b200c_carver_set_width(B200Carver *c, int w1);
 /* lqr_carver_flatten (render.c:325,636; A.11) / transpose (A.11), both recursive on attached carvers */

@@ -368,3 +368,109 @@ int harness_render_batch(const char *liblqr_path, const unsigned char *const *la
     pthread_mutex_destroy(&job.mu);
     return !job.failed;
 }
+
+/* ---- the same batch, LOCKSTEP: the images are taken in groups of `group`; a group's carvers are set up one after the
+ * other (the call sequence above, no masks), resized by ONE call -- lqr_b200_batch_resize, which advances all of them
+ * with shared launches on the device -- and written back one after the other.  `nthreads` groups are in flight, so the
+ * uploads and read-outs of one group overlap the seams of another. */
+typedef LqrRetVal (*BatchResizeFn)(LqrCarver **, gint, gint, gint);
+
+typedef struct {
+    BatchJob job;
+    int group;
+} LockstepJob;
+
+static void *lockstep_worker(void *arg)
+{
+    LockstepJob *lj = (LockstepJob *) arg;
+    BatchJob *job = &lj->job;
+    const HarnessVals *v = job->v;
+    const size_t ow = (size_t) (v->width > v->new_width ? v->width : v->new_width);
+    const size_t oh = (size_t) (v->height > v->new_height ? v->height : v->new_height);
+    Api api_storage, *api = &api_storage;
+    BatchResizeFn batch_resize;
+    unsigned char *scratch = (unsigned char *) malloc(ow * oh * v->bpp);
+    LqrCarver **cs = (LqrCarver **) calloc((size_t) lj->group, sizeof(LqrCarver *));
+    double sums[5] = {0, 0, 0, 0, 0};
+    int failed = scratch == NULL || cs == NULL || !bind_api(api, job->path);
+    batch_resize = failed ? NULL : (BatchResizeFn) dlsym(api->dl, "lqr_b200_batch_resize");
+    while (!failed) {
+        int i0, g, k;
+        double t0, t1, t2, t3;
+        pthread_mutex_lock(&job->mu);
+        i0 = job->next;
+        g = job->n - i0 < lj->group ? job->n - i0 : lj->group;
+        job->next += g > 0 ? g : 0;
+        pthread_mutex_unlock(&job->mu);
+        if (g <= 0) break;
+        t0 = now_ms();
+        for (k = 0; k < g && !failed; k++) {
+            guchar *rgb = rgb_buffer_from_layer(job->layers[i0 + k], v->width, v->height, v->bpp);      /* render.c:220 */
+            cs[k] = rgb ? api->carver_new(rgb, v->width, v->height, v->bpp) : NULL;                      /* render.c:222 */
+            if (!cs[k] || api->carver_init(cs[k], v->delta_x, v->rigidity) != LQR_OK) {                  /* render.c:224 */
+                failed = 1;
+                break;
+            }
+            api->set_energy_function_builtin(cs[k], (LqrEnergyFuncBuiltinType) v->nrg_func);             /* render.c:234 */
+            api->set_resize_order(cs[k], (LqrResizeOrder) v->res_order);                                 /* render.c:235 */
+            api->set_side_switch_frequency(cs[k], 2);                                                    /* render.c:237 */
+            api->set_enl_step(cs[k], v->enl_step / 100);                                                 /* render.c:238 */
+        }
+        t1 = now_ms();
+        if (!failed) {
+            if (batch_resize) {
+                if (batch_resize(cs, g, v->new_width, v->new_height) != LQR_OK) failed = 1;
+            } else {
+                for (k = 0; k < g; k++)
+                    if (api->carver_resize(cs[k], v->new_width, v->new_height) != LQR_OK) failed = 1;   /* render.c:318 */
+            }
+        }
+        t2 = now_ms();
+        for (k = 0; k < g; k++) {
+            if (!cs[k]) continue;
+            if (!failed) {
+                if (api->get_width(cs[k]) != v->new_width || api->get_height(cs[k]) != v->new_height) failed = 1;
+                write_carver_to_layer(api, cs[k], job->outs ? job->outs[i0 + k] : scratch, v->new_width, v->new_height, v->bpp);
+            }
+            api->carver_destroy(cs[k]);                                                                   /* render.c:376 */
+            cs[k] = NULL;
+        }
+        t3 = now_ms();
+        sums[0] += t1 - t0, sums[2] += t2 - t1, sums[3] += t3 - t2, sums[4] += t3 - t0;
+    }
+    free(scratch);
+    free(cs);
+    pthread_mutex_lock(&job->mu);
+    job->failed |= failed;
+    for (int k = 0; k < 5; k++) job->sums[k] += sums[k];
+    pthread_mutex_unlock(&job->mu);
+    return NULL;
+}
+
+int harness_render_lockstep(const char *liblqr_path, const unsigned char *const *layers, unsigned char *const *outs, int n,
+                            int group, int nthreads, const HarnessVals *v, double *sums, double *wall_ms)
+{
+    LockstepJob lj;
+    pthread_t th[64];
+    double t0;
+    int k;
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > 64) nthreads = 64;
+    if (group < 1) group = 1;
+    memset(&lj, 0, sizeof lj);
+    lj.job.path = liblqr_path, lj.job.layers = layers, lj.job.outs = outs, lj.job.v = v, lj.job.n = n;
+    lj.group = group;
+    pthread_mutex_init(&lj.job.mu, NULL);
+    t0 = now_ms();
+    for (k = 0; k < nthreads; k++)
+        if (pthread_create(&th[k], NULL, lockstep_worker, &lj) != 0) {
+            nthreads = k;
+            lj.job.failed = 1;
+            break;
+        }
+    for (k = 0; k < nthreads; k++) pthread_join(th[k], NULL);
+    *wall_ms = now_ms() - t0;
+    for (k = 0; k < 5; k++) sums[k] = lj.job.sums[k];
+    pthread_mutex_destroy(&lj.job.mu);
+    return !lj.job.failed;
+}

@@ -340,3 +340,67 @@ def test_range_extension_without_flatten(product, oracle, kernel_mode):
     first, last = outs[0][0][3], outs[0][-1][3]
     assert np.array_equal((first > 0) & (first <= 10), (last > 0) & (last <= 10))
     assert np.array_equal(outs[0][-1][1], img)  # back at the reference size: the original
+
+
+@pytest.mark.parametrize("w,h,new_w,new_h,n", [(160, 90, 150, 90, 12), (200, 120, 176, 120, 5), (96, 140, 110, 150, 4)])
+def test_batch_resize_lockstep(product, oracle, w, h, new_w, new_h, n):
+    """lqr_b200_batch_resize: n independent images advanced by shared launches (image = blockIdx.z, argument blocks in a
+    table in HBM) give, image by image, what n separate lqr_carver_resize calls give on the oracle -- pixels and seam
+    maps, shrinking, enlarging and along both directions."""
+    imgs = [synth.smooth_noise(w, h, 4, seed=900 + i) for i in range(n)]
+
+    def run(lib, batched):
+        cs = []
+        for img in imgs:
+            c = lib.carver(img)
+            c.init(1, 0.0)
+            c.set_side_switch_frequency(2)
+            c.set_dump_vmaps()
+            cs.append(c)
+        if batched:
+            lqr.batch_resize(lib, cs, new_w, new_h)
+        else:
+            for c in cs:
+                c.resize(new_w, new_h)
+        out = [(c.scan_image().copy(), [v.data.copy() for v in c.flushed_vmaps()]) for c in cs]
+        for c in cs:
+            c.destroy()
+        return out
+
+    want = run(oracle, False)
+    got = run(product, True)
+    for i, ((gi, gv), (wi, wv)) in enumerate(zip(got, want)):
+        assert gi.shape == wi.shape and np.array_equal(gi, wi), f"image {i} differs"
+        assert len(gv) == len(wv) and all(np.array_equal(a, b) for a, b in zip(gv, wv)), f"seam maps of image {i} differ"
+
+
+def test_batch_resize_mixed_falls_back(product, oracle):
+    """Carvers that do not agree in geometry are resized one after the other by the same call."""
+    imgs = [synth.smooth_noise(120 + 8 * i, 80, 4, seed=950 + i) for i in range(3)]
+    outs = []
+    for lib in (product, oracle):
+        cs = [lib.carver(im).init(1, 0.0) for im in imgs]
+        if lib is product:
+            lqr.batch_resize(lib, cs, 100, 80)
+        else:
+            for c in cs:
+                c.resize(100, 80)
+        outs.append([c.scan_image().copy() for c in cs])
+        for c in cs:
+            c.destroy()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_c_lockstep_driver_matches_oracle(pkg, oracle):
+    """tests/harness harness_render_lockstep: groups of images set up, resized by one lqr_b200_batch_resize call and written
+    back from C host threads, two groups in flight (the last group is a partial one)."""
+    import importlib
+    harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+    w, h, n = 192, 108, 20
+    imgs = [synth.smooth_noise(w, h, 4, seed=700 + i) for i in range(22)]
+    vals = V(new_width=w - n, new_height=h)
+    outs = harness.render_lockstep(pkg.SHIM_PATH, imgs, vals, group=8, in_flight=2, keep_outputs=True)["outputs"]
+    for img, got in zip(imgs, outs):
+        want = render.render_noninteractive(oracle, img, vals).image
+        assert np.array_equal(got, want)

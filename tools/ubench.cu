@@ -178,6 +178,75 @@ __global__ void k_row_body_lag(const float *en_g, float *m_g, long long *cyc, in
     m_g[go + 1] = mp[0] + mp[1] + mp[2] + mp[3];
 }
 
+// Software-pipelined variant: the near test of row r-1 is issued in the shadow of row r's shuffles (it only needs row
+// r-1's values and old values), its vote is consumed at the end of row r.  PACKED: additions as add.rn.f32x2 (sm_100).
+template <bool PACKED>
+__global__ void k_row_body_pipe(const float *en_g, float *m_g, long long *cyc, int rows, int pitch)
+{
+    extern __shared__ float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float *es = sm + (size_t) warp * 2 * 16 * 128;
+    float *os = es + 16 * 128;
+    for (int i = lane; i < 16 * 128; i += 32) {
+        es[i] = en_g[(i * 13 + warp) % 4096];
+        os[i] = en_g[(i * 7 + warp) % 4096] * 100.f;
+    }
+    __syncthreads();
+    float mp[4] = {1.f + lane, 2.f, 3.f, 4.f};
+    float4 po = make_float4(0.f, 0.f, 0.f, 0.f); // old values of row r-1
+    const float inf = __int_as_float(0x7f800000);
+    const float leftfloor = lane == 0 ? inf : -inf;
+    unsigned go = warp * 128 + 4 * lane;
+    int redo = 0;
+    long long t0 = clock64();
+    for (int r0 = 0; r0 < rows; r0 += 16) {
+#pragma unroll 4
+        for (int r = 0; r < 16; ++r) {
+            const float l0 = __shfl_up_sync(0xffffffffu, mp[3], 1);
+            const float rr = __shfl_down_sync(0xffffffffu, mp[0], 1);
+            const float4 e4 = *reinterpret_cast<const float4 *>(es + r * 128 + 4 * lane);
+            const float4 o4 = *reinterpret_cast<const float4 *>(os + r * 128 + 4 * lane);
+            // near test of the previous row, in the shadow of the shuffles
+            unsigned u0, u1, u2, u3;
+            if (PACKED) {
+                const float2 d01 = __fadd2_rn(make_float2(mp[0], mp[1]), make_float2(-po.x, -po.y));
+                const float2 d23 = __fadd2_rn(make_float2(mp[2], mp[3]), make_float2(-po.z, -po.w));
+                u0 = __float_as_uint(d01.x) * 2u - 2u, u1 = __float_as_uint(d01.y) * 2u - 2u;
+                u2 = __float_as_uint(d23.x) * 2u - 2u, u3 = __float_as_uint(d23.y) * 2u - 2u;
+            } else {
+                u0 = __float_as_uint(__fsub_rn(po.x, mp[0])) * 2u - 2u, u1 = __float_as_uint(__fsub_rn(po.y, mp[1])) * 2u - 2u;
+                u2 = __float_as_uint(__fsub_rn(po.z, mp[2])) * 2u - 2u, u3 = __float_as_uint(__fsub_rn(po.w, mp[3])) * 2u - 2u;
+            }
+            const bool pend = min(min(u0, u1), min(u2, u3)) <= 2u * 0x3727C5ACu - 2u;
+            const bool any = __any_sync(0xffffffffu, pend);
+            const float l = fmaxf(l0, leftfloor);
+            float nv[4];
+            const float b0 = fminf(fminf(l, mp[0]), mp[1]), b1 = fminf(fminf(mp[0], mp[1]), mp[2]);
+            const float b2 = fminf(fminf(mp[1], mp[2]), mp[3]), b3 = fminf(fminf(mp[2], mp[3]), rr);
+            if (PACKED) {
+                const float2 a01 = __fadd2_rn(make_float2(e4.x, e4.y), make_float2(b0, b1));
+                const float2 a23 = __fadd2_rn(make_float2(e4.z, e4.w), make_float2(b2, b3));
+                nv[0] = a01.x, nv[1] = a01.y, nv[2] = a23.x, nv[3] = a23.y;
+            } else {
+                nv[0] = __fadd_rn(e4.x, b0), nv[1] = __fadd_rn(e4.y, b1), nv[2] = __fadd_rn(e4.z, b2), nv[3] = __fadd_rn(e4.w, b3);
+            }
+            if (any) {
+                ++redo;
+                nv[0] += 1.f;
+            }
+            *reinterpret_cast<float4 *>(m_g + go) = make_float4(nv[0], nv[1], nv[2], nv[3]);
+            go += pitch;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) mp[i] = nv[i];
+            po = o4;
+        }
+    }
+    long long t1 = clock64();
+    if (lane == 0) cyc[warp] = t1 - t0;
+    if (threadIdx.x == 0) cyc[nw] = redo;
+    m_g[go + 1] = mp[0] + mp[1] + mp[2] + mp[3];
+}
+
 // near key on the fma pipe: bits(d) * 2 - 2 as an integer multiply-add (the compiler turns the C expression into an
 // IADD3, which shares the alu pipe with the 3-input minima)
 __device__ __forceinline__ unsigned nearkey(float d)
@@ -341,6 +410,15 @@ int main()
         for (int rep = 0; rep < 2; ++rep) k_row_body_lag<<<1, nw * 32, smem>>>(d_f, d_f + (8 << 20), d_c, rows, pitch);
         CHECK(cudaMemcpy(h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost));
         printf("row body, lagged vote every row, %2d warps: %.1f cycles/row (redo %lld)\n", nw, (double) h_c[0] / rows, h_c[nw]);
+    }
+    for (int nw : {1, 3, 4}) {
+        const size_t smem = (size_t) nw * 2 * 16 * 128 * 4;
+        for (int rep = 0; rep < 2; ++rep) k_row_body_pipe<false><<<1, nw * 32, smem>>>(d_f, d_f + (8 << 20), d_c, rows, pitch);
+        CHECK(cudaMemcpy(h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost));
+        printf("row body, pipelined near test, %2d warps: %.1f cycles/row (redo %lld)\n", nw, (double) h_c[0] / rows, h_c[nw]);
+        for (int rep = 0; rep < 2; ++rep) k_row_body_pipe<true><<<1, nw * 32, smem>>>(d_f, d_f + (8 << 20), d_c, rows, pitch);
+        CHECK(cudaMemcpy(h_c, d_c, sizeof h_c, cudaMemcpyDeviceToHost));
+        printf("row body, pipelined near test, f32x2, %2d warps: %.1f cycles/row (redo %lld)\n", nw, (double) h_c[0] / rows, h_c[nw]);
     }
     run_body2<8, false>("2-row steps, vote/8 ", d_f, d_c, rows, pitch);
     run_body2<8, true>("2-row steps, vote/8, imad key", d_f, d_c, rows, pitch);
