@@ -1692,7 +1692,7 @@ int b200c_batch_build_maps(B200Carver **cs, int n, int depth)
                m->lr_freq == L->lr_freq && m->generic == L->generic && m->use_trace == L->use_trace &&
                m->use_graph == L->use_graph && m->bd_maxseg == L->bd_maxseg && m->mates.empty();
     }
-    if (!same || n == 1 || g_timing) {
+    if (!same || n == 1) {
         for (int i = 0; i < n; ++i) B_TRY(b200c_carver_build_maps(cs[i], depth, 1, nullptr, nullptr));
         return B200C_OK;
     }
