@@ -13,7 +13,11 @@ carver set-up, energy map, m-map DP, 200 x (backtrack, carve, band energy, band 
   N > 1 : one process per GPU (torchrun), every rank carves its own image (weak scaling, no collective on
           the data path); value = all ranks' seams / max-over-ranks time.
   --impl reference : the CPU oracle port of liblqr (liblqr itself is not vendored in the reference tree)
-          on one host core -- liblqr is single-threaded and one image's seams are strictly sequential.
+          on the host cores -- liblqr is single-threaded and one image's seams are strictly sequential, so one core per
+          image: 1 image at N=1, N images on N cores (rank 0 runs them all) at N>1.
+  config4_batch (extra object in the same line): BASELINE.json configs[3], the 256-image batch (1920x1080 RGBA, 100 seams
+          each), image i -> rank i mod N (strong scaling), carved by the LOCKSTEP batch engine (b200c_batch_build_maps /
+          lqr_b200_batch_resize: one launch per step for a whole group of images).  --config 4 makes it the headline.
 """
 from __future__ import annotations
 
@@ -37,6 +41,16 @@ pkg = importlib.import_module("gimp-lqr-plugin_b200")
 W, H, SEAMS, CH = 3840, 2160, 200, 4
 WORKLOAD = f"{W}x{H} RGBA, {SEAMS} vertical seams ({W}->{W - SEAMS}), plug-in defaults, one image per GPU"
 METRIC, UNIT = "seams_per_sec_4k_rgba", "seams/s"
+# the same dict in both arms (the driver compares them key by key)
+CONFIG = {"workload": WORKLOAD, "seams_per_step": SEAMS, "l2": "flushed between timed steps (256 MiB write)",
+          "timing": "b200 arm: CUDA events on the engine's stream per step, max over ranks; reference arm: host clock"}
+B_W, B_H, B_SEAMS, B_IMAGES = 1920, 1080, 100, 256
+B_METRIC = "seams_per_sec_batch256_1080p_rgba"
+B_WORKLOAD = (f"batch {B_IMAGES} x {B_W}x{B_H} RGBA, {B_SEAMS} vertical seams each ({B_W}->{B_W - B_SEAMS}), plug-in defaults, "
+              "image i -> rank i mod N")
+B_CONFIG = {"workload": B_WORKLOAD, "seams_per_image": B_SEAMS, "images": B_IMAGES,
+            "l2": "working set of a shard (GBs) far exceeds the 126 MB L2",
+            "timing": "b200 arm: CUDA events on the engine's stream around the whole shard, max over ranks; reference arm: host clock"}
 
 
 def peaks():
@@ -106,7 +120,7 @@ def bind_engine():
         "b200c_set_device": (I, [I]), "b200c_set_timing": (None, [I]), "b200c_launch_count": (C.c_long, []),
         "b200c_stage_ms": (C.c_double, [C.c_char_p, C.POINTER(C.c_long)]), "b200c_stage_reset": (None, []),
         "b200c_update_cells": (C.c_ulonglong, []), "b200c_last_error": (C.c_char_p, []),
-        "b200c_device_count": (I, []),
+        "b200c_device_count": (I, []), "b200c_batch_build_maps": (I, [C.POINTER(P), I, I]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(eng, name)
@@ -147,16 +161,47 @@ def abi_step(lib_path, img, seams=SEAMS):
     return out, res
 
 
+def _oracle_images(images, seams, w, h):
+    """Carves every image through the oracle's Lqr API on its own host thread (the C calls release the GIL)."""
+    harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+    vals = pkg.render.PlugInVals(new_width=w - seams, new_height=h)
+    if len(images) == 1:
+        return [harness.render(pkg.ORACLE_PATH, images[0], vals)[0]]
+    outs = [None] * len(images)
+
+    def work(i):
+        outs[i] = harness.render(pkg.ORACLE_PATH, images[i], vals)[0]
+
+    ths = [threading.Thread(target=work, args=(i,)) for i in range(len(images))]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return outs
+
+
 def run_reference(args, rank):
+    """The CPU arm: the oracle port of liblqr through the same C call sequence.  One image per core (liblqr is
+    single-threaded and an image's seams are sequential): 1 image at N=1, N images on N host threads at N>1."""
     if rank != 0:
         return
-    img = pkg.synth.smooth_noise(W, H, CH)
-    est_step = 2.5  # s, one full config-2 pass on one core
-    seams = SEAMS
-    if (args.steps + args.warmup) * est_step > 170:
-        seams = max(20, int(SEAMS * 170 / ((args.steps + args.warmup) * est_step)))
+    n = max(1, args.gpus)
+    cores = min(n, os.cpu_count() or 1)
+    if args.config == 4:
+        w, h, seams_full, est = B_W, B_H, B_SEAMS, 0.35
+        per_step = max(cores, min(B_IMAGES, 2 * cores))  # bounded sample: images per step
+    else:
+        w, h, seams_full, est = W, H, SEAMS, 2.5
+        per_step = n
+    seams = seams_full
+    waves = -(-per_step // cores)
+    if (args.steps + args.warmup) * est * waves > 170:
+        seams = max(20, int(seams_full * 170 / ((args.steps + args.warmup) * est * waves)))
+    imgs = [pkg.synth.smooth_noise(w, h, CH, seed=pkg.synth.SEED + i) for i in range(per_step)]
+
     def step():
-        return abi_step(pkg.ORACLE_PATH, img, seams)[0]
+        for i in range(0, per_step, cores):
+            _oracle_images(imgs[i:i + cores], seams, w, h)
 
     for _ in range(args.warmup):
         step()
@@ -164,30 +209,129 @@ def run_reference(args, rank):
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    value = seams * args.steps / dt
-    sample = (f"{args.steps} x ({W}x{H} RGBA, {seams} seams of the {SEAMS}-seam workload) through the Lqr API incl. "
-              "scan_line read-out; C oracle restating liblqr (liblqr itself is not in the reference tree), gcc -O2, "
-              "1 thread: liblqr is single-threaded and one image's seams are sequential")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "seams_per_step": seams},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+    value = per_step * seams * args.steps / dt
+    sample = (f"{args.steps} x ({per_step} image(s) of {w}x{h} RGBA, {seams} seams of the {seams_full}-seam workload each, "
+              f"{cores} at a time on {cores} host thread(s)) through the Lqr API incl. scan_line read-out; C oracle restating "
+              "liblqr (liblqr itself is not in the reference tree), gcc -O2; liblqr is single-threaded and one image's "
+              "seams are sequential, so the CPU arm scales by images only")
+    line = {"impl": "reference", "metric": METRIC if args.config != 4 else B_METRIC, "value": value, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak" if args.config != 4 else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": CONFIG if args.config != 4 else B_CONFIG,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline():
+    """The oracle port on one host core, 3 x the full config-2 workload; returns (record, carved image)."""
     img = pkg.synth.smooth_noise(W, H, CH)
-    times = []
+    times, out = [], None
     for _ in range(3):
         t0 = time.perf_counter()
-        abi_step(pkg.ORACLE_PATH, img)
+        out = abi_step(pkg.ORACLE_PATH, img)[0].copy()
         times.append(time.perf_counter() - t0)
     t = statistics.median(times)
     return {"value": SEAMS / t, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"3 x the full workload ({WORKLOAD}) through the Lqr API, median; C oracle restating liblqr "
-                      "(unverified against real liblqr), gcc -O2, 1 host core (liblqr is single-threaded)"}
+                      "(unverified against real liblqr), gcc -O2, 1 host core (liblqr is single-threaded)"}, out
+
+
+def profile_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from this round's committed ncu capture
+    summary (profiles/r02_kernels.json, written by tools/ncu_summarize.py); None when there is no capture."""
+    try:
+        with open(os.path.join(REPO, "profiles", "r02_kernels.json")) as f:
+            k = json.load(f)["kernels"][kernel]
+        return float(k["dram_bytes_read"]) + float(k["dram_bytes_write"])
+    except Exception:
+        return None
+
+
+def cold_start_s():
+    """Fresh process -> last scan_line of the config-2 workload through the C ABI (a GIMP plug-in is one process per
+    non-interactive invocation): wall seconds, measured in a child process."""
+    code = ("import importlib,sys,time;t0=time.perf_counter();sys.path.insert(0,%r);"
+            "pkg=importlib.import_module('gimp-lqr-plugin_b200');h=importlib.import_module('gimp-lqr-plugin_b200.harness');"
+            "img=pkg.synth.smooth_noise(%d,%d,%d);t1=time.perf_counter();"
+            "h.render(pkg.SHIM_PATH,img,pkg.render.PlugInVals(new_width=%d,new_height=%d));"
+            "print(time.perf_counter()-t1)" % (REPO, W, H, CH, W - SEAMS, H))
+    try:
+        out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+        return float(out.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
+
+
+def batch_device(eng, d_in, d_out, group):
+    """A shard of the batch, images already in HBM: lockstep sessions of `group` carvers (b200c_batch_build_maps)."""
+    n = d_in.shape[0]
+    P = C.c_void_p
+    for g0 in range(0, n, group):
+        g = min(group, n - g0)
+        cs = []
+        try:
+            for i in range(g):
+                c = eng.b200c_carver_new_device(d_in[g0 + i].data_ptr(), B_W, B_H, CH)
+                if not c:
+                    raise RuntimeError(eng.b200c_last_error().decode())
+                cs.append(c)
+                if not (eng.b200c_carver_init(c, 1, 0.0) == 1 and eng.b200c_carver_set_energy_function(c, 2) == 1 and
+                        eng.b200c_carver_set_side_switch_frequency(c, 2) == 1):
+                    raise RuntimeError(eng.b200c_last_error().decode())
+            if eng.b200c_batch_build_maps((P * g)(*cs), g, B_SEAMS + 1) != 1:
+                raise RuntimeError(eng.b200c_last_error().decode())
+            for i, c in enumerate(cs):
+                if not (eng.b200c_carver_set_width(c, B_W - B_SEAMS) == 1 and
+                        eng.b200c_carver_readout_device(c, d_out[g0 + i].data_ptr()) == 1):
+                    raise RuntimeError(eng.b200c_last_error().decode())
+        finally:
+            for c in cs:
+                eng.b200c_carver_destroy(c)
+
+
+def bench_batch(eng, torch, dist, dev, rank, world, steps, warmup, group):
+    """BASELINE.json configs[3]: 256 x 1920x1080 RGBA, 100 seams each, image i -> rank i mod N; no collective on the
+    data path.  Returns this rank's (device ms per pass, e2e ms per pass, images in the shard, output digest)."""
+    batch = importlib.import_module("gimp-lqr-plugin_b200.batch")
+    harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
+    mine = batch.shard_indices(B_IMAGES, world, rank)
+    host = np.stack([batch.batch_image(i, B_W, B_H, CH) for i in mine])
+    d_in = torch.from_numpy(host).to(dev)
+    d_out = torch.empty((len(mine), B_H, B_W - B_SEAMS, CH), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        eng.b200c_set_stream(C.c_void_p(stream.cuda_stream))
+        for _ in range(max(1, min(warmup, 2))):
+            batch_device(eng, d_in[:group], d_out[:group], group)
+        stream.synchronize()
+        if world > 1:
+            dist.barrier()
+        evs = []
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            batch_device(eng, d_in, d_out, group)
+            b.record(stream)
+            evs.append((a, b))
+        stream.synchronize()
+        dev_ms = sum(a.elapsed_time(b) for a, b in evs) / steps
+        eng.b200c_set_stream(None)
+    first = d_out[0].cpu().numpy()
+    del d_in, d_out
+    # e2e: host buffers through the C ABI (harness_render_lockstep: groups set up, resized by one lqr_b200_batch_resize
+    # call, written back; a few groups in flight so that the copies of one overlap the seams of another)
+    vals = pkg.render.PlugInVals(new_width=B_W - B_SEAMS, new_height=B_H)
+    layers = [host[i] for i in range(len(mine))]
+    g2, fl = max(1, min(16, len(layers) // 4 or 1)), 4
+    harness.render_lockstep(pkg.SHIM_PATH, layers[: g2 * fl], vals, group=g2, in_flight=fl)
+    if world > 1:
+        dist.barrier()
+    runs = [harness.render_lockstep(pkg.SHIM_PATH, layers, vals, group=g2, in_flight=fl, keep_outputs=(k == 0))
+            for k in range(max(1, min(steps, 3)))]
+    e2e_ms = statistics.median(r["wall_ms"] for r in runs)
+    assert np.array_equal(runs[0]["outputs"][0], first), "batch: device-resident and C-ABI paths disagree"
+    return dev_ms, e2e_ms, len(mine), (g2, fl)
 
 
 def main():
@@ -196,9 +340,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4],
+                    help="headline workload: BASELINE.json configs[1] (one 4K image per GPU, default) or configs[3] (the "
+                         "256-image batch, strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--batch-in-flight", type=int, default=8,
-                    help="N=1 only: also time 2x this many images of the workload, this many in flight (0 = skip)")
+    ap.add_argument("--no-batch", action="store_true", help="skip the config-4 batch object of the default line")
+    ap.add_argument("--batch-group", type=int, default=128, help="images per lockstep session (device-resident leg)")
+    ap.add_argument("--batch-in-flight", type=int, default=0,
+                    help="N=1 only: also time 2x this many 4K images, this many in flight on host threads (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -225,17 +374,61 @@ def main():
     pkg.load_product()  # fails loudly when the CUDA engine is not built
     eng.b200c_set_device(local_rank)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_max(vals):
+        """max over ranks of every entry, plus the per-rank rows (for attribution of stragglers)"""
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        rows = [t.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(rows, t)
+        else:
+            rows = [t]
+        per_rank = [r.tolist() for r in rows]
+        return [max(r[i] for r in per_rank) for i in range(len(vals))], per_rank
+
+    # ================= config 4: the 256-image batch, sharded over the ranks =================================
+    batch_obj = None
+    if args.config == 4 or not args.no_batch:
+        b_steps = args.steps if args.config == 4 else max(1, min(args.steps, 3))
+        with ClockSampler(local_rank) as bclk:
+            dev_ms, e2e_ms, n_mine, (g2, fl) = bench_batch(eng, torch, dist, dev, rank, world, b_steps, warmup,
+                                                           args.batch_group)
+        (dev_max, e2e_max), per_rank = gather_max([dev_ms, e2e_ms])
+        total_seams = B_IMAGES * B_SEAMS
+        batch_obj = {
+            "metric": B_METRIC, "value": total_seams / (dev_max * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
+            "ms_per_pass": dev_max, "config": B_CONFIG, "images_per_rank": n_mine, "lockstep_group": args.batch_group,
+            "e2e": {"value": total_seams / (e2e_max * 1e-3), "unit": UNIT, "ms_per_pass": e2e_max,
+                    "h2d_bytes_per_pass": B_IMAGES * B_W * B_H * CH, "d2h_bytes_per_pass": B_IMAGES * (B_W - B_SEAMS) * B_H * CH,
+                    "path": f"tests/harness harness_render_lockstep -> liblqr-1.so: groups of {g2} carvers per "
+                            f"lqr_b200_batch_resize call, {fl} groups in flight per rank, pageable host buffers"},
+            "per_rank_ms": [{"device": r[0], "e2e": r[1]} for r in per_rank],
+            "clocks": bclk.summary(),
+            "collective": "none on the data path (independent images); ranks only meet at the timing barrier",
+        }
+
+    if args.config == 4:
+        if rank == 0:
+            line = {"metric": B_METRIC, "value": batch_obj["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": warmup, "ms_per_step": batch_obj["ms_per_pass"], "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": B_CONFIG, "e2e": batch_obj["e2e"],
+                    "gpu_launches": None, "clocks": batch_obj["clocks"], "per_rank_ms": batch_obj["per_rank_ms"]}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ================= config 2: one 4K image per GPU (the headline) =====================================
     img = pkg.synth.smooth_noise(W, H, CH, seed=pkg.synth.SEED + rank)
     d_in = torch.from_numpy(img).to(dev)
     d_out = torch.empty((H, W - SEAMS, CH), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     # ---------------- value: device-resident, CUDA events on the engine's stream ----------------------
     with torch.cuda.stream(stream):
@@ -272,7 +465,8 @@ def main():
             device_step(eng, d_in.data_ptr(), d_out.data_ptr())
         stream.synchronize()
         stages = {}
-        for s in ["energy_full", "mmap_full", "seam_jumps", "vpath", "carve", "energy_band", "mmap_update", "mmap_tail", "fix_parents", "inflate", "readout"]:
+        for s in ["energy_full", "mmap_full", "seam_jumps", "vpath", "carve", "energy_band", "mmap_update", "mmap_tail",
+                  "fix_parents", "inflate", "readout"]:
             n = C.c_long()
             ms = eng.b200c_stage_ms(s.encode(), C.byref(n))
             if n.value:
@@ -295,11 +489,10 @@ def main():
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     assert np.array_equal(out_abi, out_dev), "device-resident and C-ABI paths disagree"
+    out_abi = out_abi.copy()
 
-    # ---------------- several images in flight on this GPU (a batch host; SURVEY.md config 4's shape) ---------------
-    # Same workload and C-ABI path as e2e, host threads in C (harness_render_batch), one stream per image: the row-serial
-    # chains of different images overlap on different SMs.  Reported beside the headline, not as it.
-    batch_line = None
+    # ---------------- several 4K images in flight on host threads (optional, N=1) -------------------------------
+    in_flight_line = None
     if world == 1 and args.batch_in_flight > 0:
         harness = importlib.import_module("gimp-lqr-plugin_b200.harness")
         vals = pkg.render.PlugInVals(new_width=W - SEAMS, new_height=H)
@@ -307,15 +500,12 @@ def main():
         harness.render_batch(pkg.SHIM_PATH, [img] * k, vals, in_flight=k)  # warm-up: staging buffers, lanes, graphs
         runs = [harness.render_batch(pkg.SHIM_PATH, [img] * (2 * k), vals, in_flight=k) for _ in range(3)]
         r = sorted(runs, key=lambda x: x["wall_ms"])[1]  # median of three batches
-        batch_line = {"value": 2 * k * SEAMS / (r["wall_ms"] * 1e-3), "unit": UNIT, "images": 2 * k, "in_flight": k,
-                      "wall_ms": r["wall_ms"], "batches": "median of 3",
-                      "path": "tests/harness harness_render_batch -> liblqr-1.so, one host thread + one stream per image"}
+        in_flight_line = {"value": 2 * k * SEAMS / (r["wall_ms"] * 1e-3), "unit": UNIT, "images": 2 * k, "in_flight": k,
+                          "wall_ms": r["wall_ms"], "batches": "median of 3",
+                          "path": "tests/harness harness_render_batch -> liblqr-1.so, one host thread + one stream per image"}
 
     # ---------------- reduce over ranks ------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, e2e_ms_max = t.tolist()
+    (dev_ms_max, e2e_ms_max), per_rank = gather_max([dev_ms, e2e_s * 1e3])
     value = world * SEAMS * args.steps / (dev_ms_max / 1e3)
     e2e_value = world * SEAMS * args.steps / (e2e_ms_max / 1e3)
 
@@ -329,34 +519,32 @@ def main():
             alg_bytes = 13.0 * cells / max(n_l, 1)  # per evaluated band cell: en 4 + m 4 + parent 1 read, m 4 written
             note = ("k_band_dp: 13 B per evaluated band cell (compact maps); row-serial chain of h dependent rows on one "
                     "SM -- latency-bound, not bandwidth-bound, see DESIGN.md section 4")
+            kname = "k_band_dp"
         elif dom == "mmap_full":
             alg_bytes = 8.0 * (W - SEAMS / 2) * H
             note = "full DP: 8 B/px (en read + m written)"
+            kname = "k_mmap_full_strips"
         else:
             alg_bytes = 8.0 * W * H / 2
             note = "index-table shift: 8 B x (W - x_seam) per row"
+            kname = "k_carve"
         dur_s = stages[dom]["us_per_launch"] * 1e-6
         achieved = alg_bytes / dur_s / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one k_band_dp launch, from the committed ncu --set full capture
-        # (profiles/r01_band_dp_ncu_summary.txt: 7.73 MB read, 0 written back before the kernel ends -- the maps are L2-resident)
-        traffic = 7.73e6 if dom == "mmap_update" else None
         mf = stages.get("mmap_full")
         roof_full = None
         if mf:
-            # launches_per_step counts the row-block launches of all full passes; one pass = all its row blocks
-            passes = 3.0
-            t_pass = mf["ms_per_step"] / passes * 1e-3
+            passes = mf["launches_per_step"] / max(1.0, float((H + 31) // 32)) if mf["launches_per_step"] > 8 else mf["launches_per_step"]
+            t_pass = mf["ms_per_step"] / max(passes, 1.0) * 1e-3
             a_full = 8.0 * (W - SEAMS / 2) * H / t_pass / 1e9
             roof_full = {"bound": "hbm", "achieved": a_full, "peak": peak, "unit": "GB/s", "frac": a_full / peak,
-                         "traffic": None, "kernel": "k_mmap_full_strips (one full m-map DP pass = h/32 launches, 8 B/px)",
-                         "ms_per_pass": t_pass * 1e3}
+                         "traffic": profile_traffic("k_mmap_full_strips"),
+                         "kernel": "full m-map DP pass (8 B/px: en read + m written), single 4K image", "ms_per_pass": t_pass * 1e3,
+                         "passes_per_step": passes}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "l2": "flushed between timed steps (256 MiB write)",
-                       "timing": "CUDA events on the engine's stream per step, max over ranks",
-                       "mpixel_per_s_carved": value * (W - SEAMS / 2) * H / 1e6},
+            "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "mpixel_per_s_carved": value * (W - SEAMS / 2) * H / 1e6,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": W * H * CH,
                     "d2h_bytes_per_step": (W - SEAMS) * H * CH, "ms_per_step": e2e_ms_max / args.steps,
                     "phases_ms": {k: round(v, 3) for k, v in phases.items()},
@@ -367,16 +555,25 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": dom, "share_of_step": stages[dom]["ms_per_step"] / total_stage,
+                         "traffic": profile_traffic(kname), "kernel": dom, "share_of_step": stages[dom]["ms_per_step"] / total_stage,
                          "peak_source": peak_src, "note": note},
             "roofline_mmap_full": roof_full,
             "kernels": {k: {kk: round(vv, 4) for kk, vv in v.items()} for k, v in stages.items()},
+            "per_rank_ms": [{"device_per_step": r[0] / args.steps, "e2e_per_step": r[1] / args.steps} for r in per_rank],
             "wall_s_timed_region": wall,
         }
-        if batch_line:
-            line["batch_in_flight"] = batch_line
+        if batch_obj:
+            line["config4_batch"] = batch_obj
+        if in_flight_line:
+            line["batch_in_flight"] = in_flight_line
+        if world == 1:
+            line["cold_e2e_s"] = cold_start_s()
         if not args.no_cpu_baseline and world == 1:
-            line["cpu_baseline"] = cpu_baseline()
+            base, out_cpu = cpu_baseline()
+            line["cpu_baseline"] = base
+            # the CPU leg carves rank 0's image: the C-ABI output of the CUDA path must be the same bytes
+            line["parity_checked"] = bool(np.array_equal(out_cpu, out_abi))
+            assert line["parity_checked"], "CUDA path and CPU oracle disagree on the bench workload"
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -145,6 +145,8 @@ struct Lane {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr; // blocking-sync event: see carver_sync()
+    cudaEvent_t prog[4] = {nullptr, nullptr, nullptr, nullptr}; // progress points of a build session (build_vsmap)
+    int *seams_h = nullptr;     // mapped pinned word: seams of the running session the device has completed
     std::map<int, LaneGraph> graphs; // per kernel set of the per-seam loop (graph_key)
 };
 std::mutex g_lane_mu;
@@ -159,6 +161,9 @@ void lane_destroy(Lane *l)
     for (cudaEvent_t e : l->ev)
         if (e) cudaEventDestroy(e);
     if (l->done) cudaEventDestroy(l->done);
+    for (cudaEvent_t e : l->prog)
+        if (e) cudaEventDestroy(e);
+    if (l->seams_h) cudaFreeHost(l->seams_h);
     if (l->pooled && l->stream) cudaStreamDestroy(l->stream);
     delete l;
 }
@@ -187,6 +192,9 @@ Lane *lane_acquire(int device, bool use_ext, cudaStream_t ext)
     bool ok = use_ext || cudaStreamCreateWithFlags(&l->stream, cudaStreamNonBlocking) == cudaSuccess;
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&l->ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&l->prog[i], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaHostAlloc((void **) &l->seams_h, 64, cudaHostAllocMapped) == cudaSuccess;
+    if (ok) *l->seams_h = 0;
     if (!ok) {
         --g_lanes_busy;
         lane_destroy(l);
@@ -233,6 +241,7 @@ struct B200Carver {
     int level = 1, max_level = 1;
     int channels = 0, alpha = -1, transposed = 0;
     bool active = false, nrg_active = false, nrg_uptodate = false;
+    bool raw_ident = false; // the index table is the identity since init_raw (no carve, no inflate yet)
     B200Carver *root = nullptr;
     std::vector<B200Carver *> attached;
 
@@ -328,6 +337,7 @@ DevP view(const B200Carver *c)
 {
     DevP p;
     p.dyn = nullptr;
+    p.dyn_host = nullptr;
     p.w = c->w;
     p.h = c->h;
     p.w0 = c->w0;
@@ -344,6 +354,7 @@ DevP view(const B200Carver *c)
     p.read_kind = c->read_kind;
     p.nrg_radius = c->nrg_radius;
     p.use_rig = c->rigidity != 0.f;
+    p.raw_ident = c->raw_ident && c->w == c->w0 && c->w0 == c->w_start ? 1 : 0;
     p.bd_maxseg = c->bd_maxseg;
     p.rgb = c->rgb;
     p.vs = c->vs;
@@ -375,6 +386,7 @@ DevP view_dyn(const B200Carver *c)
     DevP p = view(c);
     p.w = c->w_epoch;
     p.dyn = c->dyn_d;
+    p.dyn_host = (c->lane && c->mates.empty()) ? c->lane->seams_h : nullptr; // UVA: the mapped word's host address is its device address
     return p;
 }
 
@@ -441,6 +453,7 @@ int init_raw(B200Carver *c)
     dim3 grid((c->w_start + 255) / 256, c->h_start);
     StageScope sc("init_raw", c->stream);
     k_init_raw<<<grid, 256, 0, c->stream>>>(c->raw, c->w_start, c->h_start);
+    c->raw_ident = true;
     return check_launch("k_init_raw");
 }
 
@@ -522,7 +535,7 @@ int build_emap(B200Carver *c)
 {
     if (c->nrg_uptodate) return B200C_OK;
     B_TRY(upload_tab(c, false));
-    dim3 grid((c->pitch + 255) / 256, c->h, batch_n(c));
+    dim3 grid((c->pitch + EF_TW - 1) / EF_TW, (c->h + EF_TH - 1) / EF_TH, batch_n(c));
     StageScope sc("energy_full", c->stream);
     k_energy_full<<<grid, 256, 0, c->stream>>>(view(c), tab_static(c));
     B_TRY(check_launch("k_energy_full"));
@@ -534,47 +547,58 @@ bool fast_path(const B200Carver *c) { return !c->generic; }
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the device that is current when it is called, and one
 // process may drive several GPUs (b200c_set_device): the opt-in is tracked per device.
-template <int D>
-void raise_smem_limits_d(cudaError_t &err)
+// It is also LAZY -- only the instances a carver can launch (its delta_x, with / without rigidity; both tie rules) are
+// touched: with lazy module loading every cudaFuncSetAttribute pulls that kernel's code onto the device, and a one-shot
+// plug-in process (GIMP runs one per non-interactive invocation) should not pay for the instances it never uses.
+template <int D, bool RIG>
+void raise_smem_limits_dr(cudaError_t &err)
 {
     auto set = [&err](const void *fn, size_t bytes) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) bytes);
         if (e != cudaSuccess && err == cudaSuccess) err = e;
     };
-    set((const void *) k_band_tail<D, true, false>, bt_smem_bytes(D, true));
-    set((const void *) k_band_tail<D, true, true>, bt_smem_bytes(D, true));
-    set((const void *) k_band_tail<D, false, false>, bt_smem_bytes(D, false));
-    set((const void *) k_band_tail<D, false, true>, bt_smem_bytes(D, false));
-    set((const void *) k_band_dp<D, false, false>, bd_smem_bytes());
-    set((const void *) k_band_dp<D, false, true>, bd_smem_bytes());
-    set((const void *) k_band_dp<D, true, false>, bd_smem_bytes());
-    set((const void *) k_band_dp<D, true, true>, bd_smem_bytes());
-    set((const void *) k_mmap_full_strips<D, false, false>, mf_smem_bytes(D, false));
-    set((const void *) k_mmap_full_strips<D, false, true>, mf_smem_bytes(D, false));
-    set((const void *) k_mmap_full_strips<D, true, false>, mf_smem_bytes(D, true));
-    set((const void *) k_mmap_full_strips<D, true, true>, mf_smem_bytes(D, true));
+    set((const void *) k_band_tail<D, RIG, false>, bt_smem_bytes(D, RIG));
+    set((const void *) k_band_tail<D, RIG, true>, bt_smem_bytes(D, RIG));
+    set((const void *) k_band_dp<D, RIG, false>, bd_smem_bytes());
+    set((const void *) k_band_dp<D, RIG, true>, bd_smem_bytes());
+    set((const void *) k_mmap_full_strips<D, RIG, false>, mf_smem_bytes(D, RIG));
+    set((const void *) k_mmap_full_strips<D, RIG, true>, mf_smem_bytes(D, RIG));
 }
 
-int raise_smem_limits(int device)
+int raise_smem_limits(const B200Carver *c)
 {
     static std::mutex mu;
-    static std::map<int, cudaError_t> done; // device -> outcome of the opt-in
+    static std::map<int, cudaError_t> done; // (device, delta_x, rigidity) -> outcome of the opt-in
+    const int device = c->device, D = c->delta_x > 4 ? 4 : c->delta_x;
+    const bool rig = c->rigidity != 0.f;
+    const int key = device * 64 + D * 2 + (rig ? 1 : 0), key0 = device * 64 + 63;
     std::lock_guard<std::mutex> lk(mu);
-    auto it = done.find(device);
+    cudaError_t err = cudaSuccess;
+    if (done.find(key0) == done.end()) { // the kernels without template parameters, once per device
+        err = cudaSetDevice(device);
+        if (err == cudaSuccess) err = cudaFuncSetAttribute((const void *) k_seam_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sp_smem_bytes());
+        if (err == cudaSuccess) err = cudaFuncSetAttribute((const void *) k_seam_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st_chase_smem());
+        done.emplace(key0, err);
+    }
+    if (done[key0] != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", done[key0]);
+    auto it = done.find(key);
     if (it == done.end()) {
-        cudaError_t err = cudaSetDevice(device);
+        err = cudaSetDevice(device);
         if (err == cudaSuccess) {
-            cudaError_t e = cudaFuncSetAttribute((const void *) k_seam_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sp_smem_bytes());
-            if (e != cudaSuccess) err = e;
-            e = cudaFuncSetAttribute((const void *) k_seam_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st_chase_smem());
-            if (e != cudaSuccess) err = e;
-            raise_smem_limits_d<0>(err);
-            raise_smem_limits_d<1>(err);
-            raise_smem_limits_d<2>(err);
-            raise_smem_limits_d<3>(err);
-            raise_smem_limits_d<4>(err);
+            switch (D * 2 + (rig ? 1 : 0)) {
+                case 0: raise_smem_limits_dr<0, false>(err); break;
+                case 1: raise_smem_limits_dr<0, true>(err); break;
+                case 2: raise_smem_limits_dr<1, false>(err); break;
+                case 3: raise_smem_limits_dr<1, true>(err); break;
+                case 4: raise_smem_limits_dr<2, false>(err); break;
+                case 5: raise_smem_limits_dr<2, true>(err); break;
+                case 6: raise_smem_limits_dr<3, false>(err); break;
+                case 7: raise_smem_limits_dr<3, true>(err); break;
+                case 8: raise_smem_limits_dr<4, false>(err); break;
+                default: raise_smem_limits_dr<4, true>(err); break;
+            }
         }
-        it = done.emplace(device, err).first;
+        it = done.emplace(key, err).first;
     }
     if (it->second != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", it->second);
     return B200C_OK;
@@ -647,7 +671,7 @@ int build_mmap(B200Carver *c)
 {
     B_TRY(upload_tab(c, false));
     if (fast_path(c) && c->delta_x <= 4) {
-        B_TRY(raise_smem_limits(c->device));
+        B_TRY(raise_smem_limits(c));
         const int R = mf_rows(c->delta_x), S = 128 - 2 * mf_hk(c->delta_x);
         const int nstrips = (c->w + 4 + S - 1) / S;
         const int grid = (nstrips + MF_WARPS - 1) / MF_WARPS;
@@ -697,6 +721,7 @@ int inflate(B200Carver *c, int l)
     dfree(c, c->bias);
     dfree(c, c->rigmask);
     c->nrg_uptodate = false; // the compact maps keep their size (w_start x h); the next build_maps refills them
+    c->raw_ident = false;
     c->rgb = new_rgb;
     if (!c->root) {
         dfree(c, c->vs);
@@ -753,7 +778,7 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     int n = vpath_launch_list(c, out);
     out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false};
-    out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + 7) / 8), dim3(256), 0, 0, false};
+    out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + B200C_EB_ROWS - 1) / B200C_EB_ROWS), dim3(256), 0, 0, false};
     if (!with_update) return n;
     if (band) {
         out[n++] = {"mmap_update", band_dp_fn(c, false), dim3(1), dim3(BD_THREADS), bd_smem_bytes(), 2, false};
@@ -866,7 +891,7 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
 int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
 {
     cudaStream_t s = c->stream;
-    if (fast_path(c)) B_TRY(raise_smem_limits(c->device));
+    if (fast_path(c)) B_TRY(raise_smem_limits(c));
     const bool last = c->w - 1 <= 1; // the image is about to be one pixel wide
     const bool lr_switch = !last && c->lr_freq && ((l - c->max_level + lr_switch_interval / 2) % lr_switch_interval) == 0;
     if (last) {
@@ -900,6 +925,7 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
         m->level++;
         m->w--;
         m->nrg_uptodate = !last;
+        m->raw_ident = false;
     });
     if (last) {
         StageScope sc("finish_vsmap", s);
@@ -926,7 +952,8 @@ int gather_rig(B200Carver *c)
     return check_launch("k_gather_rig");
 }
 
-int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user, bool do_inflate)
+int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user, bool do_inflate,
+                int update_phase = 0)
 {
     int lr_switch_interval = 0;
     if (depth == 0) depth = c->w_start + 1;
@@ -939,7 +966,7 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
     if (!c->mates.empty()) for_batch(c, [](B200Carver *m) { m->use_tail = false; }); // one grid barrier cannot serve many images
     if (c->use_tail && fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX) {
         // the tail kernel needs a grid barrier: every CTA of its grid must be resident at once (cooperative launch)
-        B_TRY(raise_smem_limits(c->device));
+        B_TRY(raise_smem_limits(c));
         int coop = 0, sms = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
@@ -961,11 +988,42 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
         CU_TRY(e);
     }
     B_TRY(upload_tab(c, true));
-    for (int l = first; l < depth; ++l) {
-        if (progress && ((l - first) % update_step) == 0) {
-            if (progress(user, l - first)) return fail(B200C_CANCEL, "cancelled by progress callback");
+    // Progress (LqrProgress update, render.c:767-779): liblqr reports "i seams done" when they ARE done.  The seam loop
+    // is queued asynchronously, so every progress point is marked by an event in the queue and its callback is
+    // delivered -- on this, the caller's thread -- once that event has completed, one update step behind the
+    // enqueue front (the device never runs dry while the host is in the callback).  A callback that asks to cancel
+    // stops the enqueueing; the seams already queued (at most one step) still complete.
+    struct Point { int seam, ev; };
+    Point pending[4];
+    int n_pending = 0, n_points = 0;
+    bool cancelled = false;
+    if (c->lane && c->lane->seams_h) *c->lane->seams_h = 0;
+    auto deliver = [&]() -> int { // the oldest pending point
+        const Point pt = pending[0];
+        for (int i = 1; i < n_pending; ++i) pending[i - 1] = pending[i];
+        --n_pending;
+        if (pt.ev >= 0) CU_TRY(cudaEventSynchronize(c->lane->prog[pt.ev]));
+        if (progress(user, pt.seam)) cancelled = true;
+        return B200C_OK;
+    };
+    for (int l = first; l < depth && !cancelled; ++l) {
+        const int i = l - first;
+        if (progress && ((i + update_phase) % update_step) == 0) {
+            int ev = -1;
+            if (i > 0 && c->lane) { // completes when the seams before i are done
+                ev = n_points++ & 3;
+                CU_TRY(cudaEventRecord(c->lane->prog[ev], c->stream));
+            }
+            if (n_pending == 4) B_TRY(deliver());
+            pending[n_pending++] = {i, ev};
         }
         B_TRY(seam_iteration(c, l, lr_switch_interval));
+        while (n_pending && !cancelled && pending[0].seam + update_step <= i + 1) B_TRY(deliver());
+    }
+    while (n_pending && !cancelled) B_TRY(deliver());
+    if (cancelled) {
+        CU_TRY(carver_sync(c)); // the queued seams complete; the carver is left mid-session, as liblqr leaves it
+        return fail(B200C_CANCEL, "cancelled by progress callback");
     }
     {
         // the staged kernels check their own window invariants on the device; a violation is a hard error
@@ -1660,6 +1718,18 @@ int b200c_carver_rigmask_add_rgb_area(B200Carver *c, const unsigned char *rgb, i
 
 int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user)
 {
+    return b200c_carver_build_maps_phase(c, depth, update_step, 0, progress, user);
+}
+
+int b200c_carver_seams_done(const B200Carver *c)
+{
+    if (!c || !c->lane || !c->lane->seams_h) return -1;
+    return *reinterpret_cast<volatile int *>(c->lane->seams_h);
+}
+
+int b200c_carver_build_maps_phase(B200Carver *c, int depth, int update_step, int update_phase, b200c_progress_fn progress,
+                                  void *user)
+{
     if (!c) return fail(B200C_ERROR, "build_maps: NULL");
     if (depth <= c->max_level) return B200C_OK;
     if (!c->active) return fail(B200C_ERROR, "build_maps: carver not initialised");
@@ -1669,7 +1739,7 @@ int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_pro
     B_TRY(build_emap(c));
     B_TRY(gather_rig(c));
     B_TRY(build_mmap(c));
-    B_TRY(build_vsmap(c, depth, update_step, progress, user, true));
+    B_TRY(build_vsmap(c, depth, update_step, progress, user, true, update_phase < 0 ? 0 : update_phase));
     return B200C_OK;
 }
 

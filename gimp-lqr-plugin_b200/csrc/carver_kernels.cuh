@@ -40,6 +40,7 @@ struct DevP {
     int leftright;
     int grad_kind, read_kind, nrg_radius;
     int use_rig;       // rigidity != 0
+    int raw_ident;     // the index table is the identity (raw[y][x] == y * w0 + x): pixels can be read without it
     int bd_maxseg;     // band DP: widest window (in segments) the tiled path takes (test knob B200C_BD_MAXSEG)
     const uint8_t *rgb;
     int *vs;
@@ -59,6 +60,7 @@ struct DevP {
     unsigned long long *cells; // running count of band cells evaluated by the incremental DP
     long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
     int *dyn;          // seam counter of the current build session, or NULL: see seam_view()
+    int *dyn_host;     // mapped host word that receives the number of COMPLETED seams of the session, or NULL
     int *tail;         // band DP -> tail kernel: {first row left to do (h: none), hull lo, hull hi} of this seam, or NULL
     int *err;          // device error word: bit 0 band left its staged window, bit 1 backtrack met a dead parent, bit 2 bulk copy timed out
 };
@@ -70,6 +72,15 @@ struct DevP {
 // Every kernel of the seam search takes its carver's argument block by value AND an optional table of blocks in HBM: a
 // batch session (b200c_batch_build_maps) advances many images with ONE launch per step, image = blockIdx.z.
 __device__ __forceinline__ DevP pick_image(const DevP &p0, const DevP *tab) { return tab ? tab[blockIdx.z] : p0; }
+
+// first thing of every iteration (one thread of the backtrack kernel): the seam counter moves on; every kernel of the
+// previous iterations has finished by now (queue order), so the counter's value IS the number of completed seams --
+// published to the host for the progress callbacks
+__device__ __forceinline__ void advance_seam(const DevP &p)
+{
+    const int i = ++*p.dyn;
+    if (p.dyn_host) *reinterpret_cast<volatile int *>(p.dyn_host) = i;
+}
 
 __device__ __forceinline__ DevP seam_view(DevP p, int post, int *seam = nullptr)
 {
@@ -86,20 +97,31 @@ __device__ __forceinline__ DevP seam_view(DevP p, int post, int *seam = nullptr)
 // ------------------------------------------------------------------------------------------------
 // A.2 pixel reading: 8-bit channel / 255 in double; brightness = mean of colour channels, luma =
 // Rec.709 weights; both multiplied by alpha when the image has an alpha channel.
-__device__ __forceinline__ double px_scalar(const DevP &p, int z)
+// t255: optional table of (double) v / 255.0 for v in 0..255 (the same correctly rounded quotients, looked up instead
+// of divided: a double division is a long software sequence on the GPU)
+__device__ __forceinline__ double px_scalar(const DevP &p, int z, const double *t255 = nullptr)
 {
     const uint8_t *q = p.rgb + (size_t) z * p.channels;
+    auto n255 = [&](unsigned v) { return t255 ? t255[v] : (double) v / 255.0; };
+    if (p.channels == 4) { // one 4-byte load per RGBA pixel; the arithmetic is the one below
+        const uchar4 c = *reinterpret_cast<const uchar4 *>(q);
+        const double r = n255(c.x), g = n255(c.y), b = n255(c.z);
+        const double v4 = p.read_kind == READ_LUMA
+                              ? __dadd_rn(__dadd_rn(__dmul_rn(0.2126, r), __dmul_rn(0.7152, g)), __dmul_rn(0.0722, b))
+                              : __dadd_rn(__dadd_rn(r, g), b) / 3.0;
+        return __dmul_rn(v4, n255(c.w));
+    }
     double v;
     if (p.channels <= 2) {
-        v = (double) q[0] / 255.0;
+        v = n255(q[0]);
     } else {
-        const double r = (double) q[0] / 255.0, g = (double) q[1] / 255.0, b = (double) q[2] / 255.0;
+        const double r = n255(q[0]), g = n255(q[1]), b = n255(q[2]);
         if (p.read_kind == READ_LUMA)
             v = __dadd_rn(__dadd_rn(__dmul_rn(0.2126, r), __dmul_rn(0.7152, g)), __dmul_rn(0.0722, b));
         else
             v = __dadd_rn(__dadd_rn(r, g), b) / 3.0;
     }
-    if (p.alpha >= 0) v = __dmul_rn(v, (double) q[p.alpha] / 255.0);
+    if (p.alpha >= 0) v = __dmul_rn(v, n255(q[p.alpha]));
     return v;
 }
 
@@ -195,27 +217,82 @@ __global__ void __launch_bounds__(256) k_gather_rig(const DevP p0, const DevP *t
     p.rig[(size_t) y * p.pitch + x] = p.rigmask ? p.rigmask[p.raw[(size_t) y * p.raw_stride + x]] : 1.f;
 }
 
-// K1 -- A.3 full energy map (lqr_carver_build_emap): one thread per visible pixel.
+// K1 -- A.3 full energy map (lqr_carver_build_emap).  A CTA owns a tile of EF_TW x EF_TH pixels of the CURRENT image:
+// the brightness / luma of the tile and its one-pixel halo is computed ONCE per pixel (fp64, as liblqr's rcache) into
+// shared memory -- RGBA pixels with one 4-byte load each, straight from the row when the index table is still the
+// identity (a fresh, flattened or transposed carver: p.raw_ident), through the table otherwise -- and every thread then
+// forms the central differences of its pixels from the staged values.  Same operations in the same order as
+// energy_at(), so the band updates (k_energy_band) and this kernel agree bit for bit.
+#define EF_TW 128
+#define EF_TH 16
 __global__ void __launch_bounds__(256) k_energy_full(const DevP p0, const DevP *tab)
 {
     const DevP p = pick_image(p0, tab);
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
-    if (x >= p.pitch || y >= p.h) return;
-    // columns right of the image hold +inf in en and m: a sentinel that never wins a minimum, so the DP kernels
-    // need no right-border case
-    p.en[(size_t) y * p.pitch + x] = x < p.w ? energy_at(p, x, y) : __int_as_float(0x7f800000);
+    __shared__ double sb[EF_TH + 2][EF_TW + 2];
+    __shared__ double t255[256]; // v / 255.0, each quotient divided once per CTA
+    const int x0 = blockIdx.x * EF_TW, y0 = blockIdx.y * EF_TH;
+    const float inf = __int_as_float(0x7f800000);
+    if (p.grad_kind != GRAD_NULL) {
+        t255[threadIdx.x] = (double) threadIdx.x / 255.0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < (EF_TH + 2) * (EF_TW + 2); i += 256) {
+            const int ty = i / (EF_TW + 2), tx = i - ty * (EF_TW + 2);
+            const int x = x0 + tx - 1, y = y0 + ty - 1;
+            double v = 0.0;
+            if (x >= 0 && x < p.w && y >= 0 && y < p.h)
+                v = px_scalar(p, p.raw_ident ? y * p.w0 + x : p.raw[(size_t) y * p.raw_stride + x], t255);
+            sb[ty][tx] = v;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < EF_TH * EF_TW; i += 256) {
+        const int ty = i / EF_TW, tx = i - ty * EF_TW;
+        const int x = x0 + tx, y = y0 + ty;
+        if (x >= p.pitch || y >= p.h) continue;
+        float e = inf; // columns right of the image hold +inf in en and m: a sentinel that never wins a minimum
+        if (x < p.w) {
+            e = 0.f;
+            if (p.grad_kind != GRAD_NULL) {
+                const double b = sb[ty + 1][tx + 1];
+                double gx, gy;
+                if (y == 0)
+                    gy = __dsub_rn(p.h > 1 ? sb[ty + 2][tx + 1] : 0.0, b);
+                else if (y < p.h - 1)
+                    gy = __dmul_rn(__dsub_rn(sb[ty + 2][tx + 1], sb[ty][tx + 1]), 0.5);
+                else
+                    gy = __dsub_rn(b, sb[ty][tx + 1]);
+                if (x == 0)
+                    gx = __dsub_rn(p.w > 1 ? sb[ty + 1][tx + 2] : 0.0, b);
+                else if (x < p.w - 1)
+                    gx = __dmul_rn(__dsub_rn(sb[ty + 1][tx + 2], sb[ty + 1][tx]), 0.5);
+                else
+                    gx = __dsub_rn(b, sb[ty + 1][tx]);
+                if (p.grad_kind == GRAD_NORM)
+                    e = (float) sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
+                else if (p.grad_kind == GRAD_SUMABS)
+                    e = (float) __dmul_rn(__dadd_rn(fabs(gx), fabs(gy)), 0.5);
+                else
+                    e = (float) fabs(gx);
+            }
+            if (p.bias) {
+                const int z = p.raw_ident ? y * p.w0 + x : p.raw[(size_t) y * p.raw_stride + x];
+                e = __fadd_rn(e, __fdiv_rn(p.bias[z], (float) p.w_start));
+            }
+        }
+        p.en[(size_t) y * p.pitch + x] = e;
+    }
 }
 
-// K1b -- A.8 energy band after a carve (lqr_carver_update_emap): one warp per row derives the row's
-// [nrg_xmin, nrg_xmax] from the seam positions of rows y-radius..y+radius and recomputes that band.
-// p.w is the width AFTER the carve; vpath_x is in pre-carve coordinates.
+// K1b -- A.8 energy band after a carve (lqr_carver_update_emap): eight threads per row derive the row's
+// [nrg_xmin, nrg_xmax] from the seam positions of rows y-radius..y+radius and recompute that band (a few cells: the
+// seam moves at most delta_x columns per row).  p.w is the width AFTER the carve; vpath_x is in pre-carve coordinates.
+#define B200C_EB_ROWS 32 // rows per CTA of 256 threads
 __global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP *tab)
 {
     const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
-    const int lane = threadIdx.x & 31;
-    const int y = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int sub = threadIdx.x & 7;
+    const int y = blockIdx.x * B200C_EB_ROWS + (threadIdx.x >> 3);
     if (y >= p.h) return;
     const int r = p.nrg_radius;
     const int own = p.vpath_x[y];
@@ -227,12 +304,12 @@ __global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP
     }
     xmin = max(0, xmin);
     xmax = min(p.w - 1, xmax);
-    if (lane == 0) {
+    if (sub == 0) {
         p.nrg_xmin[y] = xmin;
         p.nrg_xmax[y] = xmax;
         p.nrg_pack[y] = ((unsigned) xmin & 0xffffffu) | ((unsigned) max(xmax - xmin + 1, 0) << 24);
     }
-    for (int x = xmin + lane; x <= xmax; x += 32) p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
+    for (int x = xmin + sub; x <= xmax; x += 8) p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
 }
 
 // K2 (generic) -- A.5 full m-map DP (lqr_carver_build_mmap): one CTA walks the rows, the row is spread
@@ -366,7 +443,7 @@ __global__ void __launch_bounds__(1024) k_vpath(const DevP pin0, const DevP *tab
     const DevP pin = pick_image(pin0, tab);
     __shared__ float s_v[32];
     __shared__ int s_x[32];
-    if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam
+    if (pin.dyn && threadIdx.x == 0) advance_seam(pin); // this iteration's seam
     __syncthreads();
     const DevP p = seam_view(pin, 0);
     int x = last_row_argmin(p, s_v, s_x);

@@ -31,6 +31,7 @@ typedef struct {
     int (*bias_add_rgb_area)(B200Carver *, const unsigned char *, int, int, int, int, int, int);
     int (*rigmask_add_rgb_area)(B200Carver *, const unsigned char *, int, int, int, int, int);
     int (*build_maps)(B200Carver *, int, int, b200c_progress_fn, void *);
+    int (*build_maps_phase)(B200Carver *, int, int, int, b200c_progress_fn, void *);
     int (*batch_build_maps)(B200Carver **, int, int);
     int (*set_width)(B200Carver *, int);
     int (*flatten)(B200Carver *);
@@ -88,6 +89,7 @@ static int engine_load_once(void)
     BIND(bias_add_rgb_area, "b200c_carver_bias_add_rgb_area");
     BIND(rigmask_add_rgb_area, "b200c_carver_rigmask_add_rgb_area");
     BIND(build_maps, "b200c_carver_build_maps");
+    BIND(build_maps_phase, "b200c_carver_build_maps_phase");
     BIND(batch_build_maps, "b200c_batch_build_maps");
     BIND(set_width, "b200c_carver_set_width");
     BIND(flatten, "b200c_carver_flatten");
@@ -455,14 +457,16 @@ static gint step_limit(gfloat enl_step, gint ref)
     return d < 1 ? 1 : d;
 }
 
-/* engine -> shim progress hook: called before every seam, on the caller's thread */
+/* engine -> shim progress hook: called on the caller's thread at every progress point, once the device has completed
+ * the seams it reports.  gimp_progress_update is cast to the hook's type (render.c:773): its gboolean TRUE is LQR_OK;
+ * anything else cancels the resize, as in liblqr (LQR_USRCANCEL). */
 static int on_seam(void *user, int seam_index)
 {
     LqrCarver *r = (LqrCarver *) user;
     gint done = seam_index + r->session_rescale_current;
     if (done % r->session_update_step == 0 && r->progress && r->progress->update) {
         LqrRetVal ret = r->progress->update((gdouble) done / (gdouble) r->session_rescale_total);
-        (void) ret; /* gimp_progress_update's gboolean is not a cancel request (render.c:773) */
+        if (ret != LQR_OK) return 1;
     }
     return 0;
 }
@@ -496,7 +500,8 @@ static LqrRetVal resize_direction(LqrCarver *r, gint target, gboolean along_w)
         w_start = EG(r, B200C_W_START);
         new_w = target < w_start + delta_max ? target : w_start + delta_max;
         gamma = target - new_w;
-        LQR_CATCH((LqrRetVal) g_eng.build_maps(r->eng, delta0 + 1, 1, on_seam, r));
+        LQR_CATCH((LqrRetVal) g_eng.build_maps_phase(r->eng, delta0 + 1, r->session_update_step,
+                                                     r->session_rescale_current % r->session_update_step, on_seam, r));
         LQR_CATCH((LqrRetVal) g_eng.set_width(r->eng, new_w));
         r->session_rescale_current = r->session_rescale_total - (gamma > 0 ? gamma : -gamma);
         if (r->dump_vmaps) LQR_CATCH(vmap_internal_dump(r));

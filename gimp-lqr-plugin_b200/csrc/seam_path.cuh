@@ -100,7 +100,7 @@ __device__ __forceinline__ void sp_build_jumps(const signed char *tile, short *j
 __global__ void __launch_bounds__(SP_THREADS, 1) k_seam_path(const DevP pin0, const DevP *tab)
 {
     const DevP pin = pick_image(pin0, tab);
-    if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam (this kernel is the first of every iteration)
+    if (pin.dyn && threadIdx.x == 0) advance_seam(pin); // this iteration's seam
     __syncthreads();
     const DevP p = seam_view(pin, 0);
     extern __shared__ __align__(128) unsigned char sp_smem[];

@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, cons
 __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP pin0, const DevP *tab)
 {
     const DevP pin = pick_image(pin0, tab);
-    if (pin.dyn && threadIdx.x == 0) ++*pin.dyn; // this iteration's seam
+    if (pin.dyn && threadIdx.x == 0) advance_seam(pin); // this iteration's seam
     __syncthreads();
     const DevP p = seam_view(pin, 0);
     extern __shared__ __align__(16) unsigned char st_smem[];

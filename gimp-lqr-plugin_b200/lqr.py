@@ -222,7 +222,8 @@ class Carver:
             lib.lqr_progress_set_init(p, cb)
             cbs.append(cb)
         if on_update:
-            cb = PROGRESS_UPDATE(lambda f: (on_update(f), LQR_OK)[1])
+            # a hook that returns an LqrRetVal other than LQR_OK asks to cancel (None counts as LQR_OK)
+            cb = PROGRESS_UPDATE(lambda f: LQR_OK if (r := on_update(f)) is None else int(r))
             lib.lqr_progress_set_update(p, cb)
             cbs.append(cb)
         if on_end:

@@ -34,7 +34,8 @@ extern "C" {
 
 typedef struct B200Carver B200Carver;
 
-/* called before seam `seam_index` (0-based within this build_maps call) is searched; nonzero = cancel */
+/* called for the progress point "seam_index seams of this build_maps call are done" (liblqr calls its update hook
+ * before it searches seam `seam_index`); nonzero = cancel */
 typedef int (*b200c_progress_fn)(void *user, int seam_index);
 
 B200C_API int b200c_abi_version(void);
@@ -68,6 +69,14 @@ B200C_API int b200c_carver_rigmask_add_rgb_area(B200Carver *c, const unsigned ch
  * per-seam loop (backtrack, carve, band energy, band DP / side switch) up to `depth`, inflate, width reset.
  * `progress` (may be NULL) is invoked on the calling thread when seam_index % update_step == 0. */
 B200C_API int b200c_carver_build_maps(B200Carver *c, int depth, int update_step, b200c_progress_fn progress, void *user);
+/* the same with the callback points shifted: `progress` is invoked when (seam_index + update_phase) % update_step == 0.
+ * The callback for "i seams done" is delivered only after the device HAS completed them (an event in the queue marks the
+ * point; delivery runs one update step behind the enqueue front); a nonzero return stops the session: the seams
+ * already queued complete, the call returns B200C_CANCEL and leaves the carver mid-session, as liblqr does. */
+B200C_API int b200c_carver_build_maps_phase(B200Carver *c, int depth, int update_step, int update_phase,
+                                            b200c_progress_fn progress, void *user);
+/* seams of the running (or last) build session the device has completed, read from a mapped host word: never blocks */
+B200C_API int b200c_carver_seams_done(const B200Carver *c);
 /* The same build_maps session for n independent carvers of equal geometry and knobs (a batch of images, the reference's
  * batch use: batch/batch-gimp-lqr.scm:19-66), advanced in lockstep: ONE launch per step for all of them (image =
  * blockIdx.z), one host thread.  Carvers that do not agree are carved one by one.  Returns when all are done. */

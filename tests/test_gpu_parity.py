@@ -404,3 +404,47 @@ def test_c_lockstep_driver_matches_oracle(pkg, oracle):
     for img, got in zip(imgs, outs):
         want = render.render_noninteractive(oracle, img, vals).image
         assert np.array_equal(got, want)
+
+
+def test_progress_reports_completed_seams(product, oracle, engine):
+    """LqrProgress update hooks (render.c:767-779) fire for COMPLETED seams: the engine marks every progress point with
+    an event in its queue and delivers the callback once the device is past it.  At delivery of fraction i/total the
+    mapped completed-seams word must show at least i-1 (the event guarantees i; the word is written by the first kernel
+    of the next seam).  Same fractions, same count as the oracle."""
+    w, h, n = 640, 480, 100
+    img = synth.smooth_noise(w, h, 4)
+    engine.b200c_carver_seams_done.restype = C.c_int
+    engine.b200c_carver_seams_done.argtypes = [C.c_void_p]
+    logs = {}
+    for name, lib in (("oracle", oracle), ("product", product)):
+        log = []
+        with lib.carver(img) as c:
+            c.init(1, 0.0)
+            eh = product.dll.lqr_b200_engine_handle(c.handle) if lib is product else None
+            c.set_progress(on_update=lambda f, eh=eh, log=log: log.append((f, engine.b200c_carver_seams_done(eh) if eh else -1)))
+            c.resize(w - n, h)
+        logs[name] = log
+    assert [f for f, _ in logs["product"]] == [f for f, _ in logs["oracle"]]
+    assert len(logs["product"]) >= 40
+    for f, done in logs["product"]:
+        assert done >= round(f * n) - 1, f"callback for {f:.2f} delivered with only {done} seams complete"
+    # the callbacks are spread over the run, not fired while enqueueing: completed-seam counts grow from call to call
+    dones = [d for _, d in logs["product"]]
+    assert dones[-1] >= n - 4 and sum(b > a for a, b in zip(dones, dones[1:])) >= len(dones) // 2
+
+
+def test_progress_cancel(product):
+    """A hook that does not return LQR_OK cancels the resize: LQR_USRCANCEL, queued seams completed, handle destroyable."""
+    img = synth.smooth_noise(320, 240, 4)
+    calls = []
+    with product.carver(img) as c:
+        c.init(1, 0.0)
+
+        def on_update(f):
+            calls.append(f)
+            return lqr.LQR_OK if len(calls) < 5 else lqr.LQR_ERROR
+
+        c.set_progress(on_update=on_update)
+        with pytest.raises(lqr.LqrError, match="LqrRetVal 3"):
+            c.resize(220, 240)
+    assert len(calls) == 5
