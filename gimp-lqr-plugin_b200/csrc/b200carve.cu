@@ -31,6 +31,7 @@
 #include "seam_path.cuh"
 #include "seam_trace.cuh"
 #include "mmap_full_cluster.cuh"
+#include "mmap_cluster.cuh"
 
 using namespace b200c;
 
@@ -266,6 +267,7 @@ struct B200Carver {
     int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
     bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
     bool use_trace = true;                    // B200C_TRACE=0: the single-CTA staged backtrack (seam_path.cuh)
+    bool use_cluster = true;                  // B200C_CLUSTER=0: the full DP as h/32 strip launches (mmap_full_cluster.cuh)
     // batch session (b200c_batch_build_maps): this carver LEADS, its launches advance the mates too (image = blockIdx.z)
     std::vector<B200Carver *> mates;
     DevP *tab_d = nullptr;                    // [2][n]: per-seam argument blocks, then the full-pass ones
@@ -516,6 +518,7 @@ int alloc_maps(B200Carver *c)
         B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, K + 1));
         B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, K));
         B_TRY(encode_map(&c->maps.pdx, c->pdx, true, c->pitch, c->h_start, K));
+        B_TRY(encode_map(&c->maps.mst, c->m, false, c->pitch, c->h_start, K));
         c->maps.rig = c->maps.en;
     }
     return B200C_OK;
@@ -667,9 +670,74 @@ void launch_mmap_full_d(B200Carver *c, int gridx, int y0, int rows)
     else k_mmap_full_strips<D, false, false><<<grid, MF_THREADS, sm, c->stream>>>(p, y0, rows, tab);
 }
 
+// the full DP as one cluster launch per pass (mmap_cluster.cuh) + the parents of the finished map
+template <int D, bool RIG>
+int launch_mmap_cluster_dr(B200Carver *c, int csize, int nwarps)
+{
+    const void *fn = (const void *) k_mmap_full_cluster<D, RIG>;
+    const size_t smem = (size_t) nwarps * mc_warp_bytes(RIG);
+    {
+        static std::mutex mu;
+        static std::map<int, bool> done; // per device
+        std::lock_guard<std::mutex> lk(mu);
+        if (!done[c->device]) {
+            CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            CU_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * mc_warp_bytes(RIG)));
+            done[c->device] = true;
+        }
+    }
+    DevP p = view(c);
+    const DevP *tab = tab_static(c);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(csize, 1, batch_n(c));
+    cfg.blockDim = dim3(nwarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = csize, at[0].val.clusterDim.y = 1, at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void *args[3] = {&p, &nwarps, &tab};
+    CU_TRY(cudaLaunchKernelExC(&cfg, fn, args));
+    const dim3 pg((c->w + 1023) / 1024, c->h > 1 ? c->h - 1 : 1, batch_n(c));
+    if (c->leftright)
+        k_parents_full<D, RIG, true><<<pg, 256, 0, c->stream>>>(p, tab);
+    else
+        k_parents_full<D, RIG, false><<<pg, 256, 0, c->stream>>>(p, tab);
+    return check_launch("k_parents_full");
+}
+
+int launch_mmap_cluster(B200Carver *c, int csize, int nwarps)
+{
+    const bool rig = c->rigidity != 0.f;
+    switch (c->delta_x * 2 + (rig ? 1 : 0)) {
+        case 0: return launch_mmap_cluster_dr<0, false>(c, csize, nwarps);
+        case 1: return launch_mmap_cluster_dr<0, true>(c, csize, nwarps);
+        case 2: return launch_mmap_cluster_dr<1, false>(c, csize, nwarps);
+        case 3: return launch_mmap_cluster_dr<1, true>(c, csize, nwarps);
+        case 4: return launch_mmap_cluster_dr<2, false>(c, csize, nwarps);
+        case 5: return launch_mmap_cluster_dr<2, true>(c, csize, nwarps);
+        case 6: return launch_mmap_cluster_dr<3, false>(c, csize, nwarps);
+        case 7: return launch_mmap_cluster_dr<3, true>(c, csize, nwarps);
+        case 8: return launch_mmap_cluster_dr<4, false>(c, csize, nwarps);
+        default: return launch_mmap_cluster_dr<4, true>(c, csize, nwarps);
+    }
+}
+
 int build_mmap(B200Carver *c)
 {
     B_TRY(upload_tab(c, false));
+    if (fast_path(c) && c->delta_x <= 4 && c->use_cluster) {
+        const int wlim = std::min((c->w + 4 + 3) & ~3, c->pitch);
+        const int nseg = (wlim + MC_S - 1) / MC_S;
+        int nwarps = nseg <= 64 ? 4 : (nseg + 15) / 16, csize = 1;
+        while (csize * nwarps < nseg) csize *= 2;
+        if (csize <= 16 && nwarps <= 8) {
+            StageScope sc("mmap_full", c->stream, 2);
+            return launch_mmap_cluster(c, csize, nwarps);
+        }
+    }
     if (fast_path(c) && c->delta_x <= 4) {
         B_TRY(raise_smem_limits(c));
         const int R = mf_rows(c->delta_x), S = 128 - 2 * mf_hk(c->delta_x);
@@ -1409,6 +1477,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
         if (gr) c->use_graph = atoi(gr) != 0;
         const char *tl = getenv("B200C_TAIL");
         if (tl) c->use_tail = atoi(tl) != 0;
+        const char *cl = getenv("B200C_CLUSTER");
+        if (cl) c->use_cluster = atoi(cl) != 0;
         const char *tr = getenv("B200C_TRACE");
         if (tr) c->use_trace = atoi(tr) != 0;
         const char *ms = getenv("B200C_BD_MAXSEG");

@@ -125,6 +125,14 @@ __device__ __forceinline__ void bd_tma_load_2d(void *dst_smem, const CUtensorMap
         "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(bd_saddr(mbar))
         : "memory");
 }
+// shared -> global 2-D tile store (TMA), tracked by the issuing thread's bulk async-group
+__device__ __forceinline__ void bd_tma_store_2d(const CUtensorMap *tm, int c0, int c1, const void *src_smem)
+{
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                     reinterpret_cast<unsigned long long>(tm)),
+                 "r"(c0), "r"(c1), "r"(bd_saddr(src_smem))
+                 : "memory");
+}
 __device__ __forceinline__ void bd_bar_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory"); }
 
 // ------------------------------------------------------------------------------------------- compute warps
@@ -318,7 +326,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             if (slot >= SL::nslot) slot -= SL::nslot;
             const unsigned char *sb = ring + (size_t) slot * SL::bytes;
             const int cc = c & (BD_BW - 1);
-            const float *op = reinterpret_cast<const float *>(sb) + cc;               // m rows -1 .. K-1
+            float *op = const_cast<float *>(reinterpret_cast<const float *>(sb)) + cc; // m rows -1 .. K-1: old values in, new out
             const float *ep = reinterpret_cast<const float *>(sb + SL::off_e) + cc;   // en rows 0 .. K-1
             const float *gq = reinterpret_cast<const float *>(sb + SL::off_g) + cc;   // rigidity mask rows (RIG)
 
@@ -333,7 +341,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             if (d.y0 == 0) { // row 0 of the image: m = en (A.8; true of every cell of the row, evaluated or not)
                 const float4 e4 = ld4(ep);
                 mp[0] = e4.x, mp[1] = e4.y, mp[2] = e4.z, mp[3] = e4.w;
-                if (st) *reinterpret_cast<float4 *>(p.m + ((size_t) d.y0 * p.pitch + x0)) = e4;
+                if (st) *reinterpret_cast<float4 *>(op) = e4;
                 r = 1;
             }
             long long tr0 = 0;
@@ -352,7 +360,6 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             // the slow path needs no register state beyond the row counter: the unrolled fast rows stay free of moves.
             float *vr = vring + 4 * lane; // [4][128] per warp
             bool pend = false;            // row r-1 has a near cell in this lane
-            unsigned go = (unsigned) (d.y0 + r) * (unsigned) p.pitch + (unsigned) x0; // < 2^31 cells per map
             int r0 = r;                   // entry row of the fast loop
             *reinterpret_cast<float4 *>(vr + 3 * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]);
             unsigned key = 0xffffffffu;
@@ -362,7 +369,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 c.ring2 = vr + 2 * 128, c.ring3 = vr + 3 * 128;
                 c.e = ep + q * BD_BW, c.o = op + q * BD_BW, c.g = gq + q * BD_BW;
                 c.pold = pp + q * BD_BW;
-                c.dst = st ? p.m + (go - p.pitch) : nullptr;
+                c.dst = st ? op + q * BD_BW : nullptr; // over the row's old values, which this call reads first
                 c.leftfloor = leftfloor;
                 c.rigmap = p.rigmap;
                 c.has_next = has_next;
@@ -377,7 +384,10 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             // fetched first thing here (past the last row of the chunk that reads the neighbouring box of the ring and
             // is never used), so the chain never waits for shared memory.
             float4 ce = ld4(ep + r * BD_BW), co = ld4(op + r * BD_BW), cg = RIG ? ld4(gq + r * BD_BW) : one4;
-            float *gm = p.m + go; // this lane's cells of the row being computed
+            // Results go back into the tile, over the old values of the same cells, one row LATE -- when the vote has
+            // confirmed the row (the slow path still needs a pending row's old values) -- and only from the lanes that own
+            // the columns (st): everything else in the tile keeps the values it was fetched with.  After the chunk barrier
+            // the producer writes the boxes back to HBM with bulk tensor stores: no global store on the chain.
             auto fast_row = [&](const float *e_next, const float *o_next, const float *g_next, int slot) -> bool {
                 const float4 ne = ld4(e_next), no = ld4(o_next), ng = RIG ? ld4(g_next) : one4;
                 float nv[4];
@@ -390,12 +400,11 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 #endif
                 if (__any_sync(full, pend)) return true;
 #ifndef BD_EXP_NO_STORE
-                if (st) bd_st_global(gm, nv);
+                if (st) *reinterpret_cast<float4 *>(const_cast<float *>(o_next) - 2 * BD_BW) = make_float4(mp[0], mp[1], mp[2], mp[3]);
 #endif
 #ifndef BD_EXP_NO_VRING
                 *reinterpret_cast<float4 *>(vr + slot * 128) = make_float4(nv[0], nv[1], nv[2], nv[3]);
 #endif
-                gm += p.pitch;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) mp[i] = nv[i];
                 ce = ne, co = no, cg = ng;
@@ -415,16 +424,13 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                     for (; r < rows; ++r)
                         if (fast_row(ep + (r + 1) * BD_BW, op + (r + 1) * BD_BW, gq + (r + 1) * BD_BW, (r - r0) & 3)) { hit = true; break; }
                 if (!hit) break;
-                go = (unsigned) (d.y0 + r) * (unsigned) p.pitch + (unsigned) x0;
-                slow(r - 1, true); // row r-1 settled, row r redone from it: both are final now
-                if (st) bd_st_global(gm, mp);
-                gm += p.pitch;
+                slow(r - 1, true); // row r-1 settled (and stored), row r redone from it; it is stored once confirmed
                 pend = key <= BD_NEAR_MAX;
                 r0 = ++r;
                 ce = ld4(ep + r * BD_BW), co = ld4(op + r * BD_BW), cg = RIG ? ld4(gq + r * BD_BW) : one4;
             }
-            go = (unsigned) (d.y0 + rows) * (unsigned) p.pitch + (unsigned) x0;
             if (__any_sync(full, pend)) slow(rows - 1, false); // the last row of the chunk is still open
+            else if (st) *reinterpret_cast<float4 *>(op + (rows - 1) * BD_BW) = make_float4(mp[0], mp[1], mp[2], mp[3]);
             long long te0 = 0;
             if (BD_PROF && p.dbg) {
                 te0 = clock64();
@@ -450,6 +456,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
         }
         long long t1 = 0;
         if (BD_PROF && p.dbg) t1 = clock64();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the tile rows written above, for the bulk stores
         bd_bar_chunk();
         if (BD_PROF && p.dbg) t_bar += clock64() - t1;
         hl_lo = d.hlo;
@@ -473,7 +480,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
 
 // ------------------------------------------------------------------------------------------- producer warp
 struct BdMaps {
-    CUtensorMap m, en, pdx, rig; // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
+    CUtensorMap m, en, pdx, rig, mst; // mst: the m-map again with boxes of K rows, for the stores // 2-D tiled maps over the compact arrays: boxes of 128 x (K+1) (m) / 128 x K rows
 };
 
 template <int D, bool RIG>
@@ -613,7 +620,17 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             if (kp >= k + 2) publish_ready(k + 1), ready = k + 1;
             if (BD_PROF && p.dbg) t_tiles += clock64() - tw0;
         }
-        bd_bar_chunk(); // end of chunk k: its slots are free, the hull of its last row is known
+        bd_bar_chunk(); // end of chunk k: the hull of its last row is known, its new values are in the tiles
+        // write chunk k's boxes back (rows 0 .. K-1 of every m box; rows past the image are clipped by the tensor map),
+        // and let the copies READ the slots before these are handed to a later chunk's loads
+        if (lane < nb_k) {
+            int slot = dk->slot0 + lane;
+            if (slot >= SL::nslot) slot -= SL::nslot;
+            bd_tma_store_2d(&tm.mst, dk->llo + lane * BD_BW, y0_k, ring + (size_t) slot * SL::bytes + BD_BW * 4);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
+        __syncwarp();
         slots_free += nb_k;
         const int *hull_k = hull + (k & 1) * (2 * BD_NCW);
         int lo = lane < BD_NCW ? hull_k[2 * lane] : INT_MAX;
@@ -623,6 +640,9 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         yl = y0_k + rows_k - 1;
     }
     if (BD_PROF && p.dbg && lane == 0) atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) t_tiles);
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // every store has landed before the kernel goes on / ends
+    asm volatile("fence.proxy.async;" ::: "memory");
+    __threadfence();
     if (lane == 0 && p.cells) atomicAdd(p.cells, cells);
     if (lane == 0 && p.fixn) *p.fixn = kp - 1; // chunks whose parents k_fix_parents has to recompute (the last is the end marker)
     if (BD_PROF && p.dbg && lane == 0) {

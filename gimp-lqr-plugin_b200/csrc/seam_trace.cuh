@@ -27,7 +27,7 @@ namespace b200c {
 #define ST_CHASE_THREADS 1024
 #define ST_HMAX 8192
 #define ST_MAXBLK ((ST_HMAX + 27) / 28 + 1)
-#define ST_CHASE_DYN (160 * 1024) // staging area of the chase kernel (jump triangle, then parent tiles)
+#define ST_CHASE_DYN (176 * 1024) // staging area of the chase kernel (jump triangle, then parent tiles)
 
 __host__ __device__ inline int st_rows(int delta_x) { return delta_x <= 3 ? 32 : 28; } // R * delta_x <= 127: a jump fits a byte
 __host__ __device__ inline int st_nblk(int h, int delta_x) { return h > 1 ? (h - 1 + st_rows(delta_x) - 1) / st_rows(delta_x) : 0; }
@@ -109,14 +109,30 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
     while ((G + 1) * (G + 1) * reach + (G + 1) * 48 <= ST_CHASE_DYN && G < nblk) ++G;
     for (int b0 = 0; b0 < nblk; b0 += G) {
         const int g = min(G, nblk - b0), xg = ent[b0];
-        if (tid < g) { // layout of the triangle: row k holds columns [a_k, a_k + n_k) with a_k 16-byte aligned
-            int off = 0;
-            for (int k = 0; k < tid; ++k) {
-                const int a = max(xg - k * reach, 0) & ~15, e = min((xg + k * reach + 16) & ~15, p.pitch);
-                off += e - a;
+        // layout of the triangle: row k holds columns [a_k, a_k + n_k) with a_k 16-byte aligned; the row offsets are an
+        // exclusive prefix sum of the widths (two-level warp scan over at most 1024 rows)
+        {
+            const int lane = tid & 31, wid = tid >> 5;
+            int wdt = 0;
+            if (tid < g) {
+                const int a = max(xg - tid * reach, 0) & ~15, e = min((xg + tid * reach + 16) & ~15, p.pitch);
+                wdt = e - a;
             }
-            roff[tid] = off;
-            rcol[tid] = off - (max(xg - tid * reach, 0) & ~15); // stage index of column 0 of this row
+            int incl = wdt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_x[wid] = incl;
+            __syncthreads();
+            int base = 0;
+            for (int i = 0; i < wid; ++i) base += s_x[i];
+            if (tid < g) {
+                const int off = base + incl - wdt;
+                roff[tid] = off;
+                rcol[tid] = off - (max(xg - tid * reach, 0) & ~15); // stage index of column 0 of this row
+            }
         }
         __syncthreads();
         for (int k = tid >> 5; k < g; k += ST_CHASE_THREADS / 32) { // a warp per row of the triangle; copies are asynchronous
