@@ -131,7 +131,7 @@ thread_local bool g_use_ext_stream = false;
 struct LaneGraph {
     cudaGraph_t graph = nullptr; // owns the nodes whose handles address the executable's nodes
     cudaGraphExec_t exec = nullptr;
-    cudaGraphNode_t node[8] = {};
+    cudaGraphNode_t node[10] = {};
     int n = 0;
 };
 void lane_graph_reset(LaneGraph *g)
@@ -265,6 +265,8 @@ struct B200Carver {
     int4 *fix_d = nullptr;                    // band-DP chunk table for k_fix_parents (+ its count)
     int *fixn_d = nullptr;
     int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
+    int *far_d = nullptr;                     // rows whose FAR carve phase is done in this session (DevP::far)
+    bool use_split = true;                    // B200C_SPLIT=0: one carve launch per seam, nothing runs beside the band DP
     bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
     bool use_trace = true;                    // B200C_TRACE=0: the single-CTA staged backtrack (seam_path.cuh)
     bool use_cluster = true;                  // B200C_CLUSTER=0: the full DP as h/32 strip launches (mmap_full_cluster.cuh)
@@ -335,6 +337,13 @@ int check_launch(const char *what)
     return B200C_OK;
 }
 
+bool fast_path(const B200Carver *c);
+// the carve runs as NEAR + FAR launches, FAR beside the band DP: a lone image on the tiled band path only
+bool split_carve(const B200Carver *c)
+{
+    return c->use_split && c->mates.empty() && fast_path(c) && c->delta_x <= 4 && c->h <= BD_HMAX && c->far_d;
+}
+
 DevP view(const B200Carver *c)
 {
     DevP p;
@@ -376,6 +385,7 @@ DevP view(const B200Carver *c)
     p.fix = c->fix_d;
     p.fixn = c->fixn_d;
     p.tail = c->use_tail ? c->tail_d : nullptr;
+    p.far = nullptr;
     p.err = c->err_d;
     p.cells = c->cells_d;
     p.dbg = c->dbg_d;
@@ -388,7 +398,8 @@ DevP view_dyn(const B200Carver *c)
     DevP p = view(c);
     p.w = c->w_epoch;
     p.dyn = c->dyn_d;
-    p.dyn_host = (c->lane && c->mates.empty()) ? c->lane->seams_h : nullptr; // UVA: the mapped word's host address is its device address
+    p.dyn_host = (c->lane && c->mates.empty()) ? c->lane->seams_h : nullptr;
+    p.far = split_carve(c) ? c->far_d : nullptr; // UVA: the mapped word's host address is its device address
     return p;
 }
 
@@ -817,10 +828,12 @@ struct SeamLaunch {
     const void *fn;
     dim3 grid, block;
     size_t smem;
-    int second; // second kernel argument after the DevP block: 0 none, 1 the session's visibility epoch, 2 the tensor maps
+    int second; // second kernel argument after the DevP block: 0 none, 1 the session's visibility epoch + carve phase, 2 the tensor maps
     bool coop;  // cooperative launch (grid barrier inside)
+    int phase = 0; // k_carve: 0 whole row, 1 NEAR, 2 FAR
+    int dep = -1;  // graph: index of the launch this one waits for (-1: the one before it)
 };
-constexpr int kSeamLaunchMax = 8;
+constexpr int kSeamLaunchMax = 10;
 
 // the backtrack: jump tables over all SMs + a short chase (seam_trace.cuh); the single-CTA staged chase for delta_x > 4;
 // the plain walk with B200C_GENERIC=1
@@ -845,8 +858,16 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     int n = vpath_launch_list(c, out);
-    out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false};
+    int near_at = -1;
+    if (split_carve(c) && with_update) {
+        near_at = n;
+        out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false, 1};
+        out[n++] = {"carve_far", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false, 2};
+    } else {
+        out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false};
+    }
     out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + B200C_EB_ROWS - 1) / B200C_EB_ROWS), dim3(256), 0, 0, false};
+    if (near_at >= 0) out[n - 1].dep = near_at; // beside the FAR phase
     if (!with_update) return n;
     if (band) {
         out[n++] = {"mmap_update", band_dp_fn(c, false), dim3(1), dim3(BD_THREADS), bd_smem_bytes(), 2, false};
@@ -863,7 +884,7 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
 // kernel parameters of one launch of the list: (DevP, table) | (DevP, int, table) | (DevP, BdMaps, table, map table)
 struct SeamArgs {
     DevP p;
-    int epoch;
+    int epoch, phase;
     const DevP *tab;
     const BdMaps *mtab;
     void *ptr[4];
@@ -871,7 +892,11 @@ struct SeamArgs {
     {
         int n = 0;
         ptr[n++] = &p;
-        if (l.second == 1) ptr[n++] = &epoch;
+        if (l.second == 1) {
+            ptr[n++] = &epoch;
+            phase = l.phase;
+            ptr[n++] = &phase;
+        }
         if (l.second == 2) ptr[n++] = const_cast<BdMaps *>(&c->maps);
         ptr[n++] = &tab;
         if (l.second == 2) ptr[n++] = &mtab;
@@ -912,7 +937,7 @@ int graph_key(const B200Carver *c)
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4) |
-           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0) | (c->mates.empty() ? 0 : 1 << 14);
+           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0) | (c->mates.empty() ? 0 : 1 << 14) | (split_carve(c) ? 1 << 15 : 0);
 }
 
 // Points the lane's graph for the current kernel set at this carver's session: the first time the nodes are added and
@@ -936,7 +961,7 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
         kp.sharedMemBytes = (unsigned) L[i].smem;
         kp.kernelParams = a.of(c, L[i]);
         if (fresh) {
-            e = cudaGraphAddKernelNode(&g.node[i], g.graph, i ? &g.node[i - 1] : nullptr, i ? 1 : 0, &kp);
+            e = cudaGraphAddKernelNode(&g.node[i], g.graph, i ? &g.node[L[i].dep >= 0 ? L[i].dep : i - 1] : nullptr, i ? 1 : 0, &kp);
             if (e == cudaSuccess && L[i].coop) {
                 cudaKernelNodeAttrValue v = {};
                 v.cooperative = 1;
@@ -972,7 +997,7 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
         }
         StageScope sc2("carve", s);
-        k_carve<<<dim3(c->h, 1, batch_n(c)), B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch, tab_dyn(c));
+        k_carve<<<dim3(c->h, 1, batch_n(c)), B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch, 0, tab_dyn(c));
         B_TRY(check_launch("k_carve"));
     } else if (lr_switch || !c->use_graph || g_timing) {
         B_TRY(launch_seam_kernels(c, !lr_switch));
@@ -1050,7 +1075,8 @@ int build_vsmap(B200Carver *c, int depth, int update_step, b200c_progress_fn pro
         cudaError_t e = cudaSuccess;
         for_batch(c, [&](B200Carver *m) {
             m->vs_epoch = first + m->max_level - 1;
-            const cudaError_t e1 = cudaMemsetAsync(m->dyn_d, 0xff, sizeof(int), c->stream);
+            cudaError_t e1 = cudaMemsetAsync(m->dyn_d, 0xff, sizeof(int), c->stream);
+            if (e1 == cudaSuccess && m->far_d) e1 = cudaMemsetAsync(m->far_d, 0, sizeof(int), c->stream);
             if (e == cudaSuccess) e = e1;
         });
         CU_TRY(e);
@@ -1477,6 +1503,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
         if (gr) c->use_graph = atoi(gr) != 0;
         const char *tl = getenv("B200C_TAIL");
         if (tl) c->use_tail = atoi(tl) != 0;
+        const char *sp = getenv("B200C_SPLIT");
+        if (sp) c->use_split = atoi(sp) != 0;
         const char *cl = getenv("B200C_CLUSTER");
         if (cl) c->use_cluster = atoi(cl) != 0;
         const char *tr = getenv("B200C_TRACE");
@@ -1624,6 +1652,7 @@ void b200c_carver_destroy(B200Carver *c)
     dfree(c, c->fix_d);
     dfree(c, c->fixn_d);
     dfree(c, c->tail_d);
+    dfree(c, c->far_d);
     dfree(c, c->err_d);
     dfree(c, c->dyn_d);
     drop_seam_graphs(c);
@@ -1669,6 +1698,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->fix_d, (size_t) c->h / 8 + 4, true));
     B_TRY(dalloc(c, &c->fixn_d, 1, true));
     B_TRY(dalloc(c, &c->tail_d, 4, true));
+    B_TRY(dalloc(c, &c->far_d, 1, true));
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     B_TRY(dalloc(c, &c->dyn_d, 1, true));

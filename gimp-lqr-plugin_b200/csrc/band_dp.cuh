@@ -486,7 +486,7 @@ struct BdMaps {
 template <int D, bool RIG>
 __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, unsigned char *ring, const unsigned *nrg,
                                             BdDesc *desc, const int *hull, unsigned long long *mbar, volatile int *misc,
-                                            int lane)
+                                            int lane, int seam)
 {
     using SL = BdSlot<D, RIG>;
     constexpr int HK = SL::HK, S = SL::S, K = SL::K;
@@ -499,6 +499,27 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
     unsigned long long cells = 0;
     long long t_plan = 0;
 
+    // The FAR phase of this seam's carve (k_carve phase 2) may still be running beside this kernel: in row y the columns
+    // from max(s[y] - delta_x - 1, 0) + B200C_CARVE_SPAN on are its business until it has counted all h rows.  A window
+    // that reaches that far (a band over a thousand columns wide) waits for it; so does the end of the tiled path when
+    // rows are left to the tail kernel / the wide-window loop, which read whole rows.
+    bool far_done = p.far == nullptr;
+    auto far_wait = [&]() {
+        const int need = (seam + 1) * p.h;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*reinterpret_cast<volatile int *>(p.far) < need) {
+            // FAR never waits for anybody, so this ends as soon as it has run; should the two kernels ever be put in
+            // one hardware queue, give up after 2 s and flag the session instead of hanging the device
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 2000000000ull) {
+                if (lane == 0) atomicOr(p.err, 8);
+                break;
+            }
+        }
+        __threadfence();
+        far_done = true;
+    };
     // plans chunk kp and issues its tiles; false when it has to wait for ring space
     auto plan_issue = [&]() -> bool {
         const long long tp0 = (BD_PROF && p.dbg) ? clock64() : 0;
@@ -536,6 +557,13 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             if (nseg > min(BD_NCW, p.bd_maxseg) || nb > SL::nslot) end_y = ya;
         }
         if (end_y < 0 && nb > slots_free) return false;
+        if (end_y < 0 && !far_done) {
+            int cmin = INT_MAX; // leftmost energy-band start of the rows the tiles cover (incl. the row above the chunk)
+            for (int j = max(ya - 1, 0) + lane; j <= ya + rows - 1; j += 32) cmin = min(cmin, (int) (nrg[j] & 0xffffffu));
+            cmin = __reduce_min_sync(full, cmin);
+            if (llo + nb * BD_BW > max(cmin - D - 1, 0) + B200C_CARVE_SPAN) far_wait();
+        }
+        if (end_y >= 0 && end_y < p.h && !far_done) far_wait();
         if (end_y >= 0) {
             if (lane == 0) {
                 dd->rows = 0;
@@ -800,7 +828,8 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin0, cons
 {
     const DevP pin = pick_image(pin0, tab);
     const BdMaps &tm = mtab ? mtab[blockIdx.z] : tm0; // tensor maps of this image: kernel parameter, or table in HBM
-    const DevP p = seam_view(pin, 1);
+    int seam;
+    const DevP p = seam_view(pin, 1, &seam);
     extern __shared__ __align__(128) unsigned char bd_smem[];
     unsigned char *ring = bd_smem;
     unsigned *nrg = reinterpret_cast<unsigned *>(ring + BD_RING_BYTES);
@@ -823,7 +852,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin0, cons
     __syncthreads();
 
     if (warp == 0) {
-        bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane);
+        bd_producer<D, RIG>(p, tm, ring, nrg, desc, hull, mbar, misc, lane, seam);
     } else {
         bd_compute<D, RIG, LR>(p, ring, hand, vals + (size_t) (warp - 1) * 4 * 128, desc, hull, misc + 4, warp - 1, lane);
     }

@@ -61,6 +61,7 @@ struct DevP {
     long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
     int *dyn;          // seam counter of the current build session, or NULL: see seam_view()
     int *dyn_host;     // mapped host word that receives the number of COMPLETED seams of the session, or NULL
+    int *far;          // count of rows whose FAR carve phase is done in this session (k_carve phase 2), or NULL
     int *tail;         // band DP -> tail kernel: {first row left to do (h: none), hull lo, hull hi} of this seam, or NULL
     int *err;          // device error word: bit 0 band left its staged window, bit 1 backtrack met a dead parent, bit 2 bulk copy timed out
 };
@@ -469,7 +470,12 @@ __global__ void __launch_bounds__(1024) k_vpath(const DevP pin0, const DevP *tab
 // slot another thread already overwrote.
 #define B200C_CARVE_THREADS 256
 #define B200C_CARVE_ITEMS 4
-__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, int vs_value, const DevP *tab)
+// phase 0: the whole row.  phases 1 / 2 split it so that the band DP of the same seam can start early (it only reads
+// columns near the seam): 1 = NEAR, the visibility mark and the first chunk of B200C_CARVE_SPAN columns from the seam;
+// 2 = FAR, every later chunk, launched after NEAR (it overwrites the column NEAR's last cell is read from) and counted in
+// p.far when done.  Whoever moves the row's last cell also writes the +inf sentinel into the vacated column.
+#define B200C_CARVE_SPAN (B200C_CARVE_THREADS * B200C_CARVE_ITEMS)
+__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, int vs_value, int phase, const DevP *tab)
 {
     const DevP pin = pick_image(pin0, tab);
     int seam;
@@ -482,9 +488,12 @@ __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, 
     int8_t *pdx = p.pdx + o;
     const int s = p.vpath_x[y];
     const int sp = y > 0 ? p.vpath_x[y - 1] : INT_MIN;
-    if (threadIdx.x == 0) p.vs[raw[s]] = vs_value; // read before the first barrier, i.e. before any store
+    if (threadIdx.x == 0 && phase != 2) p.vs[raw[s]] = vs_value; // read before the first barrier, i.e. before any store
     const int start = max(s - p.delta_x - 1, 0);   // cells left of the seam stay put but may see their parent move
-    for (int base = start; base < p.w; base += B200C_CARVE_THREADS * B200C_CARVE_ITEMS) {
+    const bool one_chunk = start + B200C_CARVE_SPAN >= p.w; // NEAR moves the whole row
+    const int from = phase == 2 ? start + B200C_CARVE_SPAN : start;
+    const int to = phase == 1 ? min(p.w, start + B200C_CARVE_SPAN) : p.w;
+    for (int base = from; base < to; base += B200C_CARVE_SPAN) {
         int vr[B200C_CARVE_ITEMS], vd[B200C_CARVE_ITEMS];
         float ve[B200C_CARVE_ITEMS], vm[B200C_CARVE_ITEMS], vg[B200C_CARVE_ITEMS];
 #pragma unroll
@@ -522,7 +531,13 @@ __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, 
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) en[p.w] = m[p.w] = __int_as_float(0x7f800000); // the vacated column joins the sentinels
+    if (threadIdx.x == 0) {
+        if (phase == 0 || (phase == 1) == one_chunk) en[p.w] = m[p.w] = __int_as_float(0x7f800000); // the vacated column joins the sentinels
+        if (phase != 1 && p.far) { // FAR done (a whole-row launch counts as both phases)
+            __threadfence();
+            atomicAdd(p.far, 1);
+        }
+    }
 }
 
 // A.7 finish_vsmap: the image is one pixel wide; the survivors get the largest level.

@@ -25,9 +25,11 @@ namespace b200c {
 #define MC_RING 16   // energy rows per warp in shared memory
 #define MC_AHEAD 12  // rows fetched ahead of the chain
 
-__host__ __device__ constexpr int mc_rows(int delta_x) { return delta_x <= 1 ? 32 : MC_HK / delta_x; }
+__host__ __device__ constexpr int mc_rows(int delta_x) { return delta_x <= 1 ? 32 : (delta_x == 2 ? 16 : 8); } // rows * delta_x <= MC_HK
+__host__ __device__ constexpr int mc_batch(int delta_x) { return mc_rows(delta_x) < 16 ? mc_rows(delta_x) : 16; } // rows per fetch
 // bytes of shared memory per warp: energy ring (+ rigidity-mask ring), two parities of two halo buffers
-__host__ __device__ constexpr int mc_warp_bytes(bool rig) { return MC_RING * 512 * (rig ? 2 : 1) + 2 * 2 * MC_HK * 4; }
+// (without a mask: two buffers of a batch of at most 16 rows; with one: the two row rings)
+__host__ __device__ constexpr int mc_warp_bytes(bool rig) { return (rig ? MC_RING * 512 * 2 : 2 * 16 * 512) + 2 * 2 * MC_HK * 4; }
 
 __device__ __forceinline__ void mc_cp16(void *dst_smem, const void *src)
 {
@@ -68,13 +70,13 @@ __global__ void k_mmap_full_cluster(const DevP p0, int nwarps, const DevP *tab)
     unsigned char *wb = mc_smem + (size_t) warp * mc_warp_bytes(RIG);
     float *es = reinterpret_cast<float *>(wb);                                  // [MC_RING][128]
     float *gs = es + MC_RING * 128;                                             // [MC_RING][128] (RIG)
-    float *halo = reinterpret_cast<float *>(wb + MC_RING * 512 * (RIG ? 2 : 1)); // [2 parities][2 sides][MC_HK]
+    float *halo = reinterpret_cast<float *>(wb + (RIG ? MC_RING * 512 * 2 : 2 * 16 * 512)); // [2 parities][2 sides][MC_HK]
     // where this warp's interior edges go: the right halo of segment g-1, the left halo of segment g+1
     const int gl = g - 1, gr = g + 1;
     const bool has_l = gl >= 0, has_r = gr < (int) csize * nwarps;
     auto halo_of = [&](int seg, int parity, int side) -> unsigned {
         const unsigned char *wbs = mc_smem + (size_t) (seg % nwarps) * mc_warp_bytes(RIG);
-        const float *h = reinterpret_cast<const float *>(wbs + MC_RING * 512 * (RIG ? 2 : 1)) + (parity * 2 + side) * MC_HK;
+        const float *h = reinterpret_cast<const float *>(wbs + (RIG ? MC_RING * 512 * 2 : 2 * 16 * 512)) + (parity * 2 + side) * MC_HK;
         return mc_mapa(h, (unsigned) (seg / nwarps));
     };
 
@@ -82,27 +84,8 @@ __global__ void k_mmap_full_cluster(const DevP p0, int nwarps, const DevP *tab)
 #pragma unroll
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
 
-    auto fetch = [&](int y) { // energy (and rigidity-mask) row y into the ring, asynchronously
-        if (y < p.h && inmem) {
-            const size_t o = (size_t) y * p.pitch + x0;
-            mc_cp16(es + (y & (MC_RING - 1)) * 128 + 4 * lane, p.en + o);
-            if (RIG) mc_cp16(gs + (y & (MC_RING - 1)) * 128 + 4 * lane, p.rig + o);
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    for (int y = 0; y < MC_AHEAD; ++y) fetch(y);
-
-    float mp[4] = {inf, inf, inf, inf};
-    int parity = 0;
-    for (int y = 0; y < p.h; ++y) {
-        fetch(y + MC_AHEAD);
-        asm volatile("cp.async.wait_group %0;" ::"n"(MC_AHEAD) : "memory");
-        __syncwarp();
-        float4 e4 = make_float4(inf, inf, inf, inf), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (inmem) {
-            e4 = *reinterpret_cast<const float4 *>(es + (y & (MC_RING - 1)) * 128 + 4 * lane);
-            if (RIG) g4 = *reinterpret_cast<const float4 *>(gs + (y & (MC_RING - 1)) * 128 + 4 * lane);
-        }
+    // one row of the chain from its operands; stores the interior
+    auto row_step = [&](int y, const float4 e4, const float4 g4, float (&mp)[4]) {
         float nv[4];
         if (y == 0) { // row 0: m = en
             nv[0] = e4.x, nv[1] = e4.y, nv[2] = e4.z, nv[3] = e4.w;
@@ -129,27 +112,85 @@ __global__ void k_mmap_full_cluster(const DevP p0, int nwarps, const DevP *tab)
         if (interior) bd_st_global(p.m + (size_t) y * p.pitch + x0, nv);
 #pragma unroll
         for (int i = 0; i < 4; ++i) mp[i] = nv[i];
-
-        if ((y + 1) % K == 0 && y + 1 < p.h) { // end of a trapezoid: hand the interior edges over, take the halos in
-            const float4 mine = make_float4(mp[0], mp[1], mp[2], mp[3]);
-            const int c = 4 * lane - MC_HK; // column inside the interior, 0 .. 63
-            if (c >= 0 && c < MC_HK && has_l) mc_st_cluster(halo_of(gl, parity, 1) + (unsigned) c * 4u, mine);
-            if (c >= MC_S - MC_HK && c < MC_S && has_r) mc_st_cluster(halo_of(gr, parity, 0) + (unsigned) (c - (MC_S - MC_HK)) * 4u, mine);
-            __syncwarp();
-            mc_cluster_sync();
-            if (4 * lane < MC_HK) { // left halo lanes
-                if (has_l) {
-                    const float4 h = *reinterpret_cast<const float4 *>(halo + (parity * 2 + 0) * MC_HK + 4 * lane);
-                    mp[0] = h.x, mp[1] = h.y, mp[2] = h.z, mp[3] = h.w;
-                }
-            } else if (4 * lane >= MC_HK + MC_S) { // right halo lanes
-                if (has_r) {
-                    const float4 h = *reinterpret_cast<const float4 *>(halo + (parity * 2 + 1) * MC_HK + (4 * lane - MC_HK - MC_S));
-                    mp[0] = h.x, mp[1] = h.y, mp[2] = h.z, mp[3] = h.w;
-                }
+    };
+    // end of a trapezoid: hand the interior edges over, take the halos in
+    auto exchange = [&](float (&mp)[4], int parity) {
+        const float4 mine = make_float4(mp[0], mp[1], mp[2], mp[3]);
+        const int c = 4 * lane - MC_HK; // column inside the interior, 0 .. 63
+        if (c >= 0 && c < MC_HK && has_l) mc_st_cluster(halo_of(gl, parity, 1) + (unsigned) c * 4u, mine);
+        if (c >= MC_S - MC_HK && c < MC_S && has_r) mc_st_cluster(halo_of(gr, parity, 0) + (unsigned) (c - (MC_S - MC_HK)) * 4u, mine);
+        __syncwarp();
+        mc_cluster_sync();
+        if (4 * lane < MC_HK) { // left halo lanes
+            if (has_l) {
+                const float4 h = *reinterpret_cast<const float4 *>(halo + (parity * 2 + 0) * MC_HK + 4 * lane);
+                mp[0] = h.x, mp[1] = h.y, mp[2] = h.z, mp[3] = h.w;
             }
-            if (!inmem || x0 >= wlim) mp[0] = mp[1] = mp[2] = mp[3] = inf; // outside the image for good
-            parity ^= 1;
+        } else if (4 * lane >= MC_HK + MC_S) { // right halo lanes
+            if (has_r) {
+                const float4 h = *reinterpret_cast<const float4 *>(halo + (parity * 2 + 1) * MC_HK + (4 * lane - MC_HK - MC_S));
+                mp[0] = h.x, mp[1] = h.y, mp[2] = h.z, mp[3] = h.w;
+            }
+        }
+        if (!inmem || x0 >= wlim) mp[0] = mp[1] = mp[2] = mp[3] = inf; // outside the image for good
+    };
+
+    float mp[4] = {inf, inf, inf, inf};
+    int parity = 0;
+    if constexpr (!RIG) {
+        // the energy rows are fetched a BATCH (16 rows, 8 for delta_x >= 3) ahead: two buffers per warp
+        constexpr int FB = mc_batch(D);
+        float *buf = es; // [2][FB][128]
+        auto fetch_batch = [&](int c) {
+            const int y0 = c * FB;
+            if (inmem)
+                for (int r = 0; r < FB && y0 + r < p.h; ++r)
+                    mc_cp16(buf + ((c & 1) * FB + r) * 128 + 4 * lane, p.en + (size_t) (y0 + r) * p.pitch + x0);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        const int nbatch = (p.h + FB - 1) / FB;
+        fetch_batch(0);
+        for (int c = 0; c < nbatch; ++c) {
+            if (c + 1 < nbatch) fetch_batch(c + 1);
+            else asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            const int y0 = c * FB, rows = min(FB, p.h - y0);
+            const float *eb = buf + (c & 1) * FB * 128 + 4 * lane;
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) {
+                const float4 e4 = inmem ? *reinterpret_cast<const float4 *>(eb + r * 128) : make_float4(inf, inf, inf, inf);
+                row_step(y0 + r, e4, make_float4(1.f, 1.f, 1.f, 1.f), mp);
+            }
+            if ((y0 + rows) % K == 0 && y0 + rows < p.h) { // a trapezoid ends with this batch
+                exchange(mp, parity);
+                parity ^= 1;
+            }
+        }
+    } else {
+        auto fetch = [&](int y) { // energy and rigidity-mask row y into the ring, asynchronously
+            if (y < p.h && inmem) {
+                const size_t o = (size_t) y * p.pitch + x0;
+                mc_cp16(es + (y & (MC_RING - 1)) * 128 + 4 * lane, p.en + o);
+                mc_cp16(gs + (y & (MC_RING - 1)) * 128 + 4 * lane, p.rig + o);
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        for (int y = 0; y < MC_AHEAD; ++y) fetch(y);
+        for (int y = 0; y < p.h; ++y) {
+            fetch(y + MC_AHEAD);
+            asm volatile("cp.async.wait_group %0;" ::"n"(MC_AHEAD) : "memory");
+            __syncwarp();
+            float4 e4 = make_float4(inf, inf, inf, inf), g4 = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (inmem) {
+                e4 = *reinterpret_cast<const float4 *>(es + (y & (MC_RING - 1)) * 128 + 4 * lane);
+                g4 = *reinterpret_cast<const float4 *>(gs + (y & (MC_RING - 1)) * 128 + 4 * lane);
+            }
+            row_step(y, e4, g4, mp);
+            if ((y + 1) % K == 0 && y + 1 < p.h) {
+                exchange(mp, parity);
+                parity ^= 1;
+            }
         }
     }
     mc_cluster_sync(); // nobody leaves while a neighbour may still write into its halo buffers

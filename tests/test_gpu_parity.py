@@ -448,3 +448,23 @@ def test_progress_cancel(product):
         with pytest.raises(lqr.LqrError, match="LqrRetVal 3"):
             c.resize(220, 240)
     assert len(calls) == 5
+
+
+@pytest.mark.parametrize("knob", ["B200C_SPLIT", "B200C_CLUSTER", "B200C_TRACE", "B200C_GRAPH"])
+@pytest.mark.parametrize("name", ["mid_enlarge", "mid_dx3_rigmask", "wide_flat_band", "tall", "rgba_shrink_w"])
+def test_fallback_paths(product, oracle, knob, name):
+    """The round-2 fast paths switched off one at a time (read at carver creation): B200C_SPLIT=0 one carve launch per
+    seam instead of NEAR + FAR beside the band DP, B200C_CLUSTER=0 the strip launches of the full DP instead of the
+    cluster kernel, B200C_TRACE=0 the single-CTA backtrack, B200C_GRAPH=0 kernel-by-kernel launches."""
+    cs = next(c for c in CASES if c["name"] == name)
+    old = os.environ.get(knob)
+    os.environ[knob] = "0"
+    try:
+        got = cases.run_case(product, cs)
+    finally:
+        if old is None:
+            os.environ.pop(knob, None)
+        else:
+            os.environ[knob] = old
+    diffs = cases.results_equal(got, cases.run_case(oracle, cs))
+    assert not diffs, "; ".join(diffs)
