@@ -266,7 +266,8 @@ struct B200Carver {
     int *fixn_d = nullptr;
     int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
     int *far_d = nullptr;                     // rows whose FAR carve phase is done in this session (DevP::far)
-    bool use_split = true;                    // B200C_SPLIT=0: one carve launch per seam, nothing runs beside the band DP
+    bool use_split = false;                   // B200C_SPLIT=1: the carve as NEAR + FAR launches, FAR beside the band DP (measured
+                                              // SLOWER on a B200: the FAR CTAs share the band DP's SM and slow its one critical warp)
     bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
     bool use_trace = true;                    // B200C_TRACE=0: the single-CTA staged backtrack (seam_path.cuh)
     bool use_cluster = true;                  // B200C_CLUSTER=0: the full DP as h/32 strip launches (mmap_full_cluster.cuh)

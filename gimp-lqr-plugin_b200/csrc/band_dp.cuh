@@ -300,8 +300,10 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     for (int k = 0;; ++k) {
         long long tp0 = 0;
         if (BD_PROF && p.dbg) tp0 = clock64();
-        while (*ready < k) {} // normally true at once: see the producer
-        __threadfence_block();
+        if (*ready < k) { // normally false: see the producer
+            while (*ready < k) {}
+            __threadfence_block();
+        }
         const BdDesc d = desc[k % BD_NRING];
         if (d.rows == 0) break;
         int *hull_k = hull + (k & 1) * (2 * BD_NCW);

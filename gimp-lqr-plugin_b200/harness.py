@@ -130,3 +130,4 @@ def render_lockstep(lib_path: str, layers, vals: PlugInVals, group: int = 32, in
         nw, nh = vals.new_width, vals.new_height
         res["outputs"] = [a.reshape(-1)[: nw * nh * bpp].reshape(nh, nw, bpp).copy() for a in outs]
     return res
+

@@ -453,12 +453,12 @@ def test_progress_cancel(product):
 @pytest.mark.parametrize("knob", ["B200C_SPLIT", "B200C_CLUSTER", "B200C_TRACE", "B200C_GRAPH"])
 @pytest.mark.parametrize("name", ["mid_enlarge", "mid_dx3_rigmask", "wide_flat_band", "tall", "rgba_shrink_w"])
 def test_fallback_paths(product, oracle, knob, name):
-    """The round-2 fast paths switched off one at a time (read at carver creation): B200C_SPLIT=0 one carve launch per
-    seam instead of NEAR + FAR beside the band DP, B200C_CLUSTER=0 the strip launches of the full DP instead of the
+    """The round-2 paths toggled one at a time (read at carver creation): B200C_SPLIT=1 the carve as NEAR + FAR launches
+    with FAR beside the band DP (off by default: measured slower), B200C_CLUSTER=0 the strip launches of the full DP instead of the
     cluster kernel, B200C_TRACE=0 the single-CTA backtrack, B200C_GRAPH=0 kernel-by-kernel launches."""
     cs = next(c for c in CASES if c["name"] == name)
     old = os.environ.get(knob)
-    os.environ[knob] = "0"
+    os.environ[knob] = "1" if knob == "B200C_SPLIT" else "0"  # the split carve is off by default, the others on
     try:
         got = cases.run_case(product, cs)
     finally:
@@ -468,3 +468,4 @@ def test_fallback_paths(product, oracle, knob, name):
             os.environ[knob] = old
     diffs = cases.results_equal(got, cases.run_case(oracle, cs))
     assert not diffs, "; ".join(diffs)
+

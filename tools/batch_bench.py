@@ -152,7 +152,7 @@ def main():
         return
     vals = pkg.render.PlugInVals(new_width=W - SEAMS, new_height=H)
     layers = [host[i] for i in range(n)]
-    for group, fl in [(32, 2), (32, 3), (64, 2)]:
+    for group, fl in [(16, 4), (16, 8), (8, 12), (32, 4), (8, 16)]:
         harness.render_lockstep(pkg.SHIM_PATH, layers[: group * fl], vals, group=group, in_flight=fl)
         r = harness.render_lockstep(pkg.SHIM_PATH, layers, vals, group=group, in_flight=fl)
         print(f"C ABI, host buffers, group {group} x {fl} in flight: {n * SEAMS / (r['wall_ms'] * 1e-3):10.0f} seams/s  ({r['wall_ms']:.1f} ms)", flush=True)
