@@ -30,7 +30,7 @@
 #include "band_tail.cuh"
 #include "seam_path.cuh"
 #include "seam_trace.cuh"
-#include "mmap_full_cluster.cuh"
+#include "mmap_full_strips.cuh"
 #include "mmap_cluster.cuh"
 
 using namespace b200c;
@@ -270,7 +270,7 @@ struct B200Carver {
                                               // SLOWER on a B200: the FAR CTAs share the band DP's SM and slow its one critical warp)
     bool use_tail = true;                     // B200C_TAIL=0: the band kernel keeps its in-CTA wide-window loop
     bool use_trace = true;                    // B200C_TRACE=0: the single-CTA staged backtrack (seam_path.cuh)
-    bool use_cluster = true;                  // B200C_CLUSTER=0: the full DP as h/32 strip launches (mmap_full_cluster.cuh)
+    bool use_cluster = true;                  // B200C_CLUSTER=0: the full DP as h/32 strip launches (mmap_full_strips.cuh)
     // batch session (b200c_batch_build_maps): this carver LEADS, its launches advance the mates too (image = blockIdx.z)
     std::vector<B200Carver *> mates;
     DevP *tab_d = nullptr;                    // [2][n]: per-seam argument blocks, then the full-pass ones

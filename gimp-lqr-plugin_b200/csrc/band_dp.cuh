@@ -97,11 +97,13 @@ __device__ __forceinline__ void bd_mbar_arrive(void *mbar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bd_saddr(mbar)) : "memory");
 }
-// bounded wait: a copy that never completes is a bug, not a reason to hang the GPU
+// bounded wait: a copy that never completes is a bug, not a reason to hang the GPU.  The bound is TIME (2 s on the
+// global timer), not a number of polls: a tile delayed by preemption or a crowded device must not fail a resize.
 __device__ __forceinline__ bool bd_mbar_wait(void *mbar, unsigned parity)
 {
     const unsigned a = bd_saddr(mbar);
-    for (int tries = 0; tries < (1 << 22); ++tries) {
+    unsigned long long t0 = 0;
+    for (unsigned tries = 0;; ++tries) {
         unsigned ok;
         asm volatile(
             "{\n"
@@ -113,8 +115,13 @@ __device__ __forceinline__ bool bd_mbar_wait(void *mbar, unsigned parity)
             : "r"(a), "r"(parity)
             : "memory");
         if (ok) return true;
+        if ((tries & 1023u) == 1023u) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > 2000000000ull) return false;
+        }
     }
-    return false;
 }
 // global -> shared 2-D tile copy (TMA), completion counted in bytes on `mbar`; out-of-range elements arrive as 0
 __device__ __forceinline__ void bd_tma_load_2d(void *dst_smem, const CUtensorMap *tm, int c0, int c1, void *mbar)

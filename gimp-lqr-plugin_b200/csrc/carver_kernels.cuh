@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP
 
 // K2 (generic) -- A.5 full m-map DP (lqr_carver_build_mmap): one CTA walks the rows, the row is spread
 // over the threads, a block barrier separates dependent rows.  Correct for any width / delta_x; the
-// cluster kernel of mmap_full_cluster.cuh is the fast path.
+// cluster kernel of mmap_cluster.cuh is the fast path.
 __global__ void __launch_bounds__(1024) k_mmap_full(const DevP p0, const DevP *tab)
 {
     const DevP p = pick_image(p0, tab);

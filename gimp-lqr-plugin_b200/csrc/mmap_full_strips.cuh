@@ -1,4 +1,6 @@
-// mmap_full_cluster.cuh -- K2, the full m-map DP (liblqr lqr_carver_build_mmap) on the compact maps.
+// mmap_full_strips.cuh -- K2, the full m-map DP (liblqr lqr_carver_build_mmap) on the compact maps, as
+// h/32 strip launches: the FALLBACK of the one-launch cluster kernel in mmap_cluster.cuh (B200C_CLUSTER=0, or images wider
+// than 8192 columns).
 //
 // m[y][x] = en[y][x] + min over |dx| <= delta_x of m[y-1][x+dx] (+ rigidity term) is a chain of h dependent rows.
 // The image is cut into column STRIPS of 128 columns, one warp per strip, 4 consecutive cells per lane, the row
