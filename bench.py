@@ -396,31 +396,30 @@ def main():
         per_rank = [r.tolist() for r in rows]
         return [max(r[i] for r in per_rank) for i in range(len(vals))], per_rank
 
-    if args.config == 4:
-        # ================= config 4: the 256-image batch, sharded over the ranks =================================
-        batch_obj = None
-        if True:
-            b_steps = args.steps if args.config == 4 else max(1, min(args.steps, 3))
-            with ClockSampler(local_rank) as bclk:
-                dev_ms, e2e_ms, n_mine, (g2, fl, lock_ms, thr_ms) = bench_batch(eng, torch, dist, dev, rank, world, b_steps, warmup,
-                                                               args.batch_group)
-            (dev_max, e2e_max), per_rank = gather_max([dev_ms, e2e_ms])
-            total_seams = B_IMAGES * B_SEAMS
-            batch_obj = {
-                "metric": B_METRIC, "value": total_seams / (dev_max * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
-                "ms_per_pass": dev_max, "config": B_CONFIG, "images_per_rank": n_mine, "lockstep_group": args.batch_group,
-                "e2e": {"value": total_seams / (e2e_max * 1e-3), "unit": UNIT, "ms_per_pass": e2e_max,
-                        "h2d_bytes_per_pass": B_IMAGES * B_W * B_H * CH, "d2h_bytes_per_pass": B_IMAGES * (B_W - B_SEAMS) * B_H * CH,
-                        "path": ("tests/harness -> liblqr-1.so, pageable host buffers; the better of (a) harness_render_lockstep: "
-                                 f"groups of {g2} carvers per lqr_b200_batch_resize call, {fl} groups in flight per rank and (b) "
-                                 "harness_render_batch: one host thread + stream per image, 16 in flight per rank"),
-                        "lockstep_ms": lock_ms, "thread_per_image_ms": thr_ms},
-                "per_rank_ms": [{"device": r[0], "e2e": r[1]} for r in per_rank],
-                "clocks": bclk.summary(),
-                "collective": "none on the data path (independent images); ranks only meet at the timing barrier",
-            }
+    def run_batch():
+        """config 4: the 256-image batch, sharded over the ranks (image i -> rank i mod N)"""
+        b_steps = args.steps if args.config == 4 else max(1, min(args.steps, 3))
+        with ClockSampler(local_rank) as bclk:
+            b_dev_ms, b_e2e_ms, n_mine, (g2, fl, lock_ms, thr_ms) = bench_batch(eng, torch, dist, dev, rank, world, b_steps,
+                                                                              warmup, args.batch_group)
+        (dev_max, e2e_max), b_per_rank = gather_max([b_dev_ms, b_e2e_ms])
+        total_seams = B_IMAGES * B_SEAMS
+        return {
+            "metric": B_METRIC, "value": total_seams / (dev_max * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
+            "ms_per_pass": dev_max, "config": B_CONFIG, "images_per_rank": n_mine, "lockstep_group": args.batch_group,
+            "e2e": {"value": total_seams / (e2e_max * 1e-3), "unit": UNIT, "ms_per_pass": e2e_max,
+                    "h2d_bytes_per_pass": B_IMAGES * B_W * B_H * CH, "d2h_bytes_per_pass": B_IMAGES * (B_W - B_SEAMS) * B_H * CH,
+                    "path": ("tests/harness -> liblqr-1.so, pageable host buffers; the better of (a) harness_render_lockstep: "
+                             f"groups of {g2} carvers per lqr_b200_batch_resize call, {fl} groups in flight per rank and (b) "
+                             "harness_render_batch: one host thread + stream per image, 16 in flight per rank"),
+                    "lockstep_ms": lock_ms, "thread_per_image_ms": thr_ms},
+            "per_rank_ms": [{"device": r[0], "e2e": r[1]} for r in b_per_rank],
+            "clocks": bclk.summary(),
+            "collective": "none on the data path (independent images); ranks only meet at the timing barrier",
+        }
 
     if args.config == 4:
+        batch_obj = run_batch()
         if rank == 0:
             line = {"metric": B_METRIC, "value": batch_obj["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
                     "warmup": warmup, "ms_per_step": batch_obj["ms_per_pass"], "higher_is_better": True, "scaling": "strong",
@@ -514,28 +513,7 @@ def main():
                           "wall_ms": r["wall_ms"], "batches": "median of 3",
                           "path": "tests/harness harness_render_batch -> liblqr-1.so, one host thread + one stream per image"}
 
-    # ================= config 4: the 256-image batch, sharded over the ranks =================================
-    batch_obj = None
-    if not args.no_batch:
-        b_steps = args.steps if args.config == 4 else max(1, min(args.steps, 3))
-        with ClockSampler(local_rank) as bclk:
-            dev_ms, e2e_ms, n_mine, (g2, fl, lock_ms, thr_ms) = bench_batch(eng, torch, dist, dev, rank, world, b_steps, warmup,
-                                                           args.batch_group)
-        (dev_max, e2e_max), per_rank = gather_max([dev_ms, e2e_ms])
-        total_seams = B_IMAGES * B_SEAMS
-        batch_obj = {
-            "metric": B_METRIC, "value": total_seams / (dev_max * 1e-3), "unit": UNIT, "n_gpus": world, "scaling": "strong",
-            "ms_per_pass": dev_max, "config": B_CONFIG, "images_per_rank": n_mine, "lockstep_group": args.batch_group,
-            "e2e": {"value": total_seams / (e2e_max * 1e-3), "unit": UNIT, "ms_per_pass": e2e_max,
-                    "h2d_bytes_per_pass": B_IMAGES * B_W * B_H * CH, "d2h_bytes_per_pass": B_IMAGES * (B_W - B_SEAMS) * B_H * CH,
-                    "path": ("tests/harness -> liblqr-1.so, pageable host buffers; the better of (a) harness_render_lockstep: "
-                             f"groups of {g2} carvers per lqr_b200_batch_resize call, {fl} groups in flight per rank and (b) "
-                             "harness_render_batch: one host thread + stream per image, 16 in flight per rank"),
-                    "lockstep_ms": lock_ms, "thread_per_image_ms": thr_ms},
-            "per_rank_ms": [{"device": r[0], "e2e": r[1]} for r in per_rank],
-            "clocks": bclk.summary(),
-            "collective": "none on the data path (independent images); ranks only meet at the timing barrier",
-        }
+    batch_obj = None if args.no_batch else run_batch()
 
     # ---------------- reduce over ranks ------------------------------------------------------------------
     (dev_ms_max, e2e_ms_max), per_rank = gather_max([dev_ms, e2e_s * 1e3])

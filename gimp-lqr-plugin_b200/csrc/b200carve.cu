@@ -173,14 +173,16 @@ void lane_destroy(Lane *l)
 Lane *lane_acquire(int device, bool use_ext, cudaStream_t ext)
 {
     ++g_lanes_busy;
-    if (!use_ext) {
+    {
+        // a lane around a caller's stream is kept too (with its graph executables), and reused for that stream only
         std::lock_guard<std::mutex> lk(g_lane_mu);
-        for (size_t i = 0; i < g_lane_free.size(); ++i)
-            if (g_lane_free[i]->device == device) {
-                Lane *l = g_lane_free[i];
+        for (size_t i = 0; i < g_lane_free.size(); ++i) {
+            Lane *l = g_lane_free[i];
+            if (l->device == device && (use_ext ? (!l->pooled && l->stream == ext) : l->pooled)) {
                 g_lane_free.erase(g_lane_free.begin() + i);
                 return l;
             }
+        }
     }
     Lane *l = new (std::nothrow) Lane();
     if (!l) {
@@ -209,14 +211,20 @@ void lane_release(Lane *l)
 {
     if (!l) return;
     --g_lanes_busy;
-    if (l->pooled) {
+    Lane *evict = l;
+    {
         std::lock_guard<std::mutex> lk(g_lane_mu);
-        if (g_lane_free.size() < kLaneKeep) {
-            g_lane_free.push_back(l);
-            return;
-        }
+        if (g_lane_free.size() >= kLaneKeep) // full: the oldest lane around a caller's stream makes room
+            for (size_t i = 0; i < g_lane_free.size(); ++i)
+                if (!g_lane_free[i]->pooled) {
+                    evict = g_lane_free[i];
+                    g_lane_free.erase(g_lane_free.begin() + i);
+                    break;
+                }
+        if (g_lane_free.size() < kLaneKeep) g_lane_free.push_back(l);
+        if (evict == l && g_lane_free.back() == l) evict = nullptr;
     }
-    lane_destroy(l);
+    lane_destroy(evict);
 }
 
 // With many carvers in flight (a batch host: one thread per image), threads that spin in cudaStreamSynchronize get in
