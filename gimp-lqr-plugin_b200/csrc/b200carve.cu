@@ -533,7 +533,7 @@ int alloc_maps(B200Carver *c)
     if (c->active) {
         B_TRY(dalloc(c, &c->m, n, true));
         B_TRY(dalloc(c, &c->pdx, n, true));
-        B_TRY(dalloc(c, &c->jump, (size_t) st_nblk(c->h_start, c->delta_x <= 4 ? c->delta_x : 4) * c->pitch + 64, true));
+        B_TRY(dalloc(c, &c->jump, st_jump_bytes(c->h_start, c->delta_x <= 4 ? c->delta_x : 4, c->pitch), true));
         const int K = bd_rows(c->delta_x, c->rigidity != 0.f);
         B_TRY(encode_map(&c->maps.m, c->m, false, c->pitch, c->h_start, K + 1));
         B_TRY(encode_map(&c->maps.en, c->en, false, c->pitch, c->h_start, K));
@@ -849,7 +849,7 @@ constexpr int kSeamLaunchMax = 10;
 int vpath_launch_list(const B200Carver *c, SeamLaunch out[kSeamLaunchMax])
 {
     int n = 0;
-    if (fast_path(c) && c->delta_x <= 4 && c->h <= ST_HMAX && c->use_trace) {
+    if (fast_path(c) && c->delta_x <= 4 && c->h <= ST_HMAX && c->w_epoch <= ST_WMAX && c->use_trace) {
         const int nblk = st_nblk(c->h, c->delta_x);
         if (nblk > 0)
             out[n++] = {"seam_jumps", (const void *) k_seam_jumps, dim3((c->w_epoch + ST_COLS - 1) / ST_COLS, nblk), dim3(ST_THREADS),
@@ -1673,11 +1673,11 @@ void b200c_carver_destroy(B200Carver *c)
     }
     dfree(c, c->cells_d);
     if (c->dbg_d) {
-        long long v[16];
+        long long v[32];
         if (cudaMemcpyAsync(v, c->dbg_d, sizeof v, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
             carver_sync(c) == cudaSuccess) {
             fprintf(stderr, "b200c dbg:");
-            for (int i = 0; i < 16; ++i) fprintf(stderr, " %lld", v[i]);
+            for (int i = 0; i < 32; ++i) fprintf(stderr, " %lld", v[i]);
             fprintf(stderr, "\n");
         }
     }
@@ -1711,7 +1711,7 @@ int b200c_carver_init(B200Carver *c, int delta_x, float rigidity)
     B_TRY(dalloc(c, &c->err_d, 1, true));
     B_TRY(dalloc(c, &c->cells_d, 1, true));
     B_TRY(dalloc(c, &c->dyn_d, 1, true));
-    if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 16, true));
+    if (getenv("B200C_DBG")) B_TRY(dalloc(c, &c->dbg_d, 32, true));
     c->delta_x = delta_x;
     c->rigidity = rigidity;
     c->rigmap_h.assign(2 * delta_x + 1, 0.f);

@@ -58,7 +58,7 @@ struct DevP {
     int *fixn;          // number of entries of fix
     unsigned *nrg_pack; // per row: nrg_xmin | (nrg_xmax - nrg_xmin + 1) << 24, for the band DP's window planner
     unsigned long long *cells; // running count of band cells evaluated by the incremental DP
-    long long *dbg;    // optional cycle counters (B200C_DBG=1), 16 slots
+    long long *dbg;    // optional cycle counters (B200C_DBG=1), 32 slots
     int *dyn;          // seam counter of the current build session, or NULL: see seam_view()
     int *dyn_host;     // mapped host word that receives the number of COMPLETED seams of the session, or NULL
     int *far;          // count of rows whose FAR carve phase is done in this session (k_carve phase 2), or NULL
