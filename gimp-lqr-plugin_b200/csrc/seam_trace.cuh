@@ -39,6 +39,7 @@ namespace b200c {
 #define ST_MAXBLK ((ST_HMAX + 27) / 28 + 1)
 #define ST_CHASE_DYN (176 * 1024) // staging area of the chase kernel (jump triangle)
 #define ST_BAD (-128)             // sub-block jump of a path that meets a dead parent
+#define ST_PAD 1024               // bytes in front of k_seam_jumps' tile (see there)
 
 __host__ __device__ inline int st_rows(int delta_x) { return delta_x <= 3 ? 32 : 28; } // R * delta_x <= 127: a jump fits a byte
 __host__ __device__ inline int st_nblk(int h, int delta_x) { return h > 1 ? (h - 1 + st_rows(delta_x) - 1) / st_rows(delta_x) : 0; }
@@ -50,7 +51,7 @@ __device__ __forceinline__ int *st_part_x(const DevP &p, int nblk) { return rein
 static inline size_t st_jump_smem(int delta_x)
 {
     const int D = delta_x ? delta_x : 1, R = st_rows(delta_x);
-    return (size_t) R * (ST_COLS + 2 * R * D + 32) + 4 * (size_t) (ST_COLS + 6 * (R / 4) * D + 16);
+    return ST_PAD + (size_t) R * (ST_COLS + 2 * R * D + 32) + 4 * (size_t) (ST_COLS + 6 * (R / 4) * D + 16);
 }
 static inline size_t st_chase_smem() { return (size_t) ST_CHASE_DYN + (4 * ST_MAXBLK + 4) * 4 + (ST_MAXBLK + 1) * 4 * 3 + 512; }
 
@@ -110,9 +111,12 @@ __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, cons
     const int tlo = max(c0 - reach, 0) & ~15;                         // first staged column (16-byte aligned)
     const int thi = min((c0 + ST_COLS + reach + 15) & ~15, p.pitch);  // one past the last
     const int tw = thi - tlo, pieces = tw >> 4;
-    for (int i = tid; i < rows * pieces; i += ST_THREADS) {
-        const int r = i / pieces, c = (i - r * pieces) << 4;
-        st_cp16(st_smem + (size_t) r * tw + c, p.pdx + (size_t) (ybot - r) * p.pitch + tlo + c);
+    // the tile sits ST_PAD bytes into the buffer: a walk that meets a dead parent (offset -128) goes on from a column that
+    // does not matter, possibly left of the tile, before it is flagged
+    unsigned char *tile = st_smem + ST_PAD;
+    for (int r = tid >> 5; r < rows; r += ST_THREADS / 32) { // a warp per row: no index arithmetic per piece
+        const signed char *src = p.pdx + (size_t) (ybot - r) * p.pitch + tlo;
+        for (int c = tid & 31; c < pieces; c += 32) st_cp16(tile + (size_t) r * tw + (c << 4), src + (c << 4));
     }
     const int x = c0 + tid;
     // the bottom block's CTAs: arg-min of their columns of the last row (the rule of last_row_argmin)
@@ -139,30 +143,45 @@ __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, cons
         st_part_x(p, nblk)[blockIdx.x] = ax;
     }
 
-    const signed char *t = reinterpret_cast<const signed char *>(st_smem);
+    const signed char *t = reinterpret_cast<const signed char *>(tile);
     const int Wj = ST_COLS + 6 * q * D + 16, jbase = c0 - 3 * q * D; // sub-block jumps of the columns a composition can reach
-    signed char *j8s = reinterpret_cast<signed char *>(st_smem) + (size_t) R * tw;
-    // the four sub-blocks from this thread's own column: four independent chains
-    int xs[4], own[4];
-    bool bd[4];
+    signed char *j8s = reinterpret_cast<signed char *>(tile) + (size_t) R * tw;
+    // The four sub-blocks from this thread's own column: four independent chains.  A step is one shared-memory load and
+    // one add: the tile index moves on by a row plus the parent offset, the minimum of the offsets seen tells afterwards
+    // whether a dead parent (B200C_PDX_NONE = -128, smaller than any live offset) was among them.
+    int own[4] = {0, 0, 0, 0};
+    if (x < p.w) {
+        int a[4], mn[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) xs[j] = min(x - tlo, tw - 1), bd[j] = false;
-    for (int sidx = 0; sidx < q; ++sidx) {
+        for (int j = 0; j < 4; ++j) a[j] = j * q * tw + (x - tlo), mn[j] = 0;
+        if (rows == R) {
+            for (int sidx = 0; sidx < q; ++sidx) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int d = t[a[j]];
+                    a[j] += tw + d;
+                    mn[j] = min(mn[j], d);
+                }
+            }
+        } else {
+            for (int sidx = 0; sidx < q; ++sidx) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (j * q + sidx < rows) {
+                        const int d = t[a[j]];
+                        a[j] += tw + d;
+                        mn[j] = min(mn[j], d);
+                    }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int r = j * q + sidx;
-            if (r < rows) {
-                const int d = t[r * tw + xs[j]];
-                bd[j] |= d == B200C_PDX_NONE;
-                xs[j] = min(max(xs[j] + (d == B200C_PDX_NONE ? 0 : d), 0), tw - 1);
-            }
+            const int n = min(max(rows - j * q, 0), q); // rows of sub-block j
+            own[j] = mn[j] == B200C_PDX_NONE ? ST_BAD : a[j] - (j * q + n) * tw - (x - tlo);
         }
     }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        own[j] = bd[j] ? ST_BAD : xs[j] + tlo - x;
-        j8s[j * Wj + (x - jbase)] = (signed char) own[j];
-    }
+    for (int j = 0; j < 4; ++j) j8s[j * Wj + (x - jbase)] = (signed char) own[j];
     // ... and from the halo columns: sub-block j can be entered j q D columns either side of the CTA's own columns
     const int qd = q * D;
     for (int i = tid; i < 12 * qd; i += ST_THREADS) {
@@ -170,15 +189,14 @@ __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, cons
         const int o = i - (j == 1 ? 0 : (j == 2 ? 2 * qd : 6 * qd));
         const int col = o < j * qd ? c0 - j * qd + o : c0 + ST_COLS + (o - j * qd);
         if (col < 0 || col >= p.w) continue;
-        int xx = col - tlo;
-        bool bad = false;
-        const int r1 = min(j * q + q, rows);
-        for (int r = j * q; r < r1; ++r) {
-            const int d = t[r * tw + xx];
-            bad |= d == B200C_PDX_NONE;
-            xx = min(max(xx + (d == B200C_PDX_NONE ? 0 : d), 0), tw - 1);
+        const int n = min(max(rows - j * q, 0), q);
+        int a = j * q * tw + (col - tlo), mn = 0;
+        for (int r = 0; r < n; ++r) {
+            const int d = t[a];
+            a += tw + d;
+            mn = min(mn, d);
         }
-        j8s[j * Wj + (col - jbase)] = (signed char) (bad ? ST_BAD : xx + tlo - col);
+        j8s[j * Wj + (col - jbase)] = (signed char) (mn == B200C_PDX_NONE ? ST_BAD : a - (j * q + n) * tw - (col - tlo));
     }
     __syncthreads();
     if (x >= p.w) return;
@@ -261,8 +279,8 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
     ST_MARK(1);
 
     // ---- the chase through the block jumps, a group of G blocks at a time
-    int G = 1;
-    while ((G + 1) * (G + 1) * reach + (G + 1) * 48 <= ST_CHASE_DYN && G < nblk) ++G;
+    int G = min(nblk, (int) sqrtf((float) ST_CHASE_DYN / (float) reach)); // G^2 reach + 48 G <= ST_CHASE_DYN
+    while (G > 1 && G * G * reach + G * 48 > ST_CHASE_DYN) --G;
     unsigned phase = 0;
     for (int b0 = 0; b0 < nblk; b0 += G, phase ^= 1) {
         const int g = min(G, nblk - b0), xg = ent[b0];
@@ -292,6 +310,7 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
             st_bulk(stage + off, p.jump + (size_t) (b0 + tid) * p.pitch + a, (unsigned) wdt, &mbar);
         }
         __syncthreads();
+        ST_MARK(6);
         if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(st_saddr(&mbar)), "r"((unsigned) s_tot) : "memory");
         if (!st_mbar_wait(&mbar, phase) && tid == 0) atomicOr(p.err, 8);
         ST_MARK(2);
