@@ -547,7 +547,7 @@ int alloc_maps(B200Carver *c)
 int init_energy_related(B200Carver *c)
 {
     if (c->active || c->nrg_active) return fail(B200C_ERROR, "init_energy_related: already initialised");
-    B_TRY(dalloc(c, &c->raw, (size_t) c->w_start * c->h_start, false));
+    B_TRY(dalloc(c, &c->raw, (size_t) c->w_start * c->h_start + 16, false)); // slack: 16-byte accesses at the end of the last row
     B_TRY(init_raw(c));
     c->nrg_active = true;
     return alloc_maps(c);
@@ -601,6 +601,7 @@ int raise_smem_limits(const B200Carver *c)
         err = cudaSetDevice(device);
         if (err == cudaSuccess) err = cudaFuncSetAttribute((const void *) k_seam_path, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sp_smem_bytes());
         if (err == cudaSuccess) err = cudaFuncSetAttribute((const void *) k_seam_chase, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) st_chase_smem());
+        if (err == cudaSuccess) err = cudaFuncSetAttribute((const void *) k_carve_row, cudaFuncAttributeMaxDynamicSharedMemorySize, B200C_CARVE_ROW_SMEM_MAX);
         done.emplace(key0, err);
     }
     if (done[key0] != cudaSuccess) return fail(B200C_ERROR, "cudaFuncSetAttribute(max dynamic shared memory)", done[key0]);
@@ -844,6 +845,19 @@ struct SeamLaunch {
 };
 constexpr int kSeamLaunchMax = 10;
 
+// the whole-row carve: the one-pass kernel that stages the row in shared memory, unless the row does not fit (images
+// wider than ~15000 columns) or the plain kernels were asked for (B200C_GENERIC=1)
+const void *carve_row_fn(const B200Carver *c, size_t *smem)
+{
+    const size_t need = carve_row_smem(c->pitch, c->rig != nullptr);
+    if (fast_path(c) && need <= B200C_CARVE_ROW_SMEM_MAX) {
+        *smem = need;
+        return (const void *) k_carve_row;
+    }
+    *smem = 0;
+    return (const void *) k_carve;
+}
+
 // the backtrack: jump tables over all SMs + a short chase (seam_trace.cuh); the single-CTA staged chase for delta_x > 4;
 // the plain walk with B200C_GENERIC=1
 int vpath_launch_list(const B200Carver *c, SeamLaunch out[kSeamLaunchMax])
@@ -873,7 +887,9 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
         out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false, 1};
         out[n++] = {"carve_far", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false, 2};
     } else {
-        out[n++] = {"carve", (const void *) k_carve, dim3(c->h), dim3(B200C_CARVE_THREADS), 0, 1, false};
+        size_t smem = 0;
+        const void *fn = carve_row_fn(c, &smem);
+        out[n++] = {"carve", fn, dim3(c->h), dim3(B200C_CARVE_THREADS), smem, 1, false};
     }
     out[n++] = {"energy_band", (const void *) k_energy_band, dim3((c->h + B200C_EB_ROWS - 1) / B200C_EB_ROWS), dim3(256), 0, 0, false};
     if (near_at >= 0) out[n - 1].dep = near_at; // beside the FAR phase
@@ -1006,8 +1022,14 @@ int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
             if (e != cudaSuccess) return fail(B200C_ERROR, L[i].stage, e);
         }
         StageScope sc2("carve", s);
-        k_carve<<<dim3(c->h, 1, batch_n(c)), B200C_CARVE_THREADS, 0, s>>>(view_dyn(c), c->vs_epoch, 0, tab_dyn(c));
-        B_TRY(check_launch("k_carve"));
+        size_t smem = 0;
+        const void *fn = carve_row_fn(c, &smem);
+        DevP v = view_dyn(c);
+        int vs0 = c->vs_epoch, ph = 0;
+        const DevP *tb = tab_dyn(c);
+        void *args[] = {&v, &vs0, &ph, &tb};
+        const cudaError_t e = cudaLaunchKernel(fn, dim3(c->h, 1, batch_n(c)), dim3(B200C_CARVE_THREADS), args, smem, s);
+        if (e != cudaSuccess) return fail(B200C_ERROR, "k_carve", e);
     } else if (lr_switch || !c->use_graph || g_timing) {
         B_TRY(launch_seam_kernels(c, !lr_switch));
     } else {
@@ -1203,7 +1225,7 @@ int flatten(B200Carver *c)
     c->max_level = 1;
     if (c->nrg_active) {
         dfree(c, c->raw);
-        B_TRY(dalloc(c, &c->raw, n, false));
+        B_TRY(dalloc(c, &c->raw, n + 16, false)); // slack: see alloc of raw in carver_init
         B_TRY(init_raw(c));
     }
     B_TRY(alloc_maps(c));
@@ -1274,7 +1296,7 @@ int transpose(B200Carver *c)
 
     if (c->nrg_active) {
         dfree(c, c->raw);
-        B_TRY(dalloc(c, &c->raw, n, false));
+        B_TRY(dalloc(c, &c->raw, n + 16, false)); // slack: see alloc of raw in carver_init
         B_TRY(init_raw(c));
     }
     B_TRY(alloc_maps(c));

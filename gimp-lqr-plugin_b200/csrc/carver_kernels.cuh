@@ -540,6 +540,138 @@ __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, 
     }
 }
 
+// The whole-row carve of the per-seam loop: the same result as k_carve phase 0, one CTA per row, in ONE pass: the part of
+// the row from the seam on (from column base = (s - delta_x - 1) & ~15) is fetched into shared memory by bulk copies
+// (TMA: one per map, issued by one thread, no register parking, the whole row in flight), and once they have landed the
+// threads write the shifted row back with 16-byte stores.  A thread owns groups of four consecutive NEW columns
+// [xn0, xn0 + 4), xn0 a multiple of 4 (the rows of en / m / rig / pdx are 16-byte aligned).  Cells left of the seam
+// inside the first groups are written back as they were.  Nothing is stored before everything is loaded, so the in-place
+// shift needs no ordering between the threads.  The index table's rows (stride w_start, no padding) are fetched by a
+// bulk copy when they are 16-byte aligned, by ordinary loads otherwise.
+__host__ __device__ inline size_t carve_row_smem(int pitch, bool rig) { return (size_t) (pitch + 16) * (rig ? 17 : 13) + 64; }
+#define B200C_CARVE_ROW_SMEM_MAX (200 * 1024)
+
+__device__ __forceinline__ unsigned cv_saddr(const void *q) { return (unsigned) __cvta_generic_to_shared(q); }
+__device__ __forceinline__ void cv_bulk(void *dst_smem, const void *src, unsigned bytes, void *mbar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cv_saddr(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(cv_saddr(mbar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve_row(const DevP pin0, int vs_value, int /*phase*/, const DevP *tab)
+{
+    const DevP pin = pick_image(pin0, tab);
+    int seam;
+    const DevP p = seam_view(pin, 1, &seam);
+    vs_value += seam; // the level this seam's pixels get in the visibility map
+    extern __shared__ __align__(16) unsigned char cv_smem[];
+    __shared__ __align__(8) unsigned long long mbar;
+    const int y = blockIdx.x, tid = threadIdx.x;
+    const size_t o = (size_t) y * p.pitch;
+    int *raw = p.raw + (size_t) y * p.raw_stride;
+    float *en = p.en + o, *m = p.m + o, *rig = p.rig ? p.rig + o : nullptr;
+    int8_t *pdx = p.pdx + o;
+    const int s = p.vpath_x[y];
+    const int sp = y > 0 ? p.vpath_x[y - 1] : INT_MIN;
+    const int start = max(s - p.delta_x - 1, 0); // cells left of the seam stay put but may see their parent move
+    const int base = start & ~15;
+    const int n = p.pitch - base;                // staged columns: a multiple of 16
+    const int nraw = min(n, (p.w + 1 - base + 3) & ~3); // the index table's row has p.w + 1 entries
+    const int cap = p.pitch + 16;
+    float *se = reinterpret_cast<float *>(cv_smem), *sm = se + cap, *sg = sm + cap;
+    int *sr = reinterpret_cast<int *>(rig ? sg + cap : sg);
+    unsigned char *sd = reinterpret_cast<unsigned char *>(sr + cap);
+    const bool raw_bulk = ((reinterpret_cast<size_t>(raw + base) & 15) == 0);
+    const float inf = __int_as_float(0x7f800000);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(cv_saddr(&mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned) n * (rig ? 12u : 8u) + (y > 0 ? (unsigned) n : 0u) + (raw_bulk ? (unsigned) nraw * 4u : 0u);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cv_saddr(&mbar)), "r"(bytes) : "memory");
+        cv_bulk(se, en + base, (unsigned) n * 4u, &mbar);
+        cv_bulk(sm, m + base, (unsigned) n * 4u, &mbar);
+        if (rig) cv_bulk(sg, rig + base, (unsigned) n * 4u, &mbar);
+        if (y > 0) cv_bulk(sd, pdx + base, (unsigned) n, &mbar);
+        if (raw_bulk) cv_bulk(sr, raw + base, (unsigned) nraw * 4u, &mbar);
+        p.vs[raw[s]] = vs_value; // read before anything is stored
+    }
+    if (!raw_bulk)
+        for (int i = tid; i < p.w + 1 - base; i += B200C_CARVE_THREADS) sr[i] = raw[base + i];
+    __syncthreads(); // the barrier is initialised; the index table is staged
+    {
+        unsigned ok = 0;
+        unsigned long long t0 = 0;
+        for (unsigned tries = 0; !ok; ++tries) {
+            asm volatile("{\n.reg .pred q;\nmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\nselp.u32 %0, 1, 0, q;\n}\n"
+                         : "=r"(ok)
+                         : "r"(cv_saddr(&mbar))
+                         : "memory");
+            if (!ok && (tries & 1023u) == 1023u) { // a copy that never lands is a bug, not a reason to hang the GPU
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                if (t0 == 0) t0 = t;
+                else if (t - t0 > 2000000000ull) {
+                    if (tid == 0) atomicOr(p.err, 8);
+                    return;
+                }
+            }
+        }
+    }
+    const int ngroups = (p.w - base + 3) >> 2; // groups with at least one column of the image
+    for (int g = tid; g < ngroups; g += B200C_CARVE_THREADS) {
+        const int k = 4 * g, xn0 = base + k;
+        const float4 e4 = *reinterpret_cast<const float4 *>(se + k), m4 = *reinterpret_cast<const float4 *>(sm + k);
+        const float4 g4 = rig ? *reinterpret_cast<const float4 *>(sg + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const int4 r4 = *reinterpret_cast<const int4 *>(sr + k);
+        const unsigned d4 = *reinterpret_cast<const unsigned *>(sd + k);
+        // the first cell of the next group (past the staged columns only when no cell of this group moves)
+        const float oe[5] = {e4.x, e4.y, e4.z, e4.w, se[k + 4]}, om[5] = {m4.x, m4.y, m4.z, m4.w, sm[k + 4]};
+        const float og[5] = {g4.x, g4.y, g4.z, g4.w, rig ? sg[k + 4] : 0.f};
+        const int orw[5] = {r4.x, r4.y, r4.z, r4.w, sr[k + 4]};
+        const unsigned d5 = sd[k + 4];
+        float xe[4], xm[4], xg[4];
+        int xr[4];
+        unsigned pk = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int xn = xn0 + i;
+            const bool moved = xn >= s && xn < p.w; // takes the value of the cell right of it
+            xr[i] = moved ? orw[i + 1] : orw[i];
+            xg[i] = moved ? og[i + 1] : og[i];
+            xe[i] = xn >= p.w ? inf : (moved ? oe[i + 1] : oe[i]); // the vacated column joins the +inf sentinels
+            xm[i] = xn >= p.w ? inf : (moved ? om[i + 1] : om[i]);
+            const int dsame = (int) (signed char) (d4 >> (8 * i));
+            const int dnext = (int) (signed char) (i < 3 ? (d4 >> (8 * i + 8)) : d5);
+            int dn = dsame; // cells left of `start` or past the image keep their byte
+            if (xn >= start && xn < p.w) {
+                const int xo = xn + (xn >= s), d = xn >= s ? dnext : dsame;
+                const int xp = xo + d; // old column of the parent in the upper row
+                dn = (d != B200C_PDX_NONE && xp != sp) ? (xp - (xp > sp)) - xn : B200C_PDX_NONE;
+            }
+            pk |= ((unsigned) dn & 0xffu) << (8 * i);
+        }
+        *reinterpret_cast<float4 *>(en + xn0) = make_float4(xe[0], xe[1], xe[2], xe[3]);
+        *reinterpret_cast<float4 *>(m + xn0) = make_float4(xm[0], xm[1], xm[2], xm[3]);
+        if (rig) *reinterpret_cast<float4 *>(rig + xn0) = make_float4(xg[0], xg[1], xg[2], xg[3]);
+        if (y > 0) *reinterpret_cast<unsigned *>(pdx + xn0) = pk;
+        if (raw_bulk && xn0 + 3 <= p.w) {
+            *reinterpret_cast<int4 *>(raw + xn0) = make_int4(xr[0], xr[1], xr[2], xr[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (xn0 + i <= p.w) raw[xn0 + i] = xr[i];
+        }
+    }
+    if (tid == 0) {
+        if ((p.w & 3) == 0) en[p.w] = m[p.w] = inf; // the vacated column starts a group of its own: no thread wrote it
+        if (p.far) { // a whole-row launch counts as both phases of the split carve
+            __threadfence();
+            atomicAdd(p.far, 1);
+        }
+    }
+}
+
 // A.7 finish_vsmap: the image is one pixel wide; the survivors get the largest level.
 __global__ void k_finish_vsmap(const DevP pin0, const DevP *tab)
 {
