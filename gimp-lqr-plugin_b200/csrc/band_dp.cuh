@@ -222,11 +222,10 @@ __device__ __forceinline__ unsigned bd_eval(const float (&prev)[4], const float4
 // parent is unchanged -- stored, and row q+1 is evaluated again from the settled values.
 struct BdSlow {
     float mp[4], nv[4];            // out: the pending row settled, the row after it redone
-    const float *par;              // in: the pending row's parents (this lane's four cells, in the warp's value ring)
-    float *ring2, *ring3;          // out: where the two rows go in the ring (the fast loop re-enters after them)
+    const float *par;              // in: the pending row's parents (this lane's four cells: in the tile or the warp's value ring)
     const float *e, *o, *g;         // operands of the pending row in the tile (the next row's are BD_BW floats further)
     const unsigned char *pold;      // old parent offsets of the pending row (in the tile)
-    float *dst;                     // where the pending row is stored, or NULL
+    float *dst;                     // where the pending row is stored (tile or value ring)
     float leftfloor;
     const float *rigmap;
     unsigned key;                   // out: near key of the row after
@@ -267,8 +266,7 @@ __device__ __forceinline__ void bd_slow_row(BdSlow &c)
             out[i] = mo[i];
         c.mp[i] = out[i];
     }
-    if (c.dst) *reinterpret_cast<float4 *>(c.dst) = make_float4(out[0], out[1], out[2], out[3]);
-    *reinterpret_cast<float4 *>(c.ring2) = make_float4(out[0], out[1], out[2], out[3]);
+    *reinterpret_cast<float4 *>(c.dst) = make_float4(out[0], out[1], out[2], out[3]);
     if (c.has_next) {
         float nv[4];
         c.key = bd_eval<D, RIG>(out, *reinterpret_cast<const float4 *>(c.e + BD_BW), *reinterpret_cast<const float4 *>(c.o + BD_BW),
@@ -276,7 +274,6 @@ __device__ __forceinline__ void bd_slow_row(BdSlow &c)
                                 c.leftfloor, nv);
 #pragma unroll
         for (int i = 0; i < 4; ++i) c.nv[i] = nv[i];
-        *reinterpret_cast<float4 *>(c.ring3) = make_float4(nv[0], nv[1], nv[2], nv[3]);
     }
 }
 
@@ -304,9 +301,11 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
 
     bd_bar_chunk(); // chunk 0 is planned and has landed
+    long long t_start = 0, t_gap = 0, t_prev = 0;
+    if (BD_PROF && p.dbg) t_prev = clock64(), t_start = t_prev - t_all;
     for (int k = 0;; ++k) {
         long long tp0 = 0;
-        if (BD_PROF && p.dbg) tp0 = clock64();
+        if (BD_PROF && p.dbg) tp0 = clock64(), t_gap += tp0 - t_prev;
         if (*ready < k) { // normally false: see the producer
             while (*ready < k) {}
             __threadfence_block();
@@ -364,21 +363,24 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             // out-of-line slow path settles row r-1 with the full rule -- its operands are still in the tile, its
             // parents (row r-2) in the warp's value ring, its old parent offsets in the tile as well -- and
             // redoes row r.
-            // The values of the last rows live in a per-warp ring in shared memory (slot = row index relative to the
-            // loop entry, mod 4; slots 3 and 2 hold the two rows before the entry), so that leaving the fast loop for
-            // the slow path needs no register state beyond the row counter: the unrolled fast rows stay free of moves.
+            // Every row is stored ONCE, one row late -- when the vote has confirmed it -- by one 16-byte store per lane:
+            // the lanes that own their columns (st) write into the tile, over the old values of the same cells (the
+            // producer writes the boxes back to HBM with bulk tensor stores after the chunk barrier: no global store on
+            // the chain); the other lanes (halo columns, whose values still feed their neighbours' shuffles) into a
+            // per-warp ring of four rows (slot = row index relative to the loop entry, mod 4).  Either way the values
+            // of the rows up to r-2 are in shared memory when the loop is left at row r, so the slow path needs no
+            // register state beyond the row counter and the unrolled fast rows stay free of moves.
             float *vr = vring + 4 * lane; // [4][128] per warp
             bool pend = false;            // row r-1 has a near cell in this lane
             int r0 = r;                   // entry row of the fast loop
-            *reinterpret_cast<float4 *>(vr + 3 * 128) = make_float4(mp[0], mp[1], mp[2], mp[3]);
             unsigned key = 0xffffffffu;
-            auto slow = [&](int q, bool has_next) { // settles row q, redoes row q+1 (-> mp), re-bases the ring after them
+            auto slow = [&](int q, bool has_next) { // settles row q (stored), redoes row q+1 (-> mp, stored once confirmed)
                 BdSlow c;
-                c.par = vr + ((q - 1 - r0) & 3) * 128;
-                c.ring2 = vr + 2 * 128, c.ring3 = vr + 3 * 128;
+                c.par = st ? op + (q - 1) * BD_BW : vr + ((q - 1 - r0) & 3) * 128;
                 c.e = ep + q * BD_BW, c.o = op + q * BD_BW, c.g = gq + q * BD_BW;
                 c.pold = pp + q * BD_BW;
-                c.dst = st ? op + q * BD_BW : nullptr; // over the row's old values, which this call reads first
+                // over the row's old values, which the call reads first / slot 2 of the ring as re-based after the call
+                c.dst = st ? op + q * BD_BW : vr + 2 * 128;
                 c.leftfloor = leftfloor;
                 c.rigmap = p.rigmap;
                 c.has_next = has_next;
@@ -393,11 +395,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             // fetched first thing here (past the last row of the chunk that reads the neighbouring box of the ring and
             // is never used), so the chain never waits for shared memory.
             float4 ce = ld4(ep + r * BD_BW), co = ld4(op + r * BD_BW), cg = RIG ? ld4(gq + r * BD_BW) : one4;
-            // Results go back into the tile, over the old values of the same cells, one row LATE -- when the vote has
-            // confirmed the row (the slow path still needs a pending row's old values) -- and only from the lanes that own
-            // the columns (st): everything else in the tile keeps the values it was fetched with.  After the chunk barrier
-            // the producer writes the boxes back to HBM with bulk tensor stores: no global store on the chain.
-            auto fast_row = [&](const float *e_next, const float *o_next, const float *g_next, int slot) -> bool {
+            auto fast_row = [&](const float *e_next, const float *o_next, const float *g_next, int slot_prev) -> bool {
                 const float4 ne = ld4(e_next), no = ld4(o_next), ng = RIG ? ld4(g_next) : one4;
                 float nv[4];
                 key = bd_eval<D, RIG>(mp, ce, co, cg, rmap, leftfloor, nv);
@@ -408,12 +406,9 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 pend = false; // timing experiment only: never leave the fast loop (results are wrong)
 #endif
                 if (__any_sync(full, pend)) return true;
-#ifndef BD_EXP_NO_STORE
-                if (st) *reinterpret_cast<float4 *>(const_cast<float *>(o_next) - 2 * BD_BW) = make_float4(mp[0], mp[1], mp[2], mp[3]);
-#endif
-#ifndef BD_EXP_NO_VRING
-                *reinterpret_cast<float4 *>(vr + slot * 128) = make_float4(nv[0], nv[1], nv[2], nv[3]);
-#endif
+                // row r-1 is confirmed: o_next is row r+1 of the tile
+                float *dst = st ? const_cast<float *>(o_next) - 2 * BD_BW : vr + slot_prev * 128;
+                *reinterpret_cast<float4 *>(dst) = make_float4(mp[0], mp[1], mp[2], mp[3]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) mp[i] = nv[i];
                 ce = ne, co = no, cg = ng;
@@ -424,14 +419,14 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 bool hit = false;
                 for (; r + 4 <= rows; r += 4) { // (r - r0) is a multiple of 4 here: the slots are compile-time constants
                     const float *e0 = ep + (r + 1) * BD_BW, *o0 = op + (r + 1) * BD_BW, *g0 = gq + (r + 1) * BD_BW;
-                    if (fast_row(e0, o0, g0, 0)) { hit = true; break; }
-                    if (fast_row(e0 + BD_BW, o0 + BD_BW, g0 + BD_BW, 1)) { r += 1; hit = true; break; }
-                    if (fast_row(e0 + 2 * BD_BW, o0 + 2 * BD_BW, g0 + 2 * BD_BW, 2)) { r += 2; hit = true; break; }
-                    if (fast_row(e0 + 3 * BD_BW, o0 + 3 * BD_BW, g0 + 3 * BD_BW, 3)) { r += 3; hit = true; break; }
+                    if (fast_row(e0, o0, g0, 3)) { hit = true; break; }
+                    if (fast_row(e0 + BD_BW, o0 + BD_BW, g0 + BD_BW, 0)) { r += 1; hit = true; break; }
+                    if (fast_row(e0 + 2 * BD_BW, o0 + 2 * BD_BW, g0 + 2 * BD_BW, 1)) { r += 2; hit = true; break; }
+                    if (fast_row(e0 + 3 * BD_BW, o0 + 3 * BD_BW, g0 + 3 * BD_BW, 2)) { r += 3; hit = true; break; }
                 }
                 if (!hit)
                     for (; r < rows; ++r)
-                        if (fast_row(ep + (r + 1) * BD_BW, op + (r + 1) * BD_BW, gq + (r + 1) * BD_BW, (r - r0) & 3)) { hit = true; break; }
+                        if (fast_row(ep + (r + 1) * BD_BW, op + (r + 1) * BD_BW, gq + (r + 1) * BD_BW, (r - 1 - r0) & 3)) { hit = true; break; }
                 if (!hit) break;
                 slow(r - 1, true); // row r-1 settled (and stored), row r redone from it; it is stored once confirmed
                 pend = key <= BD_NEAR_MAX;
@@ -467,7 +462,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
         if (BD_PROF && p.dbg) t1 = clock64();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // the tile rows written above, for the bulk stores
         bd_bar_chunk();
-        if (BD_PROF && p.dbg) t_bar += clock64() - t1;
+        if (BD_PROF && p.dbg) t_prev = clock64(), t_bar += t_prev - t1;
         hl_lo = d.hlo;
         hl_hi = d.hhi;
     }
@@ -480,6 +475,8 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             atomicAdd((unsigned long long *) &p.dbg[6], (unsigned long long) (clock64() - t_all));
             atomicAdd((unsigned long long *) &p.dbg[7], (unsigned long long) n_rows);
             atomicAdd((unsigned long long *) &p.dbg[10], (unsigned long long) n_slow);
+            atomicAdd((unsigned long long *) &p.dbg[13], (unsigned long long) t_start);
+            atomicAdd((unsigned long long *) &p.dbg[15], (unsigned long long) t_gap);
         } else {
             atomicAdd((unsigned long long *) &p.dbg[8], (unsigned long long) n_rows);
             atomicAdd((unsigned long long *) &p.dbg[11], (unsigned long long) n_slow);
@@ -529,6 +526,17 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         __threadfence();
         far_done = true;
     };
+    // The write-back of a finished chunk (bulk tensor stores out of its boxes) is only waited for when the ring runs out
+    // of boxes: planning the next chunk and fetching it into free boxes goes on while the copies read.
+    int store_nb = 0; // boxes of the chunk whose stores are in flight
+    auto reclaim = [&]() {
+        if (store_nb) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
+            slots_free += store_nb;
+            store_nb = 0;
+        }
+    };
     // plans chunk kp and issues its tiles; false when it has to wait for ring space
     auto plan_issue = [&]() -> bool {
         const long long tp0 = (BD_PROF && p.dbg) ? clock64() : 0;
@@ -565,7 +573,10 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             // too wide for the tiled path: the tail kernel / the exact generic loop takes over at row ya
             if (nseg > min(BD_NCW, p.bd_maxseg) || nb > SL::nslot) end_y = ya;
         }
-        if (end_y < 0 && nb > slots_free) return false;
+        if (end_y < 0 && nb > slots_free) {
+            reclaim(); // the boxes of the chunk that is being written back, once the copies have read them
+            if (nb > slots_free) return false;
+        }
         if (end_y < 0 && !far_done) {
             int cmin = INT_MAX; // leftmost energy-band start of the rows the tiles cover (incl. the row above the chunk)
             for (int j = max(ya - 1, 0) + lane; j <= ya + rows - 1; j += 32) cmin = min(cmin, (int) (nrg[j] & 0xffffffu));
@@ -634,7 +645,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         if (!plan_issue()) break;
     publish_ready(0), ready = 0;
     bd_bar_chunk();
-    long long t_tiles = 0;
+    long long t_tiles = 0, t_pbar = 0, t_pstore = 0;
     for (int k = 0;; ++k) {
         // a chunk that did not fit before the last barrier is planned now that its predecessor's slots are free: the
         // compute warps are waiting for it
@@ -657,18 +668,27 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             if (kp >= k + 2) publish_ready(k + 1), ready = k + 1;
             if (BD_PROF && p.dbg) t_tiles += clock64() - tw0;
         }
+        const long long tb0 = (BD_PROF && p.dbg) ? clock64() : 0;
         bd_bar_chunk(); // end of chunk k: the hull of its last row is known, its new values are in the tiles
+        if (BD_PROF && p.dbg) { // the barrier instruction does not hold back a clock read: read the clock after a load
+            const int probe = *reinterpret_cast<const volatile int *>(hull);
+            long long tb1 = clock64();
+            if (probe == 0x7ffffff1) tb1 = 0;
+            t_pbar += tb1 - tb0;
+        }
+        const long long ts0 = (BD_PROF && p.dbg) ? clock64() : 0;
         // write chunk k's boxes back (rows 0 .. K-1 of every m box; rows past the image are clipped by the tensor map),
         // and let the copies READ the slots before these are handed to a later chunk's loads
+        reclaim(); // (the previous chunk's, if nobody needed its boxes in the meantime)
         if (lane < nb_k) {
             int slot = dk->slot0 + lane;
             if (slot >= SL::nslot) slot -= SL::nslot;
             bd_tma_store_2d(&tm.mst, dk->llo + lane * BD_BW, y0_k, ring + (size_t) slot * SL::bytes + BD_BW * 4);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncwarp();
-        slots_free += nb_k;
+        store_nb = nb_k;
+        if (BD_PROF && p.dbg) t_pstore += clock64() - ts0;
         const int *hull_k = hull + (k & 1) * (2 * BD_NCW);
         int lo = lane < BD_NCW ? hull_k[2 * lane] : INT_MAX;
         int hi = lane < BD_NCW ? hull_k[2 * lane + 1] : INT_MIN;
@@ -676,7 +696,11 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
         hhi = __reduce_max_sync(full, hi);
         yl = y0_k + rows_k - 1;
     }
-    if (BD_PROF && p.dbg && lane == 0) atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) t_tiles);
+    if (BD_PROF && p.dbg && lane == 0) {
+        atomicAdd((unsigned long long *) &p.dbg[12], (unsigned long long) t_tiles);
+        atomicAdd((unsigned long long *) &p.dbg[24], (unsigned long long) t_pbar);
+        atomicAdd((unsigned long long *) &p.dbg[25], (unsigned long long) t_pstore);
+    }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // every store has landed before the kernel goes on / ends
     asm volatile("fence.proxy.async;" ::: "memory");
     __threadfence();
