@@ -128,26 +128,26 @@ __device__ __forceinline__ double px_scalar(const DevP &p, int z, const double *
 
 // A.3 energy of the pixel at current coordinates (x, y): central differences over the four nearest
 // neighbours in the CURRENT image (through the raw index table), one-sided at the borders.
-__device__ __forceinline__ float energy_at(const DevP &p, int x, int y)
+__device__ __forceinline__ float energy_at(const DevP &p, int x, int y, const double *t255 = nullptr)
 {
     const int *row = p.raw + (size_t) y * p.raw_stride;
     const int z = row[x];
     float e = 0.f;
     if (p.grad_kind != GRAD_NULL) {
-        const double b = px_scalar(p, z);
+        const double b = px_scalar(p, z, t255);
         double gx, gy;
         if (y == 0)
-            gy = __dsub_rn(p.h > 1 ? px_scalar(p, row[p.raw_stride + x]) : 0.0, b);
+            gy = __dsub_rn(p.h > 1 ? px_scalar(p, row[p.raw_stride + x], t255) : 0.0, b);
         else if (y < p.h - 1)
-            gy = __dmul_rn(__dsub_rn(px_scalar(p, row[p.raw_stride + x]), px_scalar(p, row[x - p.raw_stride])), 0.5);
+            gy = __dmul_rn(__dsub_rn(px_scalar(p, row[p.raw_stride + x], t255), px_scalar(p, row[x - p.raw_stride], t255)), 0.5);
         else
-            gy = __dsub_rn(b, px_scalar(p, row[x - p.raw_stride]));
+            gy = __dsub_rn(b, px_scalar(p, row[x - p.raw_stride], t255));
         if (x == 0)
-            gx = __dsub_rn(p.w > 1 ? px_scalar(p, row[x + 1]) : 0.0, b);
+            gx = __dsub_rn(p.w > 1 ? px_scalar(p, row[x + 1], t255) : 0.0, b);
         else if (x < p.w - 1)
-            gx = __dmul_rn(__dsub_rn(px_scalar(p, row[x + 1]), px_scalar(p, row[x - 1])), 0.5);
+            gx = __dmul_rn(__dsub_rn(px_scalar(p, row[x + 1], t255), px_scalar(p, row[x - 1], t255)), 0.5);
         else
-            gx = __dsub_rn(b, px_scalar(p, row[x - 1]));
+            gx = __dsub_rn(b, px_scalar(p, row[x - 1], t255));
         if (p.grad_kind == GRAD_NORM)
             e = (float) sqrt(__dadd_rn(__dmul_rn(gx, gx), __dmul_rn(gy, gy)));
         else if (p.grad_kind == GRAD_SUMABS)
@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP
 {
     const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
+    __shared__ double t255[256]; // v / 255.0, each quotient divided once per CTA (a cell reads 5 pixels x 4 channels)
+    t255[threadIdx.x] = (double) threadIdx.x / 255.0;
+    __syncthreads();
     const int sub = threadIdx.x & 7;
     const int y = blockIdx.x * B200C_EB_ROWS + (threadIdx.x >> 3);
     if (y >= p.h) return;
@@ -310,7 +313,7 @@ __global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP
         p.nrg_xmax[y] = xmax;
         p.nrg_pack[y] = ((unsigned) xmin & 0xffffffu) | ((unsigned) max(xmax - xmin + 1, 0) << 24);
     }
-    for (int x = xmin + sub; x <= xmax; x += 8) p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y);
+    for (int x = xmin + sub; x <= xmax; x += 8) p.en[(size_t) y * p.pitch + x] = energy_at(p, x, y, t255);
 }
 
 // K2 (generic) -- A.5 full m-map DP (lqr_carver_build_mmap): one CTA walks the rows, the row is spread
