@@ -150,6 +150,32 @@ __global__ void __launch_bounds__(1024, 1) k_tiles(const signed char *pdx, const
     sink[tid] = stage[(tid * 131) % (NROW * R * twf)];
 }
 
+// the row walk of k_seam_chase: 272 threads, 8 dependent one-byte loads each, rows PITCH apart, data last touched by a
+// grid-wide read (as k_seam_jumps leaves it) or written by a grid-wide kernel
+__global__ void k_touch(const signed char *a, size_t n, int *sink)
+{
+    int acc = 0;
+    for (size_t i = (blockIdx.x * (size_t) blockDim.x + threadIdx.x) * 16; i < n; i += (size_t) gridDim.x * blockDim.x * 16)
+        acc += __ldcg(reinterpret_cast<const int4 *>(a + i)).x;
+    if (acc == 0x12345678) sink[0] = acc;
+}
+__global__ void __launch_bounds__(1024, 1) k_walk(const signed char *pdx, int steps, long long *cyc, int *out)
+{
+    const int tid = threadIdx.x;
+    __syncthreads();
+    const long long t0 = clock64();
+    if (tid < 272) {
+        int x = 1900 + (tid * 7) % 200, y = H - 1 - tid * 8;
+        for (int s = 0; s < steps && y - s >= 1; ++s) {
+            const int d = __ldcg(pdx + (size_t) (y - s) * PITCH + x);
+            x = min(max(x + d, 0), PITCH - 1);
+        }
+        out[tid] = x;
+    }
+    __syncthreads();
+    if (tid == 0) cyc[0] = clock64() - t0;
+}
+
 int main()
 {
     signed char *jump, *pdx;
@@ -180,6 +206,15 @@ int main()
             k_tiles<<<1, 1024, DYN>>>(pdx, ent, mode, cyc, sink);
             CHECK(cudaDeviceSynchronize());
             if (rep == 2) printf("tiles    %-30s: %6lld cycles for %d bytes\n", qn[mode], cyc[0], NROW * 32 * 80);
+        }
+    for (int mode = 0; mode < 2; ++mode)
+        for (int rep = 0; rep < 3; ++rep) {
+            k_fill<<<148 * 4, 256>>>(pdx, (size_t) PITCH * H);
+            if (mode == 1) k_touch<<<148 * 4, 256>>>(pdx, (size_t) PITCH * H, sink);
+            k_walk<<<1, 1024>>>(pdx, 8, cyc, sink);
+            CHECK(cudaDeviceSynchronize());
+            if (rep == 2) printf("walk 8 dependent byte loads x 272 threads, %s: %lld cycles (%lld per step)\n",
+                                 mode ? "after a grid-wide read " : "after a grid-wide write", cyc[0], cyc[0] / 8);
         }
     return 0;
 }
