@@ -159,9 +159,11 @@ __global__ void k_touch(const signed char *a, size_t n, int *sink)
         acc += __ldcg(reinterpret_cast<const int4 *>(a + i)).x;
     if (acc == 0x12345678) sink[0] = acc;
 }
-__global__ void __launch_bounds__(1024, 1) k_walk(const signed char *pdx, int steps, long long *cyc, int *out)
+// spread: walkers per warp (32: the 272 walkers fill 9 warps; 9: spread over all 32 warps; 1: one walker per warp)
+__global__ void __launch_bounds__(1024, 1) k_walk(const signed char *pdx, int steps, long long *cyc, int *out, int spread = 32)
 {
-    const int tid = threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int tid = spread == 32 ? (int) threadIdx.x : (lane < spread ? warp * spread + lane : 1 << 20);
     __syncthreads();
     const long long t0 = clock64();
     if (tid < 272) {
@@ -173,7 +175,7 @@ __global__ void __launch_bounds__(1024, 1) k_walk(const signed char *pdx, int st
         out[tid] = x;
     }
     __syncthreads();
-    if (tid == 0) cyc[0] = clock64() - t0;
+    if (threadIdx.x == 0) cyc[0] = clock64() - t0;
 }
 
 int main()
@@ -216,5 +218,14 @@ int main()
             if (rep == 2) printf("walk 8 dependent byte loads x 272 threads, %s: %lld cycles (%lld per step)\n",
                                  mode ? "after a grid-wide read " : "after a grid-wide write", cyc[0], cyc[0] / 8);
         }
+    for (int spread : {32, 9, 1}) {
+        for (int rep = 0; rep < 3; ++rep) {
+            k_fill<<<148 * 4, 256>>>(pdx, (size_t) PITCH * H);
+            k_touch<<<148 * 4, 256>>>(pdx, (size_t) PITCH * H, sink);
+            k_walk<<<1, 1024>>>(pdx, 8, cyc, sink, spread);
+            CHECK(cudaDeviceSynchronize());
+            if (rep == 2) printf("walk, %2d walkers per warp: %lld cycles (%lld per step)\n", spread, cyc[0], cyc[0] / 8);
+        }
+    }
     return 0;
 }
