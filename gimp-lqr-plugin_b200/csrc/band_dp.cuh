@@ -301,7 +301,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f);
 
     bd_bar_chunk(); // chunk 0 is planned and has landed
-    long long t_start = 0, t_gap = 0, t_prev = 0;
+    long long t_start = 0, t_gap = 0, t_prev = 0, t_pro1 = 0, t_epi1 = 0;
     if (BD_PROF && p.dbg) t_prev = clock64(), t_start = t_prev - t_all;
     for (int k = 0;; ++k) {
         long long tp0 = 0;
@@ -338,6 +338,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             const float *ep = reinterpret_cast<const float *>(sb + SL::off_e) + cc;   // en rows 0 .. K-1
             const float *gq = reinterpret_cast<const float *>(sb + SL::off_g) + cc;   // rigidity mask rows (RIG)
 
+            if (BD_PROF && p.dbg) t_pro1 += clock64() - tp0;
             if (d.y0 > 0) {
                 const float4 v = (x0 >= hl_lo && x0 < hl_hi) ? ld4(hand + ((k - 1) & 1) * BD_HANDW + (x0 - hl_lo)) : ld4(op);
                 mp[0] = v.x, mp[1] = v.y, mp[2] = v.z, mp[3] = v.w;
@@ -445,6 +446,7 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             // alone does not matter to the next row); po = the old values of the last row computed
             if (interior) *reinterpret_cast<float4 *>(hand + (k & 1) * BD_HANDW + (x0 - d.hlo)) = make_float4(mp[0], mp[1], mp[2], mp[3]);
             // the hull at lane granularity (4 cells): a superset of the changed cells, which is all the planner needs
+            if (BD_PROF && p.dbg) t_epi1 += clock64() - te0;
             bool chg = st;
             if (st && (rows > 1 || d.y0 > 0)) chg = mp[0] != po.x || mp[1] != po.y || mp[2] != po.z || mp[3] != po.w;
             const unsigned bal = __ballot_sync(full, chg);
@@ -476,6 +478,8 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
             atomicAdd((unsigned long long *) &p.dbg[7], (unsigned long long) n_rows);
             atomicAdd((unsigned long long *) &p.dbg[10], (unsigned long long) n_slow);
             atomicAdd((unsigned long long *) &p.dbg[13], (unsigned long long) t_start);
+            atomicAdd((unsigned long long *) &p.dbg[26], (unsigned long long) t_pro1);
+            atomicAdd((unsigned long long *) &p.dbg[27], (unsigned long long) t_epi1);
             atomicAdd((unsigned long long *) &p.dbg[15], (unsigned long long) t_gap);
         } else {
             atomicAdd((unsigned long long *) &p.dbg[8], (unsigned long long) n_rows);

@@ -183,6 +183,16 @@ def test_large_image_parity(product, oracle, w, h, seams):
     assert not diffs, "; ".join(diffs)
 
 
+@pytest.mark.parametrize("w,h,seams", [(17001, 24, 12), (9001, 40, 10)])
+def test_very_wide_rows_fall_back(product, oracle, w, h, seams):
+    """Rows wider than the one-pass carve can stage (~15 k columns) and than the jump kernel's 64 partial arg-mins
+    (16384 columns) take the plain carve and the single-CTA backtrack; rows wider than 8192 columns the strip launches of
+    the full DP.  Odd widths: the index table's rows are not 16-byte aligned."""
+    img = synth.smooth_noise(w, h, 4)
+    vals = V(new_width=w - seams, new_height=h, output_seams=True)
+    _assert_same(render.render_noninteractive(product, img, vals), render.render_noninteractive(oracle, img, vals))
+
+
 def _assert_same(got, want):
     diffs = cases.results_equal(got, want)
     assert not diffs, "; ".join(diffs)
