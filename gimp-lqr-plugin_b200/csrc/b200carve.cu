@@ -302,15 +302,47 @@ struct B200Carver {
 
     uint8_t *host_out = nullptr; // pinned read-out staging
     size_t host_out_cap = 0;
+    cudaMemPool_t pool = nullptr; // the engine's own device memory pool (engine_pool), or NULL: the default pool
 };
 
 namespace {
+
+// The engine allocates from a memory pool of its OWN per device (freed blocks stay in it: the per-resize maps are
+// reallocated at every inflate / flatten), so the host process's default pool and its release threshold are left alone.
+cudaMemPool_t engine_pool(int device)
+{
+    static std::mutex mu;
+    static std::map<int, cudaMemPool_t> pools;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = pools.find(device);
+    if (it != pools.end()) return it->second;
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    } else {
+        cudaGetLastError(); // no private pool: allocate from the device's default pool, untouched
+        pool = nullptr;
+    }
+    pools.emplace(device, pool);
+    return pool;
+}
+
+cudaError_t pool_alloc(const B200Carver *c, void **p, size_t bytes, cudaStream_t s)
+{
+    return c->pool ? cudaMallocFromPoolAsync(p, bytes, c->pool, s) : cudaMallocAsync(p, bytes, s);
+}
 
 template <class T>
 int dalloc(B200Carver *c, T **p, size_t n, bool zero)
 {
     *p = nullptr;
-    CU_TRY(cudaMallocAsync((void **) p, n * sizeof(T), c->stream));
+    CU_TRY(pool_alloc(c, (void **) p, n * sizeof(T), c->stream));
     if (zero) CU_TRY(cudaMemsetAsync(*p, 0, n * sizeof(T), c->stream));
     return B200C_OK;
 }
@@ -1551,22 +1583,7 @@ B200Carver *carver_new_common(int width, int height, int channels)
         return nullptr;
     }
     c->stream = c->lane->stream;
-    {
-        // keep freed blocks in the pool: the per-resize maps are reallocated at every inflate/flatten
-        static std::mutex mu;
-        static std::vector<int> tuned;
-        std::lock_guard<std::mutex> lk(mu);
-        bool done = false;
-        for (int d : tuned) done |= d == c->device;
-        if (!done) {
-            cudaMemPool_t pool;
-            if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) {
-                uint64_t thr = UINT64_MAX;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-            }
-            tuned.push_back(c->device);
-        }
-    }
+    c->pool = engine_pool(c->device);
     c->w = c->w0 = c->w_start = width;
     c->h = c->h0 = c->h_start = height;
     c->channels = channels;
@@ -1913,8 +1930,8 @@ int b200c_batch_build_maps(B200Carver **cs, int n, int depth)
         cs[i]->stream = L->stream;
         for (B200Carver *a : cs[i]->attached) a->stream = L->stream;
     }
-    if (cudaMallocAsync((void **) &L->tab_d, 2 * (size_t) n * sizeof(DevP), L->stream) != cudaSuccess ||
-        cudaMallocAsync((void **) &L->mtab_d, (size_t) n * sizeof(BdMaps), L->stream) != cudaSuccess)
+    if (pool_alloc(L, (void **) &L->tab_d, 2 * (size_t) n * sizeof(DevP), L->stream) != cudaSuccess ||
+        pool_alloc(L, (void **) &L->mtab_d, (size_t) n * sizeof(BdMaps), L->stream) != cudaSuccess)
         rc = fail(B200C_NOMEM, "batch_build_maps: table allocation", cudaGetLastError());
     if (rc == B200C_OK) {
         for_batch(L, [](B200Carver *m) { set_width_one(m, m->w_start - m->max_level + 1); });
