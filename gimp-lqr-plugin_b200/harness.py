@@ -56,18 +56,19 @@ def render(lib_path: str, layer: np.ndarray, vals: PlugInVals, pres=None, disc=N
         out = np.zeros(need, dtype=np.uint8)
     elif out.dtype != np.uint8 or not out.flags.c_contiguous or out.size < need:
         raise ValueError("out: contiguous uint8 buffer of at least %d bytes expected" % need)
-    vmap = np.zeros((h, w), dtype=np.int32)
+    # the seam-map sink is only written with output_seams (a zeroed layer-sized array costs milliseconds per call)
+    vmap = np.zeros((h, w), dtype=np.int32) if vals.output_seams else None
     res = HarnessResult()
     ptr = [None if m is None else m.ctypes.data for m in masks]
     ok = _load().harness_render(lib_path.encode(), layer.ctypes.data, C.byref(hv), ptr[0], ptr[1], ptr[2], out.ctypes.data,
-                                vmap.ctypes.data, C.byref(res))
+                                None if vmap is None else vmap.ctypes.data, C.byref(res))
     if not ok:
         raise RuntimeError("harness_render failed")
     img = out.reshape(-1)[: res.out_width * res.out_height * bpp].reshape(res.out_height, res.out_width, bpp)
     if own_out:
         img = img.copy()
     vm = vmap.reshape(-1)[: res.vmap_width * res.vmap_height].reshape(res.vmap_height, res.vmap_width).copy() \
-        if res.n_vmaps else None
+        if (res.n_vmaps and vmap is not None) else None
     return img, vm, res
 
 
