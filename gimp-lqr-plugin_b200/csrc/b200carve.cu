@@ -147,6 +147,7 @@ struct Lane {
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr; // blocking-sync event: see carver_sync()
     cudaEvent_t prog[4] = {nullptr, nullptr, nullptr, nullptr}; // progress points of a build session (build_vsmap)
+    cudaEvent_t rd[4] = {nullptr, nullptr, nullptr, nullptr};   // arrival of the chunks of a read-out (b200c_carver_readout)
     int *seams_h = nullptr;     // mapped pinned word: seams of the running session the device has completed
     std::map<int, LaneGraph> graphs; // per kernel set of the per-seam loop (graph_key)
 };
@@ -163,6 +164,8 @@ void lane_destroy(Lane *l)
         if (e) cudaEventDestroy(e);
     if (l->done) cudaEventDestroy(l->done);
     for (cudaEvent_t e : l->prog)
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : l->rd)
         if (e) cudaEventDestroy(e);
     if (l->seams_h) cudaFreeHost(l->seams_h);
     if (l->pooled && l->stream) cudaStreamDestroy(l->stream);
@@ -196,6 +199,7 @@ Lane *lane_acquire(int device, bool use_ext, cudaStream_t ext)
     for (int i = 0; i < 2 && ok; ++i) ok = cudaEventCreateWithFlags(&l->ev[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming | cudaEventBlockingSync) == cudaSuccess;
     for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&l->prog[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreateWithFlags(&l->rd[i], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaHostAlloc((void **) &l->seams_h, 64, cudaHostAllocMapped) == cudaSuccess;
     if (ok) *l->seams_h = 0;
     if (!ok) {
@@ -303,6 +307,7 @@ struct B200Carver {
     uint8_t *host_out = nullptr; // pinned read-out staging
     size_t host_out_cap = 0;
     cudaMemPool_t pool = nullptr; // the engine's own device memory pool (engine_pool), or NULL: the default pool
+    int rd_rows = 0, rd_chunks = 0, rd_ready = 0; // chunked read-out: rows per chunk, chunks, chunks known to have arrived
 };
 
 namespace {
@@ -1408,6 +1413,7 @@ void pinned_release(uint8_t *p, size_t cap)
 int ensure_host_out(B200Carver *c, size_t bytes)
 {
     if (bytes <= c->host_out_cap) return B200C_OK;
+    if (c->host_out) CU_TRY(carver_sync(c)); // chunks of an abandoned read-out may still be on their way into it
     pinned_release(c->host_out, c->host_out_cap);
     c->host_out = nullptr;
     c->host_out_cap = 0;
@@ -2004,21 +2010,62 @@ static int readout_to(B200Carver *c, uint8_t *d_out)
     return check_launch("k_compact_rows(readout)");
 }
 
-int b200c_carver_readout(B200Carver *c, const unsigned char **host_pixels)
+static int readout_impl(B200Carver *c, const unsigned char **host_pixels, bool chunked)
 {
     if (!c || !host_pixels) return fail(B200C_ERROR, "readout: NULL");
     HostScope hs(10);
     B_TRY(use_device(c));
-    const size_t bytes = (size_t) c->w * c->h * c->channels;
+    const size_t row_bytes = (size_t) c->w * c->channels, bytes = row_bytes * c->h;
     B_TRY(ensure_host_out(c, bytes));
     uint8_t *d_out = nullptr;
     B_TRY(dalloc(c, &d_out, bytes, false));
     B_TRY(readout_to(c, d_out));
-    CU_TRY(cudaMemcpyAsync(c->host_out, d_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    // Large images come back in up to four chunks of rows: the call returns when the FIRST has arrived, the caller's
+    // scan (b200c_carver_readout_rows) waits for the others as it reaches them, so the copy of the later rows overlaps
+    // the caller's handling of the earlier ones.  A crowded host (many carvers in flight) takes one copy and sleeps.
+    Lane *lane = c->lane ? c->lane : c->root->lane;
+    const int chunks = (chunked && bytes >= (4u << 20) && c->h >= 4 && !host_crowded()) ? 4 : 1;
+    c->rd_rows = (c->h + chunks - 1) / chunks;
+    c->rd_chunks = (c->h + c->rd_rows - 1) / c->rd_rows;
+    c->rd_ready = 0;
+    for (int i = 0; i < c->rd_chunks; ++i) {
+        const size_t off = (size_t) i * c->rd_rows * row_bytes;
+        const size_t n = (off + (size_t) c->rd_rows * row_bytes <= bytes) ? (size_t) c->rd_rows * row_bytes : bytes - off;
+        CU_TRY(cudaMemcpyAsync(c->host_out + off, d_out + off, n, cudaMemcpyDeviceToHost, c->stream));
+        if (c->rd_chunks > 1) CU_TRY(cudaEventRecord(lane->rd[i], c->stream));
+    }
     dfree(c, d_out);
-    CU_TRY(carver_sync(c));
+    if (c->rd_chunks > 1) {
+        CU_TRY(cudaEventSynchronize(lane->rd[0]));
+        c->rd_ready = 1;
+    } else {
+        CU_TRY(carver_sync(c));
+        c->rd_ready = c->rd_chunks;
+    }
     *host_pixels = c->host_out;
     return B200C_OK;
+}
+
+int b200c_carver_readout(B200Carver *c, const unsigned char **host_pixels) { return readout_impl(c, host_pixels, false); }
+int b200c_carver_readout_begin(B200Carver *c, const unsigned char **host_pixels) { return readout_impl(c, host_pixels, true); }
+
+// rows of the last read-out that have arrived in the host buffer, after waiting for the chunk that holds `row`
+int b200c_carver_readout_rows(B200Carver *c, int row)
+{
+    if (!c) return -1;
+    if (c->rd_ready < c->rd_chunks && row >= c->rd_ready * c->rd_rows) {
+        if (use_device(c) != B200C_OK) return -1;
+        Lane *lane = c->lane ? c->lane : c->root->lane;
+        while (c->rd_ready < c->rd_chunks && row >= c->rd_ready * c->rd_rows) {
+            if (cudaEventSynchronize(lane->rd[c->rd_ready]) != cudaSuccess) {
+                fail(B200C_ERROR, "readout_rows: event", cudaGetLastError());
+                return -1;
+            }
+            c->rd_ready++;
+        }
+    }
+    const int rows = c->rd_ready * c->rd_rows;
+    return rows < c->h ? rows : c->h;
 }
 
 int b200c_carver_readout_device(B200Carver *c, void *d_out)

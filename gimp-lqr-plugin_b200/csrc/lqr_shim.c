@@ -38,6 +38,7 @@ typedef struct {
     int (*transpose)(B200Carver *);
     int (*get)(const B200Carver *, int);
     int (*readout)(B200Carver *, const unsigned char **);
+    int (*readout_rows)(B200Carver *, int);
     int (*vmap)(B200Carver *, int *);
     int (*true_energy)(B200Carver *, float *);
 } Engine;
@@ -95,7 +96,8 @@ static int engine_load_once(void)
     BIND(flatten, "b200c_carver_flatten");
     BIND(transpose, "b200c_carver_transpose");
     BIND(get, "b200c_carver_get");
-    BIND(readout, "b200c_carver_readout");
+    BIND(readout, "b200c_carver_readout_begin");
+    BIND(readout_rows, "b200c_carver_readout_rows");
     BIND(vmap, "b200c_carver_vmap");
     BIND(true_energy, "b200c_carver_true_energy");
     if (g_eng.abi_version() != B200C_ABI_VERSION) {
@@ -156,6 +158,7 @@ struct _LqrCarver {
     const guchar *lines; /* engine-owned pinned buffer, NULL when stale */
     gint line_w, line_h;  /* internal geometry of `lines` */
     gint cur_line, cur_x;
+    gint lines_ready;     /* rows of `lines` that have arrived (the read-out comes back in chunks) */
     guchar pixel[4];
 };
 
@@ -647,6 +650,20 @@ static gboolean fetch_lines(LqrCarver *r)
     r->line_h = EG(r, B200C_H);
     r->cur_line = 0;
     r->cur_x = 0;
+    r->lines_ready = 0;
+    return TRUE;
+}
+
+/* the row the cursor is on has arrived in the host buffer (waits for its chunk if it has not) */
+static gboolean line_ready(LqrCarver *r, gint line)
+{
+    if (line < r->lines_ready) return TRUE;
+    r->lines_ready = g_eng.readout_rows(r->eng, line);
+    if (r->lines_ready <= line) {
+        fprintf(stderr, "liblqr-1 (b200): read-out failed: %s\n", g_eng.last_error());
+        r->lines = NULL;
+        return FALSE;
+    }
     return TRUE;
 }
 
@@ -666,6 +683,7 @@ gboolean lqr_carver_scan_line(LqrCarver *r, gint *n, guchar **rgb)
         lqr_carver_scan_reset(r);
         return FALSE;
     }
+    if (!line_ready(r, r->cur_line)) return FALSE;
     *n = r->cur_line;
     *rgb = (guchar *) (r->lines + (size_t) r->cur_line * r->line_w * r->channels);
     r->cur_line++;
@@ -682,6 +700,7 @@ gboolean lqr_carver_scan(LqrCarver *r, gint *x, gint *y, guchar **rgb)
         lqr_carver_scan_reset(r);
         return FALSE;
     }
+    if (!line_ready(r, r->cur_line)) return FALSE;
     transposed = EG(r, B200C_TRANSPOSED);
     *x = transposed ? r->cur_line : r->cur_x;
     *y = transposed ? r->cur_x : r->cur_line;

@@ -26,7 +26,7 @@ extern "C" {
 #define B200C_API
 #endif
 
-#define B200C_ABI_VERSION 1
+#define B200C_ABI_VERSION 2
 #define B200C_ERROR 0
 #define B200C_OK 1
 #define B200C_NOMEM 2
@@ -97,6 +97,12 @@ B200C_API int b200c_carver_get(const B200Carver *c, int field);
  * engine-owned pinned host buffer of w*h*channels bytes laid out by internal rows (image rows, or image
  * columns when transposed) and returns it; valid until the next call that changes the carver. */
 B200C_API int b200c_carver_readout(B200Carver *c, const unsigned char **host_pixels);
+/* the same, for a caller that consumes the rows in order (the shim's scan cursor): large images come back in chunks of
+ * rows and the call returns when the first chunk has arrived; b200c_carver_readout_rows(c, row) waits for the chunk
+ * that holds internal row `row` and returns how many rows are in the buffer by then (< 0: error), so the copy of the
+ * later rows overlaps the caller's handling of the earlier ones (write_carver_to_layer, io_functions.c:155-164). */
+B200C_API int b200c_carver_readout_begin(B200Carver *c, const unsigned char **host_pixels);
+B200C_API int b200c_carver_readout_rows(B200Carver *c, int row);
 /* same gather, left in HBM: d_out must hold w*h*channels bytes (bench.py `value` leg) */
 B200C_API int b200c_carver_readout_device(B200Carver *c, void *d_out);
 /* lqr_vmap_dump (render.c:725; io_functions.c:216-219; A.13): out = width*height ints in image orientation */

@@ -39,7 +39,7 @@ def test_engine_header_symbols_exported(pkg):
     missing = [n for n in names if not hasattr(eng, n)]
     assert not missing, f"libb200carve.so lacks {missing}"
     eng.b200c_abi_version.restype = ctypes.c_int
-    assert eng.b200c_abi_version() == 1
+    assert eng.b200c_abi_version() == 2
 
 
 def test_enum_values_match_the_pdb_contract():
