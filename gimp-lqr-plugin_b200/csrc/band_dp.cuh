@@ -72,11 +72,21 @@ struct BdSlot {
 };
 
 struct BdDesc {
-    int y0, rows, llo, nb, elo, ehi, nseg, slot0;
+    int seq;      // the chunk this entry describes, written LAST -- when its tiles have landed ("ready"): a compute warp
+                  // reads the entry's first 16 bytes, and the rest once seq is the chunk it is about to start
+    int y0, rows, llo;
+    int nb, elo, ehi, nseg;
+    int slot0;
     int ropen;    // the fetched columns reach the +inf sentinels right of the image: the right edge does not go stale
     int hlo, hhi; // columns [hlo, hhi) are handed over to the next chunk (the union of the interiors)
-    int pad;
 };
+static_assert(sizeof(BdDesc) == 48, "BdDesc is read as three 16-byte vectors");
+__device__ __forceinline__ int4 bd_lds_volatile4(const void *p)
+{
+    int4 v;
+    asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((unsigned) __cvta_generic_to_shared(p)) : "memory");
+    return v;
+}
 
 static constexpr size_t bd_smem_bytes()
 {
@@ -242,6 +252,9 @@ __device__ __forceinline__ void bd_slow_row(BdSlow &c)
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? c.rigmap[j - D] : 0.f;
     const unsigned pwo = *reinterpret_cast<const unsigned *>(c.pold);
     const float4 ce = *reinterpret_cast<const float4 *>(c.e), co = *reinterpret_cast<const float4 *>(c.o);
+    // the next row's operands, fetched now: the redo below does not wait for them (rows past the chunk: the next box)
+    const float4 ne = *reinterpret_cast<const float4 *>(c.e + BD_BW), no = *reinterpret_cast<const float4 *>(c.o + BD_BW);
+    const float4 ng = RIG ? *reinterpret_cast<const float4 *>(c.g + BD_BW) : make_float4(1.f, 1.f, 1.f, 1.f);
     const float4 cg = RIG ? *reinterpret_cast<const float4 *>(c.g) : make_float4(1.f, 1.f, 1.f, 1.f);
     const float4 pv = *reinterpret_cast<const float4 *>(c.par);
     const float prev[4] = {pv.x, pv.y, pv.z, pv.w};
@@ -269,9 +282,7 @@ __device__ __forceinline__ void bd_slow_row(BdSlow &c)
     *reinterpret_cast<float4 *>(c.dst) = make_float4(out[0], out[1], out[2], out[3]);
     if (c.has_next) {
         float nv[4];
-        c.key = bd_eval<D, RIG>(out, *reinterpret_cast<const float4 *>(c.e + BD_BW), *reinterpret_cast<const float4 *>(c.o + BD_BW),
-                                RIG ? *reinterpret_cast<const float4 *>(c.g + BD_BW) : make_float4(1.f, 1.f, 1.f, 1.f), rmap,
-                                c.leftfloor, nv);
+        c.key = bd_eval<D, RIG>(out, ne, no, ng, rmap, c.leftfloor, nv);
 #pragma unroll
         for (int i = 0; i < 4; ++i) c.nv[i] = nv[i];
     }
@@ -306,11 +317,17 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
     for (int k = 0;; ++k) {
         long long tp0 = 0;
         if (BD_PROF && p.dbg) tp0 = clock64(), t_gap += tp0 - t_prev;
-        if (*ready < k) { // normally false: see the producer
-            while (*ready < k) {}
-            __threadfence_block();
+        BdDesc d;
+        {
+            const BdDesc *dq = desc + (k % BD_NRING);
+            int4 v0 = bd_lds_volatile4(dq);
+            while (v0.x != k) v0 = bd_lds_volatile4(dq); // normally true at once: see the producer
+            const int4 v1 = bd_lds_volatile4(reinterpret_cast<const int4 *>(dq) + 1);
+            const int4 v2 = bd_lds_volatile4(reinterpret_cast<const int4 *>(dq) + 2);
+            d.seq = v0.x, d.y0 = v0.y, d.rows = v0.z, d.llo = v0.w;
+            d.nb = v1.x, d.elo = v1.y, d.ehi = v1.z, d.nseg = v1.w;
+            d.slot0 = v2.x, d.ropen = v2.y, d.hlo = v2.z, d.hhi = v2.w;
         }
-        const BdDesc d = desc[k % BD_NRING];
         if (d.rows == 0) break;
         int *hull_k = hull + (k & 1) * (2 * BD_NCW);
         if (seg < d.nseg) {
@@ -429,10 +446,13 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                     for (; r < rows; ++r)
                         if (fast_row(ep + (r + 1) * BD_BW, op + (r + 1) * BD_BW, gq + (r + 1) * BD_BW, (r - 1 - r0) & 3)) { hit = true; break; }
                 if (!hit) break;
+                // operands of the row after the redone one: fetched before the slow path, which does not touch them
+                const float4 ce_n = ld4(ep + (r + 1) * BD_BW), co_n = ld4(op + (r + 1) * BD_BW);
+                const float4 cg_n = RIG ? ld4(gq + (r + 1) * BD_BW) : one4;
                 slow(r - 1, true); // row r-1 settled (and stored), row r redone from it; it is stored once confirmed
                 pend = key <= BD_NEAR_MAX;
                 r0 = ++r;
-                ce = ld4(ep + r * BD_BW), co = ld4(op + r * BD_BW), cg = RIG ? ld4(gq + r * BD_BW) : one4;
+                ce = ce_n, co = co_n, cg = cg_n;
             }
             if (__any_sync(full, pend)) slow(rows - 1, false); // the last row of the chunk is still open
             else if (st) *reinterpret_cast<float4 *>(op + (rows - 1) * BD_BW) = make_float4(mp[0], mp[1], mp[2], mp[3]);
@@ -640,7 +660,10 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
     auto publish_ready = [&](int kk) {
         if (!bd_mbar_wait(&mbar[kk % BD_NRING], (unsigned) ((kk / BD_NRING) & 1))) atomicOr(p.err, 4);
         __threadfence_block();
-        if (lane == 0) misc[4] = kk;
+        if (lane == 0) {
+            *reinterpret_cast<volatile int *>(&desc[kk % BD_NRING].seq) = kk;
+            misc[4] = kk;
+        }
         __syncwarp();
     };
     int ready = -1;
@@ -880,6 +903,7 @@ __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin0, cons
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int y = tid; y < p.h; y += BD_THREADS) nrg[y] = p.nrg_pack[y];
+    if (tid < BD_NRING) desc[tid].seq = -1;
     if (tid == 0) {
         for (int i = 0; i < BD_NRING; ++i) bd_mbar_init(&mbar[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
