@@ -936,7 +936,7 @@ int seam_launch_list(const B200Carver *c, bool with_update, SeamLaunch out[kSeam
         if (c->use_tail) // the rows the band kernel could not tile (none, most of the time: the kernel returns at once)
             out[n++] = {"mmap_tail", band_tail_fn(c), dim3(bt_grid(c->w_epoch, c->delta_x)), dim3(BT_THREADS),
                         bt_smem_bytes(c->delta_x > 4 ? 4 : c->delta_x, c->rigidity != 0.f), 0, true};
-        out[n++] = {"fix_parents", band_dp_fn(c, true), dim3((c->h + 7) / 8), dim3(256), 0, 0, false};
+        out[n++] = {"fix_parents", band_dp_fn(c, true), dim3((c->h + 7) / 8, c->mates.empty() ? 4 : 1), dim3(256), 0, 0, false};
     } else {
         out[n++] = {"mmap_update", (const void *) k_mmap_update, dim3(1), dim3(512), 0, 0, false};
     }

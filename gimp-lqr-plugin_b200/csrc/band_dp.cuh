@@ -756,7 +756,8 @@ __global__ void __launch_bounds__(256) k_fix_parents(const DevP pin0, const DevP
     float rmap[2 * D + 1];
 #pragma unroll
     for (int j = 0; j <= 2 * D; ++j) rmap[j] = RIG ? p.rigmap[j - D] : 0.f;
-    for (int t = threadIdx.x; t < rows * nq; t += blockDim.x) {
+    // gridDim.y CTAs share a chunk: the kernel is a few dependent trips to L2 per thread, not bandwidth
+    for (int t = blockIdx.y * blockDim.x + threadIdx.x; t < rows * nq; t += blockDim.x * gridDim.y) {
         const int r = t / nq, x0 = elo + 4 * (t - r * nq), y = y0 + r;
         if (y == 0) continue;
         const float *up = p.m + (size_t) (y - 1) * p.pitch;

@@ -99,24 +99,29 @@ __device__ __forceinline__ bool st_mbar_wait(void *mbar, unsigned parity)
 __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, const DevP *tab)
 {
     const DevP pin = pick_image(pin0, tab);
-    const DevP p = seam_view_next(pin);
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ float s_v[ST_THREADS / 32];
     __shared__ int s_x[ST_THREADS / 32];
-    const int D = max(p.delta_x, 1), R = st_rows(p.delta_x), q = R >> 2, reach = R * D;
+    const int D = max(pin.delta_x, 1), R = st_rows(pin.delta_x), q = R >> 2, reach = R * D;
     const int b = blockIdx.y, c0 = blockIdx.x * ST_COLS, tid = threadIdx.x;
-    if (c0 >= p.w) return;
-    const int nblk = st_nblk(p.h, p.delta_x);
-    const int ybot = p.h - 1 - b * R, ytop = max(ybot - R + 1, 1), rows = ybot - ytop + 1;
-    const int tlo = max(c0 - reach, 0) & ~15;                         // first staged column (16-byte aligned)
-    const int thi = min((c0 + ST_COLS + reach + 15) & ~15, p.pitch);  // one past the last
-    const int tw = thi - tlo, pieces = tw >> 4;
+    const int nblk = st_nblk(pin.h, pin.delta_x);
+    const int ybot = pin.h - 1 - b * R, ytop = max(ybot - R + 1, 1), rows = ybot - ytop + 1;
+    const int tlo = max(c0 - reach, 0) & ~15;                           // first staged column (16-byte aligned)
+    const int thi = min((c0 + ST_COLS + reach + 15) & ~15, pin.pitch);  // one past the last
+    const int tw = thi - tlo, pieces = max(tw, 0) >> 4;
     // the tile sits ST_PAD bytes into the buffer: a walk that meets a dead parent (offset -128) goes on from a column that
     // does not matter, possibly left of the tile, before it is flagged
     unsigned char *tile = st_smem + ST_PAD;
+    // the copies are issued before the current width is known (it takes a trip to the seam counter in HBM): the tile
+    // only depends on the pitch
     for (int r = tid >> 5; r < rows; r += ST_THREADS / 32) { // a warp per row: no index arithmetic per piece
-        const signed char *src = p.pdx + (size_t) (ybot - r) * p.pitch + tlo;
+        const signed char *src = pin.pdx + (size_t) (ybot - r) * pin.pitch + tlo;
         for (int c = tid & 31; c < pieces; c += 32) st_cp16(tile + (size_t) r * tw + (c << 4), src + (c << 4));
+    }
+    const DevP p = seam_view_next(pin);
+    if (c0 >= p.w) { // (uniform over the CTA) nothing to do here any more: the image has shrunk past this chunk
+        st_cp_wait();
+        return;
     }
     const int x = c0 + tid;
     // the bottom block's CTAs: arg-min of their columns of the last row (the rule of last_row_argmin)
