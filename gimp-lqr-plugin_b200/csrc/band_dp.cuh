@@ -150,7 +150,13 @@ __device__ __forceinline__ void bd_tma_store_2d(const CUtensorMap *tm, int c0, i
                  "r"(c0), "r"(c1), "r"(bd_saddr(src_smem))
                  : "memory");
 }
-__device__ __forceinline__ void bd_bar_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory"); }
+// (the unaligned form: a warp whose lanes left a spin loop one by one need not have reconverged -- compute-sanitizer's
+// synccheck flags the aligned `bar.sync` in the producer)
+__device__ __forceinline__ void bd_bar_chunk()
+{
+    __syncwarp();
+    asm volatile("barrier.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory");
+}
 
 // ------------------------------------------------------------------------------------------- compute warps
 // Everything a single warp issues per row is on the critical path of the whole update, so the row body carries only
@@ -424,7 +430,12 @@ __device__ __forceinline__ void bd_compute(const DevP &p, unsigned char *ring, f
                 pend = false; // timing experiment only: never leave the fast loop (results are wrong)
 #endif
                 if (__any_sync(full, pend)) return true;
-                // row r-1 is confirmed: o_next is row r+1 of the tile
+                // row r-1 is confirmed: o_next is row r+1 of the tile.
+                // The neighbouring segment's halo lanes read these very cells as THEIR "old value" of the row, possibly
+                // after this store (compute-sanitizer's racecheck reports the pair): harmless, because the rule is
+                // idempotent -- a cell that kept its old value reads back the old value; a cell that took the new
+                // value nm reads back nm, finds d = 0 and takes its own, identical, nm.  Each 4-byte word is one or the
+                // other, never torn.
                 float *dst = st ? const_cast<float *>(o_next) - 2 * BD_BW : vr + slot_prev * 128;
                 *reinterpret_cast<float4 *>(dst) = make_float4(mp[0], mp[1], mp[2], mp[3]);
 #pragma unroll

@@ -137,6 +137,9 @@ __global__ void k_mmap_full_cluster(const DevP p0, int nwarps, const DevP *tab)
 
     float mp[4] = {inf, inf, inf, inf};
     int parity = 0;
+    // distributed shared memory may only be written once its CTA is known to run: every CTA of the cluster passes here
+    // before the first exchange
+    mc_cluster_sync();
     if constexpr (!RIG) {
         // the energy rows are fetched a BATCH (16 rows, 8 for delta_x >= 3) ahead: two buffers per warp
         constexpr int FB = mc_batch(D);

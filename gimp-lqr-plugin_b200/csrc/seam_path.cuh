@@ -41,7 +41,11 @@ __device__ __forceinline__ void sp_cp_async16(void *dst_smem, const void *src)
 __device__ __forceinline__ void sp_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void sp_cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void sp_cp_async_wait_but1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void sp_bar_helpers() { asm volatile("bar.sync 1, %0;" ::"n"(SP_THREADS - 32) : "memory"); }
+__device__ __forceinline__ void sp_bar_helpers()
+{
+    __syncwarp();
+    asm volatile("barrier.sync 1, %0;" ::"n"(SP_THREADS - 32) : "memory");
+}
 
 // stage rows [y_top, y_bot] (y_bot >= y_top), columns [wlo, wlo + tw) of pdx into `tile` (row r = y_bot - y, pitch tw);
 // the work is spread over threads first .. SP_THREADS-1
