@@ -150,9 +150,10 @@ __device__ __forceinline__ void bd_tma_store_2d(const CUtensorMap *tm, int c0, i
                  "r"(c0), "r"(c1), "r"(bd_saddr(src_smem))
                  : "memory");
 }
-// (the unaligned form: a warp whose lanes left a spin loop one by one need not have reconverged -- compute-sanitizer's
-// synccheck flags the aligned `bar.sync` in the producer)
-__device__ __forceinline__ void bd_bar_chunk()
+// the compute warps arrive converged (aligned form); the producer's lanes leave spin loops one by one and need not have
+// reconverged (compute-sanitizer's synccheck flags the aligned form there): it takes the unaligned form
+__device__ __forceinline__ void bd_bar_chunk() { asm volatile("bar.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory"); }
+__device__ __forceinline__ void bd_bar_chunk_producer()
 {
     __syncwarp();
     asm volatile("barrier.sync 1, %0;" ::"n"(BD_SYNC_THREADS) : "memory");
@@ -682,7 +683,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
     while (!ended && kp <= BD_LA)
         if (!plan_issue()) break;
     publish_ready(0), ready = 0;
-    bd_bar_chunk();
+    bd_bar_chunk_producer();
     long long t_tiles = 0, t_pbar = 0, t_pstore = 0;
     for (int k = 0;; ++k) {
         // a chunk that did not fit before the last barrier is planned now that its predecessor's slots are free: the
@@ -707,7 +708,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
             if (BD_PROF && p.dbg) t_tiles += clock64() - tw0;
         }
         const long long tb0 = (BD_PROF && p.dbg) ? clock64() : 0;
-        bd_bar_chunk(); // end of chunk k: the hull of its last row is known, its new values are in the tiles
+        bd_bar_chunk_producer(); // end of chunk k: the hull of its last row is known, its new values are in the tiles
         if (BD_PROF && p.dbg) { // the barrier instruction does not hold back a clock read: read the clock after a load
             const int probe = *reinterpret_cast<const volatile int *>(hull);
             long long tb1 = clock64();
