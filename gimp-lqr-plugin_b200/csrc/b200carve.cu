@@ -274,6 +274,7 @@ struct B200Carver {
     bool graph_fresh[2] = {false, false};     // the lane's graph for this leftright value points at this session
     LaneGraph *graph[2] = {nullptr, nullptr};
     bool use_graph = true;                    // B200C_GRAPH=0: launch the kernels one by one
+    bool use_pdl = false;                     // B200C_PDL=1: programmatic dependent launch between the nodes of the seam graph
     int4 *fix_d = nullptr;                    // band-DP chunk table for k_fix_parents (+ its count)
     int *fixn_d = nullptr;
     int *tail_d = nullptr;                    // band DP -> tail kernel hand-over (DevP::tail)
@@ -999,15 +1000,18 @@ int graph_key(const B200Carver *c)
 {
     const bool fast = fast_path(c), band = fast && c->delta_x <= 4 && c->h <= BD_HMAX;
     return (fast ? 1 : 0) | (band ? 2 : 0) | ((c->leftright & 1) << 2) | (c->rigidity != 0.f ? 8 : 0) | (c->delta_x << 4) |
-           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0) | (c->mates.empty() ? 0 : 1 << 14) | (split_carve(c) ? 1 << 15 : 0);
+           (c->use_tail ? 1 << 12 : 0) | (c->use_trace ? 1 << 13 : 0) | (c->mates.empty() ? 0 : 1 << 14) | (split_carve(c) ? 1 << 15 : 0) | (c->use_pdl ? 1 << 16 : 0);
 }
 
 // Points the lane's graph for the current kernel set at this carver's session: the first time the nodes are added and
 // the graph instantiated, later only the node parameters of the executable change.  (Stream capture is not used: with
 // other host threads waiting on their own streams, cudaStreamBeginCapture was measured to block for tens of ms.)
-int seam_graph_prepare(B200Carver *c, LaneGraph **out)
+// pdl: the edge between two ordinary kernel nodes is a PROGRAMMATIC one -- the dependent grid is launched as soon as every
+// CTA of its predecessor has started (each per-seam kernel begins with griddepcontrol.launch_dependents) and its CTAs wait
+// in griddepcontrol.wait until the predecessor has completed and flushed: the launch latency of the dependent kernel
+// disappears from the chain.  Edges that touch the cooperative tail kernel stay ordinary.
+static int seam_graph_build(B200Carver *c, LaneGraph &g, bool pdl)
 {
-    LaneGraph &g = c->lane->graphs[graph_key(c)];
     SeamLaunch L[kSeamLaunchMax];
     const int n = seam_launch_list(c, true, L);
     SeamArgs a = seam_args(c);
@@ -1023,11 +1027,20 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
         kp.sharedMemBytes = (unsigned) L[i].smem;
         kp.kernelParams = a.of(c, L[i]);
         if (fresh) {
-            e = cudaGraphAddKernelNode(&g.node[i], g.graph, i ? &g.node[L[i].dep >= 0 ? L[i].dep : i - 1] : nullptr, i ? 1 : 0, &kp);
+            const int dep = i ? (L[i].dep >= 0 ? L[i].dep : i - 1) : -1;
+            const bool prog = pdl && dep >= 0 && !L[i].coop && !L[dep].coop;
+            e = cudaGraphAddKernelNode(&g.node[i], g.graph, (dep >= 0 && !prog) ? &g.node[dep] : nullptr, (dep >= 0 && !prog) ? 1 : 0, &kp);
             if (e == cudaSuccess && L[i].coop) {
                 cudaKernelNodeAttrValue v = {};
                 v.cooperative = 1;
                 e = cudaGraphKernelNodeSetAttribute(g.node[i], cudaKernelNodeAttributeCooperative, &v);
+            }
+            if (e == cudaSuccess && prog) {
+                cudaGraphEdgeData ed = {};
+                ed.from_port = cudaGraphKernelNodePortProgrammatic;
+                ed.to_port = 0;
+                ed.type = cudaGraphDependencyTypeProgrammatic;
+                e = cudaGraphAddDependencies_v2(g.graph, &g.node[dep], &g.node[i], &ed, 1);
             }
         } else
             e = cudaGraphExecKernelNodeSetParams(g.exec, g.node[i], &kp);
@@ -1039,8 +1052,25 @@ int seam_graph_prepare(B200Carver *c, LaneGraph **out)
     }
     g.n = n;
     g_launches += n;
-    *out = &g;
     return B200C_OK;
+}
+
+int seam_graph_prepare(B200Carver *c, LaneGraph **out)
+{
+    LaneGraph &g = c->lane->graphs[graph_key(c)];
+    const bool pdl = c->use_pdl && c->mates.empty();
+    int rc = seam_graph_build(c, g, pdl);
+    if (rc != B200C_OK && pdl) { // no programmatic edges on this driver / for this kernel set: ordinary ones
+        cudaGetLastError();
+        c->use_pdl = false;
+        rc = seam_graph_build(c, c->lane->graphs[graph_key(c)], false);
+        if (rc == B200C_OK) {
+            *out = &c->lane->graphs[graph_key(c)];
+            return rc;
+        }
+    }
+    if (rc == B200C_OK) *out = &g;
+    return rc;
 }
 
 int seam_iteration(B200Carver *c, int l, int lr_switch_interval)
@@ -1570,6 +1600,8 @@ B200Carver *carver_new_common(int width, int height, int channels)
         c->generic = g && atoi(g) != 0;
         const char *gr = getenv("B200C_GRAPH");
         if (gr) c->use_graph = atoi(gr) != 0;
+        const char *pd = getenv("B200C_PDL");
+        if (pd) c->use_pdl = atoi(pd) != 0;
         const char *tl = getenv("B200C_TAIL");
         if (tl) c->use_tail = atoi(tl) != 0;
         const char *sp = getenv("B200C_SPLIT");

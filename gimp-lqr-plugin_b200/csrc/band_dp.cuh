@@ -758,6 +758,7 @@ __device__ __forceinline__ void bd_producer(const DevP &p, const BdMaps &tm, uns
 template <int D, bool RIG, bool LR>
 __global__ void __launch_bounds__(256) k_fix_parents(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     if ((int) blockIdx.x >= *p.fixn) return;
@@ -899,6 +900,7 @@ template <int D, bool RIG, bool LR>
 __global__ void __launch_bounds__(BD_THREADS, 1) k_band_dp(const DevP pin0, const __grid_constant__ BdMaps tm0, const DevP *tab,
                                                            const BdMaps *mtab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     const BdMaps &tm = mtab ? mtab[blockIdx.z] : tm0; // tensor maps of this image: kernel parameter, or table in HBM
     int seam;

@@ -39,6 +39,7 @@ __device__ __forceinline__ void bt_cp_async(void *dst_smem, const void *src, int
 template <int D, bool RIG, bool LR>
 __global__ void __launch_bounds__(BT_THREADS) k_band_tail(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     const int y_from = *reinterpret_cast<volatile int *>(p.tail);

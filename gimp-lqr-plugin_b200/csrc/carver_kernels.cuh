@@ -77,6 +77,15 @@ __device__ __forceinline__ DevP pick_image(const DevP &p0, const DevP *tab) { re
 // first thing of every iteration (one thread of the backtrack kernel): the seam counter moves on; every kernel of the
 // previous iterations has finished by now (queue order), so the counter's value IS the number of completed seams --
 // published to the host for the progress callbacks
+// Programmatic dependent launch (the seam graph with B200C_PDL=1): first thing in every kernel of the per-seam loop --
+// let the NEXT kernel of the chain be launched (its CTAs then wait here, resident), and wait until the PREVIOUS kernel
+// has completed and its writes are visible.  Both are no-ops in an ordinary launch.
+__device__ __forceinline__ void pdl_entry()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ void advance_seam(const DevP &p)
 {
     const int i = ++*p.dyn;
@@ -290,6 +299,7 @@ __global__ void __launch_bounds__(256) k_energy_full(const DevP p0, const DevP *
 #define B200C_EB_ROWS 32 // rows per CTA of 256 threads
 __global__ void __launch_bounds__(256) k_energy_band(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     __shared__ double t255[256]; // v / 255.0, each quotient divided once per CTA (a cell reads 5 pixels x 4 channels)
@@ -389,6 +399,7 @@ __device__ void update_rows_generic(const DevP &p, int y_from, int lo, int hi, i
 
 __global__ void __launch_bounds__(512) k_mmap_update(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     const DevP p = seam_view(pin, 1);
     __shared__ int s_red[64];
@@ -444,6 +455,7 @@ __device__ __forceinline__ int last_row_argmin(const DevP &p, float *s_v, int *s
 
 __global__ void __launch_bounds__(1024) k_vpath(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     __shared__ float s_v[32];
     __shared__ int s_x[32];
@@ -480,6 +492,7 @@ __global__ void __launch_bounds__(1024) k_vpath(const DevP pin0, const DevP *tab
 #define B200C_CARVE_SPAN (B200C_CARVE_THREADS * B200C_CARVE_ITEMS)
 __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve(const DevP pin0, int vs_value, int phase, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     int seam;
     const DevP p = seam_view(pin, 1, &seam);
@@ -564,6 +577,7 @@ __device__ __forceinline__ void cv_bulk(void *dst_smem, const void *src, unsigne
 
 __global__ void __launch_bounds__(B200C_CARVE_THREADS) k_carve_row(const DevP pin0, int vs_value, int /*phase*/, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     int seam;
     const DevP p = seam_view(pin, 1, &seam);

@@ -103,6 +103,7 @@ __device__ __forceinline__ void sp_build_jumps(const signed char *tile, short *j
 
 __global__ void __launch_bounds__(SP_THREADS, 1) k_seam_path(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     if (pin.dyn && threadIdx.x == 0) advance_seam(pin); // this iteration's seam
     __syncthreads();

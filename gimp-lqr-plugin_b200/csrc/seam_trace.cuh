@@ -98,6 +98,7 @@ __device__ __forceinline__ bool st_mbar_wait(void *mbar, unsigned parity)
 
 __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     extern __shared__ __align__(16) unsigned char st_smem[];
     __shared__ float s_v[ST_THREADS / 32];
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(ST_THREADS) k_seam_jumps(const DevP pin0, cons
 
 __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP pin0, const DevP *tab)
 {
+    pdl_entry();
     const DevP pin = pick_image(pin0, tab);
     long long t_mark = clock64();
     (void) t_mark;
