@@ -336,26 +336,26 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
 
     // ---- the entry columns of the sub-blocks: one thread per block, three dependent loads through J8
     const int wmax = max(p.w - 1, 0);
-    if (tid < nblk) {
-        const signed char *J8 = st_j8(p, nblk) + (size_t) (4 * tid) * p.pitch;
-        int e = min(max(ent[tid], 0), wmax);
-        sub[4 * tid] = e;
+    for (int b = tid; b < nblk; b += ST_CHASE_THREADS) {
+        const signed char *J8 = st_j8(p, nblk) + (size_t) (4 * b) * p.pitch;
+        int e = min(max(ent[b], 0), wmax);
+        sub[4 * b] = e;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int v = __ldcg(J8 + (size_t) j * p.pitch + e);
             if (v == ST_BAD) s_bad = 1;
             e = min(max(e + (v == ST_BAD ? 0 : v), 0), wmax);
-            sub[4 * tid + j + 1] = e;
+            sub[4 * b + j + 1] = e;
         }
     }
     __syncthreads();
     ST_MARK(4);
     // ---- the rows: one thread per sub-block follows the parents themselves and writes the seam
-    if (tid < 4 * nblk) {
-        const int b = tid >> 2, j = tid & 3;
+    for (int t = tid; t < 4 * nblk; t += ST_CHASE_THREADS) { // (more than 1024 sub-blocks: delta_x 4 and over 7168 rows)
+        const int b = t >> 2, j = t & 3;
         const int ybot = p.h - 1 - b * R, ytop = max(ybot - R + 1, 1);
         const int yhi = ybot - j * q, ylo = max(yhi - q + 1, ytop);
-        int x = sub[tid];
+        int x = sub[t];
         bool bad = false;
         for (int y = yhi; y >= ylo; --y) {
             p.vpath_x[y] = x;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(ST_CHASE_THREADS, 1) k_seam_chase(const DevP p
             bad |= d == B200C_PDX_NONE;
             x = min(max(x + (d == B200C_PDX_NONE ? 0 : d), 0), wmax); // a live parent is at most delta_x columns away
         }
-        if (bad || x != (j == 3 ? ent[b + 1] : sub[tid + 1])) s_bad = 1;
+        if (bad || x != (j == 3 ? ent[b + 1] : sub[t + 1])) s_bad = 1;
     }
     if (tid == 0) p.vpath_x[0] = ent[nblk];
     __syncthreads();

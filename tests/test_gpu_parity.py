@@ -193,6 +193,15 @@ def test_very_wide_rows_fall_back(product, oracle, w, h, seams):
     _assert_same(render.render_noninteractive(product, img, vals), render.render_noninteractive(oracle, img, vals))
 
 
+def test_very_tall_delta4_backtrack(product, oracle):
+    """delta_x 4 cuts the backtrack into blocks of 28 rows: over 7168 rows there are more sub-blocks (4 per block) than
+    the chase kernel has threads."""
+    w, h, seams = 72, 7400, 3
+    img = synth.smooth_noise(w, h, 4)
+    vals = V(new_width=w - seams, new_height=h, delta_x=4, output_seams=True)
+    _assert_same(render.render_noninteractive(product, img, vals), render.render_noninteractive(oracle, img, vals))
+
+
 def _assert_same(got, want):
     diffs = cases.results_equal(got, want)
     assert not diffs, "; ".join(diffs)
